@@ -1,0 +1,250 @@
+"""Shared test infrastructure: ctypes loaders for the two CPU checkers and a seeded input generator.
+
+TEST INFRASTRUCTURE ONLY.  `oracle/libbb_oracle.so` is the plain-C restatement, `oracle/_ref/libbb_ref.so`
+is the unmodified reference compiled by oracle/Makefile (present in the build container and, as a
+prebuilt file, on the GPU box).  Field elements are numpy uint64 arrays of shape (..., 4).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libbb_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libbb_ref.so")
+
+FQ, FR = 0, 1
+FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+FQ_MODULUS = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+MODULUS = {FQ: FQ_MODULUS, FR: FR_MODULUS}
+R_MONT = 1 << 256
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+
+def ptr(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+def ptr32(a):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u32p)
+
+
+def build_oracle():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "bb_oracle.c")):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        lib = C.CDLL(ORACLE_SO)
+        lib.orc_domain_new.restype = C.c_void_p
+        lib.orc_domain_new.argtypes = [C.c_size_t]
+        lib.orc_domain_free.argtypes = [C.c_void_p]
+        lib.orc_domain_constant.argtypes = [C.c_void_p, C.c_int, u64p]
+        lib.orc_ntt.argtypes = [C.c_void_p, C.c_int, u64p, u64p]
+        lib.orc_pippenger.argtypes = [u64p, u64p, C.c_size_t, C.c_size_t, u64p]
+        lib.orc_msm_normalized.argtypes = [u64p, u64p, C.c_size_t, u64p]
+        lib.orc_generate_pippenger_point_table.argtypes = [u64p, u64p, C.c_size_t]
+        lib.orc_get_optimal_bucket_width.restype = C.c_size_t
+        lib.orc_get_optimal_bucket_width.argtypes = [C.c_size_t]
+        lib.orc_fixed_wnaf.argtypes = [u64p, u32p, C.c_size_t, C.c_size_t]
+        lib.orc_mul_n.argtypes = [C.c_int, u64p, u64p, u64p, C.c_size_t]
+        lib.orc_pow_small.argtypes = [C.c_int, u64p, C.c_uint64, u64p]
+        lib.orc_g1_batch_normalize.argtypes = [u64p, C.c_size_t]
+        lib.orc_poly_evaluate.argtypes = [u64p, u64p, C.c_size_t, u64p]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    """The compiled reference (None when oracle/_ref was never built)."""
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            return None
+        lib = C.CDLL(REF_SO)
+        lib.ref_domain_new.restype = C.c_void_p
+        lib.ref_domain_new.argtypes = [C.c_size_t]
+        lib.ref_domain_free.argtypes = [C.c_void_p]
+        lib.ref_domain_constant.argtypes = [C.c_void_p, C.c_int, u64p]
+        lib.ref_domain_num_threads.restype = C.c_size_t
+        lib.ref_domain_num_threads.argtypes = [C.c_void_p]
+        lib.ref_ntt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, u64p]
+        lib.ref_pippenger.argtypes = [u64p, u64p, C.c_size_t, C.c_size_t, u64p]
+        lib.ref_pippenger_inplace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, u64p]
+        lib.ref_batched_scalar_multiplications.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_size_t, u64p]
+        lib.ref_generate_pippenger_point_table.argtypes = [u64p, u64p, C.c_size_t]
+        lib.ref_get_optimal_bucket_width.restype = C.c_size_t
+        lib.ref_get_optimal_bucket_width.argtypes = [C.c_size_t]
+        lib.ref_fixed_wnaf.argtypes = [u64p, u32p, C.c_size_t, C.c_size_t]
+        lib.ref_g1_arith_progression.argtypes = [u64p, u64p, u64p, C.c_size_t]
+        lib.ref_g1_batch_normalize.argtypes = [u64p, C.c_size_t]
+        lib.ref_poly_evaluate.argtypes = [u64p, u64p, C.c_size_t, u64p]
+        lib.ref_r_inv.restype = C.c_uint64
+        lib.ref_aligned_alloc.restype = C.c_void_p
+        lib.ref_aligned_alloc.argtypes = [C.c_size_t]
+        lib.ref_aligned_free.argtypes = [C.c_void_p]
+        for name in ("ref_fq_mul_n", "ref_fr_mul_n"):
+            getattr(lib, name).argtypes = [u64p, u64p, u64p, C.c_size_t]
+        for name in ("ref_fr_to_mont_n", "ref_fr_from_mont_n", "ref_split_endo_n"):
+            getattr(lib, name).argtypes = [u64p, u64p, C.c_size_t]
+        _ref = lib
+    return _ref
+
+
+# ---------------------------------------------------------------- integers <-> limbs
+def to_limbs(x, n=4):
+    return np.array([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)], dtype=np.uint64)
+
+
+def from_limbs(a):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1)
+    return sum(int(v) << (64 * i) for i, v in enumerate(a))
+
+
+def limbs_array(ints):
+    out = np.empty((len(ints), 4), dtype=np.uint64)
+    for i, x in enumerate(ints):
+        out[i] = to_limbs(x)
+    return out
+
+
+def mont(x, field=FR):
+    return (x * R_MONT) % MODULUS[field]
+
+
+def unmont(x, field=FR):
+    return (x * pow(R_MONT, -1, MODULUS[field])) % MODULUS[field]
+
+
+# ---------------------------------------------------------------- seeded generators
+def splitmix64(seed, count):
+    """Vectorised splitmix64 stream: `count` uint64 values from `seed` (numpy, wraps mod 2^64)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, count + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def random_field_raw(seed, n, field=FR):
+    """n uniform-ish canonical values < p as (n,4) uint64 limbs (raw, i.e. whatever form the caller deems)."""
+    raw = splitmix64(seed, 4 * n).reshape(n, 4).copy()
+    raw[:, 3] &= np.uint64(0x3FFFFFFFFFFFFFFF)  # < 2^254
+    p = to_limbs(MODULUS[field])
+    # conditional subtract p (values < 2^254 < 2p)
+    ge = np.zeros(n, dtype=bool)
+    eq = np.ones(n, dtype=bool)
+    for i in (3, 2, 1, 0):
+        ge |= eq & (raw[:, i] > p[i])
+        eq &= raw[:, i] == p[i]
+    ge |= eq
+    if ge.any():
+        borrow = np.zeros(n, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            for i in range(4):
+                a = raw[:, i]
+                d = a - p[i] - borrow
+                nb = ((a < p[i]) | ((a == p[i]) & (borrow == 1))).astype(np.uint64)
+                raw[:, i] = np.where(ge, d, a)
+                borrow = nb
+    return raw
+
+
+def random_scalars_mont(seed, n):
+    """Seeded Fr elements in canonical Montgomery form (uniform residues: Montgomery form of a uniform value)."""
+    return random_field_raw(seed, n, FR)
+
+
+def generator_multiples_table(seed, n):
+    """Pippenger 2n table for points P_i = (a0 + i*d) * G (seeded a0, d), via the oracle.
+    Returns (table (2n,8) uint64, a0, d) with a0, d python ints (non-Montgomery)."""
+    lib = oracle()
+    a0 = int(splitmix64(seed, 1)[0]) | 1
+    d = int(splitmix64(seed + 1, 1)[0]) | 1
+    pts = arithmetic_progression_points(a0, d, n)
+    table = np.zeros((2 * n, 8), dtype=np.uint64)
+    if n:
+        lib.orc_generate_pippenger_point_table(ptr(pts), ptr(table), n)
+    return table, a0, d
+
+
+def arithmetic_progression_points(a0, d, n):
+    """(n,8) affine points (a0 + i d) G using oracle mixed adds + one batch normalisation."""
+    lib = oracle()
+    if n == 0:
+        return np.zeros((0, 8), dtype=np.uint64)
+    gen = np.zeros(8, dtype=np.uint64)
+    tmp = np.zeros(4, dtype=np.uint64)
+    lib.orc_constant(11, ptr(tmp)); gen[:4] = tmp
+    lib.orc_constant(12, ptr(tmp)); gen[4:] = tmp
+    base = np.zeros(8, dtype=np.uint64)
+    step = np.zeros(8, dtype=np.uint64)
+    lib.orc_g1_scalar_mul(ptr(gen), ptr(to_limbs(mont(a0))), ptr(base))
+    lib.orc_g1_scalar_mul(ptr(gen), ptr(to_limbs(mont(d))), ptr(step))
+    jac = np.zeros((n, 12), dtype=np.uint64)
+    one = np.zeros(4, dtype=np.uint64)
+    lib.orc_constant(2, ptr(one))
+    jac[0, :8] = base
+    jac[0, 8:] = one
+    for i in range(1, n):
+        lib.orc_g1_mixed_add(ptr(jac[i - 1]), ptr(step), ptr(jac[i]))
+    lib.orc_g1_batch_normalize(ptr(jac), n)
+    return np.ascontiguousarray(jac[:, :8])
+
+
+def is_infinity(pt):
+    """pt: affine (8) or Jacobian (12) limbs."""
+    return bool(int(pt[7]) >> 63)
+
+
+def oracle_msm(scalars, table):
+    """Normalised Jacobian (12 limbs) of sum scalars[i]*P_i via the C oracle."""
+    out = np.zeros(12, dtype=np.uint64)
+    n = scalars.shape[0]
+    oracle().orc_msm_normalized(ptr(np.ascontiguousarray(scalars)), ptr(np.ascontiguousarray(table)), n, ptr(out))
+    return out
+
+
+class OracleDomain:
+    def __init__(self, n):
+        self.n = n
+        self.h = oracle().orc_domain_new(n)
+
+    def ntt(self, op, coeffs, constant=None):
+        c = np.ascontiguousarray(coeffs).copy()
+        k = ptr(np.ascontiguousarray(constant)) if constant is not None else None
+        oracle().orc_ntt(self.h, op, ptr(c), k)
+        return c
+
+    def constant(self, which):
+        r = np.zeros(4, dtype=np.uint64)
+        oracle().orc_domain_constant(self.h, which, ptr(r))
+        return r
+
+    def __del__(self):
+        try:
+            oracle().orc_domain_free(self.h)
+        except Exception:
+            pass
+
+
+NTT_OPS = {"fft": 0, "ifft": 1, "coset_fft": 2, "coset_ifft": 3, "fft_with_constant": 4,
+           "ifft_with_constant": 5, "coset_fft_with_constant": 6}
