@@ -1,0 +1,435 @@
+// extern "C" surface of libbbgpu.so — see include/bbgpu.h for the contract and the reference
+// signatures each entry point stands behind.  No CPU fallback: every compute entry point needs the
+// CUDA device selected by bbg_init().
+#include "../../include/bbgpu.h"
+#include "bbg_internal.h"
+#include "bbg_host_g1.h"
+
+#include <mutex>
+#include <vector>
+
+namespace bbg
+{
+int microbench_launch(int mode, int iters, uint32_t* d_out, int blocks, double* ops, cudaStream_t st);
+}
+
+namespace
+{
+using namespace bbg;
+
+std::mutex g_mutex;
+bool g_ready = false;
+cudaStream_t g_stream = nullptr;
+bool g_own_stream = false;
+uint64_t g_misc_launches = 0;
+
+struct GrowBuf
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) bbg_rt::dev_free(p);
+        p = nullptr;
+        bytes = 0;
+        const int e = bbg_rt::dev_alloc(&p, need);
+        if (e == 0) bytes = need;
+        return e;
+    }
+    void release()
+    {
+        if (p) bbg_rt::dev_free(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+GrowBuf g_stage_coeffs;  // NTT host path: polynomial staging
+GrowBuf g_stage_scalars; // MSM host path: scalar staging
+GrowBuf g_stage_table;   // MSM host path: unregistered point tables
+
+struct SrsEntry
+{
+    const uint64_t* host_base;
+    size_t n; // original points; table has 2n entries of 8 uint64
+    void* d_table;
+};
+std::vector<SrsEntry> g_srs;
+
+#ifndef BBG_EMULATE
+cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+#endif
+
+int ensure_ready()
+{
+    if (g_ready) return 0;
+#ifdef BBG_EMULATE
+    g_ready = true;
+    return 0;
+#else
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return BBG_E_NO_DEVICE;
+    return BBG_E_NOT_INITIALISED;
+#endif
+}
+
+// device pointer for a host point-table pointer: registered SRS (sub-range allowed) or a fresh upload
+int resolve_table(const uint64_t* points, size_t n, const void** d_table)
+{
+    for (const SrsEntry& s : g_srs)
+    {
+        if (points >= s.host_base && points + 16 * n <= s.host_base + 16 * s.n)
+        {
+            *d_table = (const char*)s.d_table + ((const char*)points - (const char*)s.host_base);
+            return 0;
+        }
+    }
+    BBG_CHECK(g_stage_table.ensure(n * 128));
+    BBG_CHECK(bbg_rt::h2d(g_stage_table.p, points, n * 128, g_stream));
+    *d_table = g_stage_table.p;
+    return 0;
+}
+
+int msm_host(const uint64_t* scalars, const uint64_t* points, size_t n, hostg1::hxyzz* out)
+{
+    if (n == 0)
+    {
+        *out = hostg1::infinity();
+        return 0;
+    }
+    if (scalars == nullptr || points == nullptr) return BBG_E_BAD_ARGUMENT;
+    const void* d_table = nullptr;
+    BBG_CHECK(resolve_table(points, n, &d_table));
+    BBG_CHECK(g_stage_scalars.ensure(n * 32));
+    BBG_CHECK(bbg_rt::h2d(g_stage_scalars.p, scalars, n * 32, g_stream));
+    return msm_device(g_stage_scalars.p, d_table, n, out, g_stream);
+}
+} // namespace
+
+extern "C" {
+
+int bbg_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_ready) return 0;
+#ifndef BBG_EMULATE
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return BBG_E_NO_DEVICE;
+    if (device < 0 || device >= count) return BBG_E_BAD_ARGUMENT;
+    BBG_CHECK(cudaSetDevice(device));
+    if (g_stream == nullptr)
+    {
+        BBG_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+        g_own_stream = true;
+    }
+    BBG_CHECK(cudaEventCreate(&g_ev_start));
+    BBG_CHECK(cudaEventCreate(&g_ev_stop));
+#else
+    (void)device;
+#endif
+    g_ready = true;
+    return 0;
+}
+
+int bbg_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_ready) return 0;
+    bbg_rt::sync(g_stream);
+    ntt_release_tables();
+    msm_release_workspace();
+    g_stage_coeffs.release();
+    g_stage_scalars.release();
+    g_stage_table.release();
+    for (SrsEntry& s : g_srs) bbg_rt::dev_free(s.d_table);
+    g_srs.clear();
+#ifndef BBG_EMULATE
+    if (g_ev_start) cudaEventDestroy(g_ev_start);
+    if (g_ev_stop) cudaEventDestroy(g_ev_stop);
+    g_ev_start = g_ev_stop = nullptr;
+    if (g_own_stream && g_stream) cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+    g_own_stream = false;
+#endif
+    g_ready = false;
+    return 0;
+}
+
+int bbg_set_stream(void* cuda_stream)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    bbg_rt::sync(g_stream);
+#ifndef BBG_EMULATE
+    if (g_own_stream && g_stream) cudaStreamDestroy(g_stream);
+#endif
+    g_stream = (cudaStream_t)cuda_stream;
+    g_own_stream = false;
+    return 0;
+}
+
+const char* bbg_error_string(int code)
+{
+    switch (code)
+    {
+    case 0: return "success";
+    case BBG_E_BAD_SIZE: return "bbgpu: NTT size must be 2^1 .. 2^22";
+    case BBG_E_BAD_OP: return "bbgpu: unknown NTT operation";
+    case BBG_E_NULL_CONSTANT: return "bbgpu: this NTT operation needs a constant";
+    case BBG_E_NOT_INITIALISED: return "bbgpu: bbg_init() has not been called";
+    case BBG_E_NO_DEVICE: return "bbgpu: no CUDA device (there is no CPU fallback)";
+    case BBG_E_BAD_ARGUMENT: return "bbgpu: bad argument";
+    case BBG_E_TOO_LARGE: return "bbgpu: MSM too large";
+    case 1001: return "bbgpu: internal: unsupported sub-transform size";
+    }
+#ifndef BBG_EMULATE
+    if (code > 0 && code < 1000) return cudaGetErrorString((cudaError_t)code);
+#endif
+    return "bbgpu: unknown error";
+}
+
+uint64_t bbg_launch_count(void) { return (uint64_t)ntt_launch_count() + (uint64_t)msm_launch_count() + g_misc_launches; }
+
+// ---- NTT ----------------------------------------------------------------------------------------
+int bbg_ntt_fr_dev(void* d_coeffs, size_t stride_elems, size_t batch, unsigned log2_n, int op, const uint64_t* constant)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (d_coeffs == nullptr && batch > 0) return BBG_E_BAD_ARGUMENT;
+    return ntt_device(d_coeffs, stride_elems, batch, log2_n, op, constant, g_stream);
+}
+
+int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, int op, const uint64_t* constant)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (batch == 0) return 0;
+    if (coeffs == nullptr) return BBG_E_BAD_ARGUMENT;
+    if (log2_n < 1 || log2_n > 22) return BBG_E_BAD_SIZE;
+    const size_t n = (size_t)1 << log2_n, bytes = n * 32;
+    BBG_CHECK(g_stage_coeffs.ensure(batch * bytes));
+    for (size_t i = 0; i < batch; ++i)
+    {
+        if (coeffs[i] == nullptr) return BBG_E_BAD_ARGUMENT;
+        BBG_CHECK(bbg_rt::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_stream));
+    }
+    BBG_CHECK(ntt_device(g_stage_coeffs.p, n, batch, log2_n, op, constant, g_stream));
+    for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_rt::d2h(coeffs[i], (char*)g_stage_coeffs.p + i * bytes, bytes, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+
+int bbg_ntt_fr(uint64_t* coeffs, unsigned log2_n, int op, const uint64_t* constant)
+{
+    uint64_t* one[1] = { coeffs };
+    return bbg_ntt_fr_batched(one, 1, log2_n, op, constant);
+}
+
+// ---- MSM ----------------------------------------------------------------------------------------
+int bbg_srs_register(const uint64_t* table_2n, size_t n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (table_2n == nullptr || n == 0) return BBG_E_BAD_ARGUMENT;
+    for (size_t i = 0; i < g_srs.size(); ++i)
+    {
+        if (g_srs[i].host_base == table_2n)
+        {
+            bbg_rt::dev_free(g_srs[i].d_table);
+            g_srs.erase(g_srs.begin() + (long)i);
+            break;
+        }
+    }
+    SrsEntry s;
+    s.host_base = table_2n;
+    s.n = n;
+    s.d_table = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
+    BBG_CHECK(bbg_rt::h2d(s.d_table, table_2n, n * 128, g_stream));
+    BBG_CHECK(bbg_rt::sync(g_stream));
+    g_srs.push_back(s);
+    return 0;
+}
+
+int bbg_srs_unregister(const uint64_t* table_2n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (size_t i = 0; i < g_srs.size(); ++i)
+    {
+        if (g_srs[i].host_base == table_2n)
+        {
+            bbg_rt::sync(g_stream);
+            bbg_rt::dev_free(g_srs[i].d_table);
+            g_srs.erase(g_srs.begin() + (long)i);
+            return 0;
+        }
+    }
+    return BBG_E_BAD_ARGUMENT;
+}
+
+int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, uint64_t out_xyz[12])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    hostg1::hxyzz r;
+    BBG_CHECK(msm_host(scalars, points_table, n, &r));
+    hostg1::to_normalized_jacobian(r, out_xyz);
+    return 0;
+}
+
+int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* points_tables, size_t n, size_t batches, uint64_t* out_xyz)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    for (size_t i = 0; i < batches; ++i)
+    {
+        hostg1::hxyzz r;
+        BBG_CHECK(msm_host(scalars[i], points_tables[i], n, &r));
+        hostg1::to_normalized_jacobian(r, out_xyz + 12 * i);
+    }
+    return 0;
+}
+
+int bbg_msm_g1_partial_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyzz[16])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    return msm_device(d_scalars, d_table, n, out_xyzz, g_stream);
+}
+
+int bbg_msm_g1_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyz[12])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    hostg1::hxyzz r;
+    BBG_CHECK(msm_device(d_scalars, d_table, n, &r, g_stream));
+    hostg1::to_normalized_jacobian(r, out_xyz);
+    return 0;
+}
+
+int bbg_g1_fold_partials(const uint64_t* partials_xyzz, size_t count, uint64_t out_xyz[12])
+{
+    hostg1::hxyzz acc = hostg1::infinity();
+    for (size_t i = 0; i < count; ++i)
+    {
+        hostg1::hxyzz p;
+        memcpy(&p, partials_xyzz + 16 * i, sizeof p);
+        acc = hostg1::add(acc, p);
+    }
+    hostg1::to_normalized_jacobian(acc, out_xyz);
+    return 0;
+}
+
+int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table_2n, size_t n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (n == 0) return 0;
+    if (points_n == nullptr || table_2n == nullptr) return BBG_E_BAD_ARGUMENT;
+    void *d_pts = nullptr, *d_tab = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc(&d_pts, n * 64));
+    int e = bbg_rt::dev_alloc(&d_tab, n * 128);
+    if (e == 0) e = bbg_rt::h2d(d_pts, points_n, n * 64, g_stream);
+    if (e == 0) e = g1_build_endo_table_device(d_pts, d_tab, n, g_stream);
+    if (e == 0) e = bbg_rt::d2h(table_2n, d_tab, n * 128, g_stream);
+    if (e == 0) e = bbg_rt::sync(g_stream);
+    bbg_rt::dev_free(d_pts);
+    if (d_tab) bbg_rt::dev_free(d_tab);
+    return e;
+}
+
+// ---- device memory helpers ------------------------------------------------------------------------
+int bbg_dev_alloc(void** d_ptr, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    return bbg_rt::dev_alloc(d_ptr, bytes);
+}
+int bbg_dev_free(void* d_ptr)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    bbg_rt::sync(g_stream);
+    return bbg_rt::dev_free(d_ptr);
+}
+int bbg_copy_h2d(void* d_dst, const void* h_src, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    BBG_CHECK(bbg_rt::h2d(d_dst, h_src, bytes, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+int bbg_copy_d2h(void* h_dst, const void* d_src, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    BBG_CHECK(bbg_rt::d2h(h_dst, d_src, bytes, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+int bbg_sync(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    return bbg_rt::sync(g_stream);
+}
+int bbg_timer_start(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+#ifndef BBG_EMULATE
+    return (int)cudaEventRecord(g_ev_start, g_stream);
+#else
+    return 0;
+#endif
+}
+int bbg_timer_stop(float* elapsed_ms)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+#ifndef BBG_EMULATE
+    BBG_CHECK(cudaEventRecord(g_ev_stop, g_stream));
+    BBG_CHECK(cudaEventSynchronize(g_ev_stop));
+    return (int)cudaEventElapsedTime(elapsed_ms, g_ev_start, g_ev_stop);
+#else
+    *elapsed_ms = 0.f;
+    return 0;
+#endif
+}
+
+int bbg_microbench(int mode, int iters, double* ops_per_second, float* elapsed_ms)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (iters <= 0 || ops_per_second == nullptr || elapsed_ms == nullptr) return BBG_E_BAD_ARGUMENT;
+#ifndef BBG_EMULATE
+    const int blocks = bbg_rt::num_sms() * 8;
+    uint32_t* d_out = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc((void**)&d_out, (size_t)blocks * 256 * 4));
+    double ops = 0;
+    int e = microbench_launch(mode, iters / 8 > 0 ? iters / 8 : 1, d_out, blocks, &ops, g_stream); // warm-up
+    float best = 0.f;
+    for (int rep = 0; rep < 5 && e == 0; ++rep)
+    {
+        cudaEventRecord(g_ev_start, g_stream);
+        e = microbench_launch(mode, iters, d_out, blocks, &ops, g_stream);
+        cudaEventRecord(g_ev_stop, g_stream);
+        if (e == 0) e = (int)cudaEventSynchronize(g_ev_stop);
+        float ms = 0.f;
+        if (e == 0) e = (int)cudaEventElapsedTime(&ms, g_ev_start, g_ev_stop);
+        if (rep == 0 || ms < best) best = ms;
+        g_misc_launches += 1;
+    }
+    bbg_rt::dev_free(d_out);
+    if (e != 0) return e;
+    *elapsed_ms = best;
+    *ops_per_second = ops / ((double)best * 1e-3);
+    return 0;
+#else
+    (void)mode;
+    *ops_per_second = 0;
+    *elapsed_ms = 0;
+    return 0;
+#endif
+}
+
+} // extern "C"

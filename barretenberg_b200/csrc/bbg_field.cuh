@@ -1,0 +1,447 @@
+// bn254 Fq / Fr arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form with R = 2^256.
+//
+// Replaces the reference's x86-64 MULX/ADCX/ADOX field layer
+//   fields/field_impl_asm.tcc:58-348, fields/asm_macros.hpp:34-413   (semantics: field_impl_int128.tcc)
+// with IMAD / carry-chain code.  Same value conventions as the reference:
+//   * "coarse" results live in [0, 2p) (reference: *_with_coarse_reduction), canonical ones in [0, p)
+//   * every routine accepts inputs in [0, 2p); 4p < 2^256 for both moduli so sums never wrap
+//   * limbs in memory are the reference's 4 x uint64 little-endian == our 8 x uint32 little-endian
+//
+// Montgomery product: operand-scanning CIOS over 32-bit words with two interleaved accumulators
+// ("even"/"odd" columns) so every 32x32->64 product lands 64-bit aligned and each (mad.lo.cc,
+// madc.hi.cc) pair can issue as one wide IMAD with carry.  Per product: 128 wide IMADs + 8 IMADs
+// for the reduction factors (SURVEY.md §8a "136 MACs").
+//
+// The carry-chain primitives have two bodies: inline PTX under __CUDA_ARCH__, and a plain C++
+// rendition used ONLY by the CPU-side kernel emulation build (tests/emul, -DBBG_EMULATE) so the
+// limb logic can be checked against the oracle on machines without a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BBG_HD __host__ __device__ __forceinline__
+#define BBG_D __device__ __forceinline__
+#else
+#define BBG_HD inline
+#define BBG_D inline
+#endif
+
+namespace bbg
+{
+
+struct fe
+{
+    uint32_t v[8];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Field parameters (values: reference curves/bn254/fq.hpp:12-64, curves/bn254/fr.hpp:12-81)
+// ---------------------------------------------------------------------------------------------
+// (accessor functions rather than static arrays: nvcc cannot ODR-use a host constexpr array in device code;
+//  after unrolling every index is a literal and the words become instruction immediates)
+#define BBG_CONST8(NAME, ...)                                                                      \
+    static BBG_HD constexpr uint32_t NAME(int i)                                                   \
+    {                                                                                              \
+        constexpr uint32_t t[8] = { __VA_ARGS__ };                                                 \
+        return t[i];                                                                               \
+    }
+struct FqParams
+{
+    BBG_CONST8(P, 0xD87CFD47u, 0x3C208C16u, 0x6871CA8Du, 0x97816A91u, 0x8181585Du, 0xB85045B6u, 0xE131A029u, 0x30644E72u)
+    BBG_CONST8(P2, 0xB0F9FA8Eu, 0x7841182Du, 0xD0E3951Au, 0x2F02D522u, 0x0302B0BBu, 0x70A08B6Du, 0xC2634053u, 0x60C89CE5u)
+    BBG_CONST8(R2, 0x538AFA89u, 0xF32CFC5Bu, 0xD44501FBu, 0xB5E71911u, 0x0A417FF6u, 0x47AB1EFFu, 0xCAB8351Fu, 0x06D89F71u)
+    BBG_CONST8(ONE, 0xC58F0D9Du, 0xD35D438Du, 0xF5C70B3Du, 0x0A78EB28u, 0x7879462Cu, 0x666EA36Fu, 0x9A07DF2Fu, 0x0E0A77C1u)
+    // cube root of unity beta (fq.hpp:53-56), Montgomery form
+    BBG_CONST8(CUBE, 0xD782E155u, 0x71930C11u, 0xFFBE3323u, 0xA6BB947Cu, 0xD4741444u, 0xAA303344u, 0x26594943u, 0x2C3B3F0Du)
+    static constexpr uint32_t NINV = 0xE4866389u; // low word of r_inv (fq.hpp:64): -p^-1 mod 2^32
+};
+struct FrParams
+{
+    BBG_CONST8(P, 0xF0000001u, 0x43E1F593u, 0x79B97091u, 0x2833E848u, 0x8181585Du, 0xB85045B6u, 0xE131A029u, 0x30644E72u)
+    BBG_CONST8(P2, 0xE0000002u, 0x87C3EB27u, 0xF372E122u, 0x5067D090u, 0x0302B0BAu, 0x70A08B6Du, 0xC2634053u, 0x60C89CE5u)
+    BBG_CONST8(R2, 0xAE216DA7u, 0x1BB8E645u, 0xE35C59E3u, 0x53FE3AB1u, 0x53BB8085u, 0x8C49833Du, 0x7F4E44A5u, 0x0216D0B1u)
+    BBG_CONST8(ONE, 0x4FFFFFFBu, 0xAC96341Cu, 0x9F60CD29u, 0x36FC7695u, 0x7879462Eu, 0x666EA36Fu, 0x9A07DF2Fu, 0x0E0A77C1u)
+    // lambda (fr.hpp:54-57, stored by the reference as fr::beta), Montgomery form
+    BBG_CONST8(CUBE, 0x4A0329B3u, 0x93E7CEDEu, 0x7A96C167u, 0x7D4FDCA7u, 0xB19A750Au, 0x8BE4BA08u, 0xA5661C25u, 0x1CBD5653u)
+    static constexpr uint32_t NINV = 0xEFFFFFFFu; // low word of r_inv (fr.hpp:81)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Carry-chain primitives
+// ---------------------------------------------------------------------------------------------
+namespace cc
+{
+// r = a + b (256 bit); returns carry out
+BBG_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b)
+{
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t t = 0;
+    for (int i = 0; i < 8; ++i)
+    {
+        t += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)t;
+        t >>= 32;
+    }
+    c = (uint32_t)t;
+#endif
+    return c;
+}
+
+// r = a - b (256 bit); returns borrow out as 0 / 0xffffffff
+BBG_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b)
+{
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t borrow = 0;
+    for (int i = 0; i < 8; ++i)
+    {
+        uint64_t t = (uint64_t)a[i] - b[i] - borrow;
+        r[i] = (uint32_t)t;
+        borrow = (t >> 32) & 1;
+    }
+    c = borrow ? 0xffffffffu : 0u;
+#endif
+    return c;
+}
+
+// acc (four 64-bit columns acc[2j+1]:acc[2j]) = x[2j] * y        (no carries between columns)
+BBG_HD void mul_row(uint32_t* acc, const uint32_t* x, uint32_t y)
+{
+#pragma unroll
+    for (int j = 0; j < 8; j += 2)
+    {
+        uint64_t t = (uint64_t)x[j] * y;
+        acc[j] = (uint32_t)t;
+        acc[j + 1] = (uint32_t)(t >> 32);
+    }
+}
+
+// acc += sum_j x[2j] * y * 2^(64 j) with one carry chain; the carry out of bit 256 is added to `top`
+BBG_HD void mad_row_carry(uint32_t* acc, uint32_t& top, const uint32_t* x, uint32_t y)
+{
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+#else
+    uint64_t carry = 0;
+    for (int j = 0; j < 8; j += 2)
+    {
+        uint64_t prod = (uint64_t)x[j] * y;
+        uint64_t lo = (uint64_t)acc[j] + (uint32_t)prod + carry;
+        acc[j] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[j + 1] + (uint32_t)(prod >> 32) + (lo >> 32);
+        acc[j + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+    top += (uint32_t)carry;
+#endif
+}
+
+// same, carry out of bit 256 dropped (callers guarantee it is zero)
+BBG_HD void mad_row(uint32_t* acc, const uint32_t* x, uint32_t y)
+{
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+#else
+    uint32_t dropped = 0;
+    mad_row_carry(acc, dropped, x, y);
+#endif
+}
+
+// Column shift fused with a row of products (the "T >>= 32" of CIOS):
+//   e0  += sh[1]                                    (leftover low word joins the new even column 0)
+//   sh   = (sh >> 64) + sum_j x[2j] * y * 2^(64 j) + carry of the line above
+// `sh` holds the old even accumulator on entry and the new odd accumulator on exit.
+BBG_HD void shift_mad_row(uint32_t* sh, uint32_t& e0, const uint32_t* x, uint32_t y)
+{
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %8, %8, %1;\n\t"
+        "madc.lo.cc.u32 %0, %9, %13, %2;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %4;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %6;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, 0;\n\t"
+        "madc.hi.u32 %7, %12, %13, 0;"
+        : "+r"(sh[0]), "+r"(sh[1]), "+r"(sh[2]), "+r"(sh[3]), "+r"(sh[4]), "+r"(sh[5]), "+r"(sh[6]), "+r"(sh[7]), "+r"(e0)
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+#else
+    uint64_t t = (uint64_t)e0 + sh[1];
+    e0 = (uint32_t)t;
+    uint64_t carry = t >> 32;
+    for (int j = 0; j < 8; j += 2)
+    {
+        uint64_t prod = (uint64_t)x[j] * y;
+        uint32_t in_lo = (j + 2 < 8) ? sh[j + 2] : 0u;
+        uint32_t in_hi = (j + 3 < 8) ? sh[j + 3] : 0u;
+        uint64_t lo = (uint64_t)in_lo + (uint32_t)prod + carry;
+        uint64_t hi = (uint64_t)in_hi + (uint32_t)(prod >> 32) + (lo >> 32);
+        sh[j] = (uint32_t)lo;
+        sh[j + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+#endif
+}
+} // namespace cc
+
+// ---------------------------------------------------------------------------------------------
+// Field operations
+// ---------------------------------------------------------------------------------------------
+template <typename FP> struct Field
+{
+    typedef FP params;
+
+    static BBG_HD fe zero()
+    {
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = 0;
+        return r;
+    }
+    template <typename Fn> static BBG_HD fe constant(Fn c)
+    {
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = c(i);
+        return r;
+    }
+    static BBG_HD fe one() { return constant([](int i) { return FP::ONE(i); }); }
+    static BBG_HD fe modulus() { return constant([](int i) { return FP::P(i); }); }
+
+    // Montgomery product, result in [0, 2p) for inputs in [0, 2p).
+    // (reference: __mul_with_coarse_reduction, field_impl_asm.tcc:332-348 / field_impl_int128.tcc:254-263;
+    //  same integer (ab + Mp)/2^256 as the 64-bit-limb reduction since M = -ab/p mod 2^256 either way)
+    static BBG_HD fe mul(const fe& a, const fe& b)
+    {
+        uint32_t A[8], B[8];            // the two column accumulators; roles swap every word of b
+        const uint32_t* ae = a.v;       // a[0], a[2], a[4], a[6]
+        const uint32_t* ao = a.v + 1;   // a[1], a[3], a[5], a[7]
+        uint32_t pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = FP::P(i);
+        const uint32_t* pe = pl;     // p[0], p[2], p[4], p[6]
+        const uint32_t* po = pl + 1; // p[1], p[3], p[5], p[7]
+
+        // word 0: even = A, odd = B
+        cc::mul_row(A, ae, b.v[0]);
+        cc::mul_row(B, ao, b.v[0]);
+        {
+            uint32_t m = A[0] * FP::NINV;
+            cc::mad_row(B, po, m);
+            cc::mad_row_carry(A, B[7], pe, m);
+        }
+#pragma unroll
+        for (int i = 1; i < 8; i += 2)
+        {
+            // odd word i: even = B, odd = A (A is shifted down two words on the way)
+            {
+                const uint32_t bi = b.v[i];
+                cc::shift_mad_row(A, B[0], ao, bi);
+                cc::mad_row_carry(B, A[7], ae, bi);
+                uint32_t m = B[0] * FP::NINV;
+                cc::mad_row(A, po, m);
+                cc::mad_row_carry(B, A[7], pe, m);
+            }
+            if (i + 1 < 8)
+            {
+                // even word i+1: even = A, odd = B
+                const uint32_t bi = b.v[i + 1];
+                cc::shift_mad_row(B, A[0], ao, bi);
+                cc::mad_row_carry(A, B[7], ae, bi);
+                uint32_t m = A[0] * FP::NINV;
+                cc::mad_row(B, po, m);
+                cc::mad_row_carry(A, B[7], pe, m);
+            }
+        }
+        // after word 7: even = B with B[0] == 0, odd = A.  result[k] = B[k+1] + A[k]
+        fe r;
+        uint32_t hi[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) hi[k] = B[k + 1];
+        hi[7] = 0;
+        cc::add8(r.v, A, hi);
+        return r;
+    }
+    static BBG_HD fe sqr(const fe& a) { return mul(a, a); }
+
+    // [0,2p) -> [0,p)   (reference: reduce_once)
+    static BBG_HD fe reduce(const fe& a)
+    {
+        fe t;
+        uint32_t pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = FP::P(i);
+        uint32_t borrow = cc::sub8(t.v, a.v, pl);
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = borrow ? a.v[i] : t.v[i];
+        return r;
+    }
+    // a + b mod 2p, inputs/outputs in [0,2p)   (reference: __add_with_coarse_reduction)
+    static BBG_HD fe add(const fe& a, const fe& b)
+    {
+        fe s, t;
+        uint32_t p2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p2[i] = FP::P2(i);
+        cc::add8(s.v, a.v, b.v);
+        uint32_t borrow = cc::sub8(t.v, s.v, p2);
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = borrow ? s.v[i] : t.v[i];
+        return r;
+    }
+    // a - b mod 2p, inputs/outputs in [0,2p)   (reference: __sub_with_coarse_reduction)
+    static BBG_HD fe sub(const fe& a, const fe& b)
+    {
+        fe d, t;
+        uint32_t p2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p2[i] = FP::P2(i);
+        uint32_t borrow = cc::sub8(d.v, a.v, b.v);
+        cc::add8(t.v, d.v, p2);
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = borrow ? t.v[i] : d.v[i];
+        return r;
+    }
+    static BBG_HD fe dbl(const fe& a) { return add(a, a); }
+    // -a in [0,2p): 2p - a  (a in [0,2p]);  maps 0 -> 2p?  no: 0 stays 0
+    static BBG_HD fe neg(const fe& a)
+    {
+        fe z = zero();
+        return sub(z, a);
+    }
+    // canonical results
+    static BBG_HD fe mul_full(const fe& a, const fe& b) { return reduce(mul(a, b)); }     // reference __mul
+    static BBG_HD fe to_mont(const fe& a) { return mul_full(a, constant([](int i) { return FP::R2(i); })); }       // field.hpp:224-232
+    static BBG_HD fe from_mont(const fe& a)                                               // field.hpp:233-236
+    {
+        fe o = zero();
+        o.v[0] = 1;
+        return mul_full(a, o);
+    }
+    static BBG_HD bool is_zero_raw(const fe& a)
+    {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= a.v[i];
+        return o == 0;
+    }
+    // a == 0 (mod p) for a in [0,2p)
+    static BBG_HD bool is_zero(const fe& a) { return is_zero_raw(reduce(a)); }
+    static BBG_HD bool eq_raw(const fe& a, const fe& b)
+    {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= a.v[i] ^ b.v[i];
+        return o == 0;
+    }
+    // a^e for a small exponent, square-and-multiply msb first; coarse result
+    static BBG_HD fe pow_u64(const fe& a, uint64_t e)
+    {
+        fe acc = one();
+        bool started = false;
+        for (int i = 63; i >= 0; --i)
+        {
+            if (started) acc = sqr(acc);
+            if ((e >> i) & 1)
+            {
+                acc = started ? mul(acc, a) : a;
+                started = true;
+            }
+        }
+        return acc;
+    }
+    // Fermat inversion a^(p-2) (reference field.hpp:345-348); canonical result
+    static BBG_HD fe invert(const fe& a)
+    {
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = FP::P(i);
+        e[0] -= 2; // neither modulus has a low word < 2
+        fe acc = one();
+        bool started = false;
+        for (int i = 255; i >= 0; --i)
+        {
+            if (started) acc = sqr(acc);
+            if ((e[i >> 5] >> (i & 31)) & 1)
+            {
+                acc = started ? mul(acc, a) : a;
+                started = true;
+            }
+        }
+        return reduce(acc);
+    }
+};
+
+typedef Field<FqParams> Fq;
+typedef Field<FrParams> Fr;
+
+// 16-byte vector load/store of a field element (the reference's field_t is 32-byte aligned)
+BBG_HD fe load_fe(const void* p)
+{
+    const uint4* q = (const uint4*)p;
+    uint4 lo = q[0], hi = q[1];
+    fe r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+BBG_HD void store_fe(void* p, const fe& a)
+{
+    uint4* q = (uint4*)p;
+    uint4 lo, hi;
+    lo.x = a.v[0]; lo.y = a.v[1]; lo.z = a.v[2]; lo.w = a.v[3];
+    hi.x = a.v[4]; hi.y = a.v[5]; hi.z = a.v[6]; hi.w = a.v[7];
+    q[0] = lo;
+    q[1] = hi;
+}
+
+} // namespace bbg

@@ -1,0 +1,40 @@
+// Internal declarations shared by the CUDA translation units behind include/bbgpu.h.
+#pragma once
+#include "bbg_rt.h"
+#include "bbg_g1.cuh"
+
+#define BBG_CHECK(expr)                                                                            \
+    do                                                                                             \
+    {                                                                                              \
+        int bbg_err_ = (int)(expr);                                                                \
+        if (bbg_err_ != 0) return bbg_err_;                                                        \
+    } while (0)
+
+namespace bbg
+{
+// NTT operation codes == the reference's seven entry points (polynomial_arithmetic.hpp:28-39)
+enum ntt_op
+{
+    OP_FFT = 0,
+    OP_IFFT = 1,
+    OP_COSET_FFT = 2,
+    OP_COSET_IFFT = 3,
+    OP_FFT_WITH_CONSTANT = 4,
+    OP_IFFT_WITH_CONSTANT = 5,
+    OP_COSET_FFT_WITH_CONSTANT = 6,
+};
+
+// device-resident NTT: batch polynomials of 2^log_n elements, `stride` elements apart, in place.
+int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int op, const uint64_t* constant, cudaStream_t stream);
+int ntt_release_tables();
+size_t ntt_launch_count();
+
+// device-resident MSM over a device point table (2n affine entries, reference layout) and device scalars.
+// Writes the un-normalised sum as XYZZ (16 x uint64: X, Y, ZZ, ZZZ) to the HOST buffer out_xyzz_host;
+// synchronises the stream (the window fold is the host-side finish, bbg_host_g1.h).
+int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t stream);
+int msm_release_workspace();
+size_t msm_launch_count();
+// table[2i] = P_i, table[2i+1] = (beta x_i, -y_i) on device (generate_pippenger_point_table layout)
+int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cudaStream_t stream);
+} // namespace bbg

@@ -1,0 +1,137 @@
+// Integer multiply-add throughput microbenchmarks: the measured IMAD roofline denominator that
+// bench.py reports field-multiplication throughput against ("measure it").
+#include "bbg_internal.h"
+
+namespace bbg
+{
+namespace
+{
+constexpr int MB_THREADS = 256;
+constexpr int MB_CHAINS = 8;
+
+// mode 0: 8 independent mad.lo.u32 chains per thread;  1: mad.wide.u32 with 64-bit accumulators
+template <int MODE> __global__ void __launch_bounds__(MB_THREADS) imad_kernel(uint32_t* out, uint32_t seed, int iters)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t x = seed ^ tid, y = (seed * 2654435761u) | 1u;
+    if (MODE == 0)
+    {
+        uint32_t acc[MB_CHAINS];
+#pragma unroll
+        for (int i = 0; i < MB_CHAINS; ++i) acc[i] = tid + i;
+        for (int it = 0; it < iters; ++it)
+        {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+#pragma unroll
+                for (int i = 0; i < MB_CHAINS; ++i) acc[i] = acc[i] * x + y;
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < MB_CHAINS; ++i) s ^= acc[i];
+        out[tid] = s;
+    }
+    else
+    {
+        uint64_t acc[MB_CHAINS];
+#pragma unroll
+        for (int i = 0; i < MB_CHAINS; ++i) acc[i] = tid + i;
+        for (int it = 0; it < iters; ++it)
+        {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+#pragma unroll
+                for (int i = 0; i < MB_CHAINS; ++i) acc[i] = (uint64_t)((uint32_t)acc[i] ^ x) * y + acc[i];
+            }
+        }
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < MB_CHAINS; ++i) s ^= acc[i];
+        out[tid] = (uint32_t)s ^ (uint32_t)(s >> 32);
+    }
+}
+
+// mode 2: the carry-chained pairs the Montgomery product is made of (4 independent 256-bit rows per thread)
+__global__ void __launch_bounds__(MB_THREADS) imad_chain_kernel(uint32_t* out, uint32_t seed, int iters)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc[4][8], x[8], top[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        x[i] = (seed + i) * 2654435761u ^ tid;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][i] = tid + i + r;
+    }
+    uint32_t y = seed | 1u;
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cc::mad_row_carry(acc[r], top[r], x, y + r);
+        y += top[0];
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= acc[r][i];
+        s ^= top[r];
+    }
+    out[tid] = s;
+}
+
+// modes 3/4: Montgomery products, two independent dependency chains per thread
+template <typename F> __global__ void __launch_bounds__(MB_THREADS) field_mul_kernel(uint32_t* out, uint32_t seed, int iters)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    fe a = F::one(), b = F::one(), m = F::one();
+    a.v[0] ^= tid;
+    b.v[1] ^= seed;
+    m.v[0] += seed & 0xff;
+    for (int it = 0; it < iters; ++it)
+    {
+        a = F::mul(a, m);
+        b = F::mul(b, m);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= a.v[i] ^ b.v[i];
+    out[tid] = s;
+}
+} // namespace
+
+// returns ops (32x32 multiply-adds, or field products) issued by the whole grid
+int microbench_launch(int mode, int iters, uint32_t* d_out, int blocks, double* ops, cudaStream_t st)
+{
+    const double threads = (double)blocks * MB_THREADS;
+    switch (mode)
+    {
+    case 0:
+        BBG_LAUNCH_NOSYNC(imad_kernel<0>, dim3(blocks), dim3(MB_THREADS), st, d_out, 12345u, iters);
+        *ops = threads * iters * 4.0 * MB_CHAINS;
+        break;
+    case 1:
+        BBG_LAUNCH_NOSYNC(imad_kernel<1>, dim3(blocks), dim3(MB_THREADS), st, d_out, 12345u, iters);
+        *ops = threads * iters * 4.0 * MB_CHAINS;
+        break;
+    case 2:
+        BBG_LAUNCH_NOSYNC(imad_chain_kernel, dim3(blocks), dim3(MB_THREADS), st, d_out, 12345u, iters);
+        *ops = threads * iters * 16.0; // 4 rows x 4 wide multiply-adds
+        break;
+    case 3:
+        BBG_LAUNCH_NOSYNC(field_mul_kernel<Fq>, dim3(blocks), dim3(MB_THREADS), st, d_out, 12345u, iters);
+        *ops = threads * iters * 2.0;
+        break;
+    case 4:
+        BBG_LAUNCH_NOSYNC(field_mul_kernel<Fr>, dim3(blocks), dim3(MB_THREADS), st, d_out, 12345u, iters);
+        *ops = threads * iters * 2.0;
+        break;
+    default: return 1007;
+    }
+    return bbg_rt::last_error();
+}
+} // namespace bbg

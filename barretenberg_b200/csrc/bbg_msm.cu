@@ -1,0 +1,558 @@
+// Pippenger multi-scalar multiplication over bn254 G1 for sm_100a.
+//
+// Replaces scalar_multiplication::pippenger / batched_scalar_multiplications
+//   (reference curves/bn254/scalar_multiplication.cpp:457-476, :576-648, :650-772) for the value they
+//   compute: sum_i k_i * P_i over the reference's interleaved 2n point table [P_i, phi(P_i)].
+// The result is a group element, independent of bucket width, thread partition and summation order
+// (SURVEY.md §8 note 3), so the pipeline below is free to be GPU-shaped:
+//
+//   1. digits   one thread per scalar: out of Montgomery form, the reference's endomorphism split
+//               (field.hpp:413-485) restated exactly in 32-bit limbs -> two 128-bit half scalars for table
+//               entries 2i and 2i+1, then signed c-bit window digits d in [-2^(c-1)+1, 2^(c-1)] (zero digits
+//               are dropped: a zero scalar costs nothing, unlike the reference's always-odd wNAF which turns
+//               it into a P + (-P) pair per round).  Histogram of (window, |d|) by global atomics.
+//   2. scan     exclusive prefix sum of the W * 2^(c-1) bucket counts.
+//   3. scatter  counting sort: (point index | sign) written at its bucket's cursor -> entries grouped by
+//               (window, bucket).  [pippenger.md:49-76 is the authors' sketch of this bucket-ordered form.]
+//   4. accumulate  the sorted entry array is cut into fixed slices of S entries, one thread per slice:
+//               perfectly balanced whatever the digit distribution.  A thread walks its slice doing mixed
+//               additions acc += +-P (XYZZ coordinates, 10 field products) and flushes at bucket boundaries;
+//               runs cut by a slice boundary go to per-slice head/tail slots.
+//   5. fix-up   one thread per bucket that spans slices: tail + heads.
+//   6. reduce   window sum = sum_b (b+1) * B_b: threads take chunks of 16 buckets (local running sums, the
+//               reference's :628-640 loop in miniature), then block-wide tree reductions produce per window the
+//               plain sums and the log2(chunks) bit-sliced sums T_r = sum_{t: bit r of t} A_t.
+//   7. finish   host: S_w = sum V + sum A + 16 * sum_r 2^r T_r, fold windows, normalise (bbg_host_g1.h).
+//
+// Work at n = 2^20 (c = 16, W = 8): 2^24 mixed adds (1.68e8 Fq products) + ~2^20 full adds; HBM: 64 MiB digits
+// written + read, 64 MiB sorted entries, ~1 GiB of 64-byte point gathers mostly served from L2.
+#include "bbg_internal.h"
+#include "bbg_host_g1.h"
+
+#include <vector>
+
+namespace bbg
+{
+namespace msmk
+{
+constexpr uint32_t NO_DIGIT = 0xffffffffu;
+constexpr int CHUNK_LOG = 4; // buckets per running-sum thread in stage 6
+
+struct Plan
+{
+    size_t n;          // scalars
+    size_t num_points; // 2n table entries
+    int c;             // window bits
+    int W;             // windows
+    uint32_t NB;       // buckets per window = 2^(c-1)
+    uint32_t total_buckets;
+    uint32_t S;        // slice length
+    size_t max_entries;
+    size_t max_slices;
+    int chunk_log;
+    uint32_t chunks_per_window;
+    int reduce_outputs; // per window: chunk bits + 2
+};
+
+// little multi-word helpers for the endomorphism split (portable: host and device)
+template <int NA, int NB_> BBG_HD void mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* out)
+{
+#pragma unroll
+    for (int i = 0; i < NA + NB_; ++i) out[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+    {
+        uint32_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < NB_; ++j)
+        {
+            const uint64_t t = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+            out[i + j] = (uint32_t)t;
+            carry = (uint32_t)(t >> 32);
+        }
+        out[i + NB_] = carry;
+    }
+}
+
+// field.hpp:413-485, restated on 32-bit words.  k canonical, non-Montgomery.  k1, k2: low 128 bits.
+BBG_HD void split_endo(const fe& k, uint32_t k1[4], uint32_t k2[4])
+{
+    // g1 = {0x7a7bd9d4391eb18d, 0x4ccef014a773d2cf, 2}, g2 = {0xd91d232ec7e0b3d7, 2},
+    // minus_b1 = {0x8211bbeb7d4f1128, 0x6f4d8248eeb859fc}, b2 = {0x89d3256894d213e3}   (field.hpp:420-426)
+    const uint32_t g1c[5] = { 0x391eb18du, 0x7a7bd9d4u, 0xa773d2cfu, 0x4ccef014u, 0x2u };
+    const uint32_t g2c[3] = { 0xc7e0b3d7u, 0xd91d232eu, 0x2u };
+    const uint32_t mb1[4] = { 0x7d4f1128u, 0x8211bbebu, 0xeeb859fcu, 0x6f4d8248u };
+    const uint32_t b2c[2] = { 0x94d213e3u, 0x89d32568u };
+    uint32_t w1[11], w2[13];
+    mul_wide<8, 3>(k.v, g2c, w1); // c1 = (g2 * k) >> 256 = w1[8..10]
+    mul_wide<8, 5>(k.v, g1c, w2); // c2 = (g1 * k) >> 256 = w2[8..12]
+    uint32_t q1w[7], q2w[7];
+    mul_wide<3, 4>(w1 + 8, mb1, q1w); // q1 = c1 * (-b1)
+    mul_wide<5, 2>(w2 + 8, b2c, q2w); // q2 = c2 * b2
+    fe q1 = Fr::zero(), q2 = Fr::zero();
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+    {
+        q1.v[i] = q1w[i];
+        q2.v[i] = q2w[i];
+    }
+    // t1 = q2 - q1 (+p on borrow)  : __sub, field_impl_int128.tcc:40-54
+    fe t1, t1p;
+    uint32_t pl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pl[i] = FrParams::P(i);
+    const uint32_t borrow = cc::sub8(t1.v, q2.v, q1.v);
+    cc::add8(t1p.v, t1.v, pl);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t1.v[i] = borrow ? t1p.v[i] : t1.v[i];
+    // t2 = t1 * lambda (Montgomery product with lambda in Montgomery form = plain product), then k + t2 reduced once
+    fe t2 = Fr::mul_full(t1, Fr::constant([](int i) { return FrParams::CUBE(i); }));
+    fe s;
+    cc::add8(s.v, k.v, t2.v);
+    s = Fr::reduce(s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        k1[i] = s.v[i];
+        k2[i] = t1.v[i];
+    }
+}
+
+// c bits of a 128-bit value starting at bit `pos` (bits beyond 127 read as zero)
+BBG_HD uint32_t window_bits(const uint32_t k[4], int pos, int c)
+{
+    const int word = pos >> 5, shift = pos & 31;
+    uint64_t lo = word < 4 ? k[word] : 0u;
+    uint64_t hi = word + 1 < 4 ? k[word + 1] : 0u;
+    const uint64_t v = (lo | (hi << 32)) >> shift;
+    return (uint32_t)v & ((1u << c) - 1u);
+}
+
+// ---- 1. digits -------------------------------------------------------------------------------------
+__global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uint32_t NB, uint32_t* digits, uint32_t* counts)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe k = Fr::from_mont(load_fe(scalars + i)); // scalar_multiplication.cpp:469-472
+    uint32_t half[2][4];
+    split_endo(k, half[0], half[1]);
+    const size_t num_points = 2 * n;
+    uint32_t carry[2] = { 0, 0 };
+    for (int w = 0; w < W; ++w)
+    {
+        uint32_t packed[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+            uint32_t d = window_bits(half[h], w * c, c) + carry[h];
+            uint32_t neg = 0;
+            carry[h] = 0;
+            if (w + 1 < W && d > NB)
+            {
+                d = (1u << c) - d;
+                neg = 0x80000000u;
+                carry[h] = 1;
+            }
+            if (d != 0)
+            {
+                // a top-window digit above NB cannot occur for half scalars < 2^127 (the reference's wNAF makes the
+                // same assumption, wnaf.hpp:11); clamp defensively so no bucket index is ever out of range
+                if (d > NB) d = NB;
+                packed[h] = (d - 1) | neg;
+                atomicAdd(&counts[(size_t)w * NB + (d - 1)], 1u);
+            }
+            else
+            {
+                packed[h] = NO_DIGIT;
+            }
+        }
+        uint2 pair;
+        pair.x = packed[0];
+        pair.y = packed[1];
+        *(uint2*)(digits + (size_t)w * num_points + 2 * i) = pair;
+    }
+}
+
+// ---- 2. scan (three small kernels; counts -> exclusive offsets, offsets[total] = number of entries) ---
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8; // per thread
+__global__ void scan_block_sums_kernel(const uint32_t* in, uint32_t count, uint32_t* block_sums)
+{
+    __shared__ uint32_t red[SCAN_BLOCK];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+    {
+        if (base + i < count) s += in[base + i];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = SCAN_BLOCK / 2; off > 0; off >>= 1)
+    {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = red[0];
+}
+// single block: exclusive scan of block_sums in place, total appended at block_sums[num_blocks]
+__global__ void scan_spine_kernel(uint32_t* block_sums, uint32_t num_blocks)
+{
+    __shared__ uint32_t buf[SCAN_BLOCK];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < num_blocks; base += SCAN_BLOCK)
+    {
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t v = idx < num_blocks ? block_sums[idx] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < SCAN_BLOCK; off <<= 1) // Hillis-Steele inclusive scan
+        {
+            uint32_t add = (int)threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += add;
+            __syncthreads();
+        }
+        const uint32_t incl = buf[threadIdx.x];
+        const uint32_t start = running;
+        if (idx < num_blocks) block_sums[idx] = start + incl - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) running = start + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[num_blocks] = running;
+}
+__global__ void scan_apply_kernel(const uint32_t* in, uint32_t count, const uint32_t* block_sums, uint32_t* out)
+{
+    __shared__ uint32_t buf[SCAN_BLOCK];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + threadIdx.x * SCAN_ITEMS;
+    uint32_t local[SCAN_ITEMS];
+    uint32_t s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+    {
+        local[i] = base + i < count ? in[base + i] : 0;
+        s += local[i];
+    }
+    buf[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < SCAN_BLOCK; off <<= 1)
+    {
+        uint32_t add = (int)threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
+        __syncthreads();
+        buf[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = block_sums[blockIdx.x] + buf[threadIdx.x] - s;
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+    {
+        if (base + i < count) out[base + i] = run;
+        run += local[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_BLOCK - 1) out[count] = block_sums[gridDim.x];
+}
+
+// ---- 3. scatter ------------------------------------------------------------------------------------
+__global__ void msm_scatter_kernel(const uint32_t* digits, size_t num_points, int W, uint32_t NB, const uint32_t* offsets,
+                                   uint32_t* fill, uint32_t* sorted)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= num_points * (size_t)W) return;
+    const uint32_t d = digits[e];
+    if (d == NO_DIGIT) return;
+    const size_t w = e / num_points;
+    const uint32_t j = (uint32_t)(e - w * num_points);
+    const size_t b = w * NB + (d & 0x7fffffffu);
+    const uint32_t pos = offsets[b] + atomicAdd(&fill[b], 1u);
+    sorted[pos] = j | (d & 0x80000000u);
+}
+
+// ---- 4. accumulate ---------------------------------------------------------------------------------
+BBG_D affine_pt fetch_point(const fe* table, uint32_t entry)
+{
+    affine_pt p = load_affine(table + 2 * (size_t)(entry & 0x7fffffffu));
+    if (entry >> 31) p.y = Fq::neg(p.y);
+    return p;
+}
+
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* sorted, const uint32_t* offsets, uint32_t total_buckets,
+                                                            const fe* table, uint32_t S, fe* buckets, fe* head, fe* tail)
+{
+    const uint32_t E = offsets[total_buckets];
+    const size_t slice = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t start64 = slice * S;
+    if (start64 >= E) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (E - start < S) ? E : start + S;
+    // bucket containing `start`: offsets[b] <= start < offsets[b+1]
+    uint32_t lo = 0, hi = total_buckets; // invariant: offsets[lo] <= start < offsets[hi]
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    uint32_t bucket_end = offsets[b + 1];
+    bool is_head = offsets[b] < start;
+    xyzz_pt acc = G1::infinity();
+    affine_pt next = fetch_point(table, sorted[start]);
+    for (uint32_t i = start; i < end; ++i)
+    {
+        if (i == bucket_end)
+        {
+            store_xyzz(is_head ? head + 4 * slice : buckets + 4 * (size_t)b, acc);
+            acc = G1::infinity();
+            is_head = false;
+            do
+            {
+                ++b;
+                bucket_end = offsets[b + 1];
+            } while (bucket_end == i); // skip empty buckets
+        }
+        const affine_pt cur = next;
+        if (i + 1 < end) next = fetch_point(table, sorted[i + 1]);
+        acc = G1::madd(acc, cur);
+    }
+    fe* dst;
+    if (is_head) dst = head + 4 * slice;              // bucket began before this slice
+    else if (bucket_end <= end) dst = buckets + 4 * (size_t)b; // complete inside the slice
+    else dst = tail + 4 * slice;                      // continues into the next slice
+    store_xyzz(dst, acc);
+}
+
+// ---- 5. fix-up of buckets that span slices; empty buckets become infinity ----------------------------
+__global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets, uint32_t S, fe* buckets, const fe* head, const fe* tail)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+    if (o0 == o1)
+    {
+        store_xyzz(buckets + 4 * (size_t)b, G1::infinity());
+        return;
+    }
+    const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
+    if (s0 == s1) return;
+    xyzz_pt sum = load_xyzz(tail + 4 * (size_t)s0);
+    for (uint32_t s = s0 + 1; s <= s1; ++s) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
+    store_xyzz(buckets + 4 * (size_t)b, sum);
+}
+
+// ---- 6a. chunk running sums: A_t = sum_v B, V_t = sum_v v * B  (v = 0 .. 2^chunk_log - 1) ---------------
+__global__ void __launch_bounds__(128) msm_chunk_kernel(const fe* buckets, uint32_t total_chunks, int chunk_log, fe* A, fe* V)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_chunks) return;
+    const fe* base = buckets + 4 * ((size_t)t << chunk_log);
+    xyzz_pt run = G1::infinity(), acc = G1::infinity();
+    for (int v = (1 << chunk_log) - 1; v >= 1; --v)
+    {
+        run = G1::add(run, load_xyzz(base + 4 * v));
+        acc = G1::add(acc, run);
+    }
+    run = G1::add(run, load_xyzz(base));
+    store_xyzz(A + 4 * (size_t)t, run);
+    store_xyzz(V + 4 * (size_t)t, acc);
+}
+
+// ---- 6b. block tree reductions: out[w][r] -------------------------------------------------------------
+// r < chunk_bits : sum of A_t over chunks t of window w with bit r set
+// r = chunk_bits : sum of V_t;   r = chunk_bits + 1 : sum of A_t
+constexpr int RED_BLOCK = 128;
+__global__ void __launch_bounds__(RED_BLOCK) msm_reduce_kernel(const fe* A, const fe* V, uint32_t chunks_per_window, int chunk_bits, fe* out)
+{
+    __shared__ uint32_t sm[RED_BLOCK * 32];
+    const int r = blockIdx.x, w = blockIdx.y;
+    const fe* src = (r == chunk_bits ? V : A) + 4 * (size_t)w * chunks_per_window;
+    xyzz_pt sum = G1::infinity();
+    for (uint32_t t = threadIdx.x; t < chunks_per_window; t += RED_BLOCK)
+    {
+        if (r < chunk_bits && !((t >> r) & 1u)) continue;
+        sum = G1::add(sum, load_xyzz(src + 4 * (size_t)t));
+    }
+    for (int off = RED_BLOCK / 2; off > 0; off >>= 1)
+    {
+        __syncthreads();
+        if ((int)threadIdx.x >= off && (int)threadIdx.x < 2 * off) store_xyzz(sm + 32 * (threadIdx.x - off), sum);
+        __syncthreads();
+        if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
+    }
+    if (threadIdx.x == 0) store_xyzz(out + 4 * ((size_t)w * (chunk_bits + 2) + r), sum);
+}
+
+// table[2i] = P_i, table[2i+1] = (beta x_i, -y_i)   (scalar_multiplication.cpp:131-140)
+__global__ void endo_table_kernel(const fe* points, fe* table, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const affine_pt p = load_affine(points + 2 * i);
+    store_affine(table + 4 * i, p);
+    store_affine(table + 4 * i + 2, G1::endo_table_entry(p));
+}
+} // namespace msmk
+
+// ================================================================================================
+// Host driver
+// ================================================================================================
+namespace
+{
+using namespace msmk;
+size_t g_msm_launches = 0;
+
+struct Workspace
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) bbg_rt::dev_free(p);
+        p = nullptr;
+        bytes = 0;
+        const int e = bbg_rt::dev_alloc(&p, need);
+        if (e == 0) bytes = need;
+        return e;
+    }
+} g_ws;
+
+int pick_window_bits(size_t n)
+{
+    // cost model: W * (2n * 10 + 2^(c-1) * ~45) field products with W = ceil(128 / c); flat optimum near log2(2n) - 5
+    int lg = 0;
+    while (((size_t)1 << lg) < 2 * n) ++lg;
+    int c = lg - 5;
+    if (c < 5) c = 5;
+    if (c > 22) c = 22;
+    return c;
+}
+
+Plan make_plan(size_t n)
+{
+    Plan pl;
+    pl.n = n;
+    pl.num_points = 2 * n;
+    pl.c = pick_window_bits(n);
+    pl.W = (128 + pl.c - 1) / pl.c;
+    pl.NB = 1u << (pl.c - 1);
+    pl.total_buckets = pl.NB * (uint32_t)pl.W;
+    pl.max_entries = pl.num_points * (size_t)pl.W;
+    pl.S = pl.max_entries >= ((size_t)1 << 26) ? 128 : (pl.max_entries >= ((size_t)1 << 20) ? 64 : 16);
+    pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
+    pl.chunk_log = CHUNK_LOG < pl.c - 1 ? CHUNK_LOG : pl.c - 1;
+    pl.chunks_per_window = pl.NB >> pl.chunk_log;
+    int bits = 0;
+    while ((1u << bits) < pl.chunks_per_window) ++bits;
+    pl.reduce_outputs = bits + 2;
+    return pl;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+} // namespace
+
+size_t msm_launch_count() { return g_msm_launches; }
+int msm_release_workspace()
+{
+    if (g_ws.p) bbg_rt::dev_free(g_ws.p);
+    g_ws.p = nullptr;
+    g_ws.bytes = 0;
+    return 0;
+}
+
+// d_out_xyzz: HOST buffer of 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sum
+int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t st)
+{
+    hostg1::hxyzz result = hostg1::infinity();
+    if (n == 0)
+    {
+        memcpy(out_xyzz_host, &result, sizeof result);
+        return 0;
+    }
+    if (2 * n > ((size_t)1 << 28)) return 1008;
+    const Plan pl = make_plan(n);
+    if (pl.max_entries >= ((size_t)1 << 32)) return 1008;
+
+    // carve the workspace
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    const size_t o_digits = carve(pl.max_entries * 4);
+    const size_t o_sorted = carve(pl.max_entries * 4 + 16);
+    const size_t o_counts = carve((size_t)pl.total_buckets * 4);
+    const size_t o_fill = carve((size_t)pl.total_buckets * 4);
+    const size_t o_offsets = carve(((size_t)pl.total_buckets + 1) * 4);
+    const uint32_t scan_blocks = (pl.total_buckets + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    const size_t o_spine = carve(((size_t)scan_blocks + 1) * 4);
+    const size_t o_buckets = carve((size_t)pl.total_buckets * 128);
+    const size_t o_head = carve(pl.max_slices * 128);
+    const size_t o_tail = carve(pl.max_slices * 128);
+    const uint32_t total_chunks = pl.chunks_per_window * (uint32_t)pl.W;
+    const size_t o_A = carve((size_t)total_chunks * 128);
+    const size_t o_V = carve((size_t)total_chunks * 128);
+    const size_t red_count = (size_t)pl.W * pl.reduce_outputs;
+    const size_t o_red = carve(red_count * 128);
+    BBG_CHECK(g_ws.ensure(off));
+    char* ws = (char*)g_ws.p;
+    uint32_t* digits = (uint32_t*)(ws + o_digits);
+    uint32_t* sorted = (uint32_t*)(ws + o_sorted);
+    uint32_t* counts = (uint32_t*)(ws + o_counts);
+    uint32_t* fill = (uint32_t*)(ws + o_fill);
+    uint32_t* offsets = (uint32_t*)(ws + o_offsets);
+    uint32_t* spine = (uint32_t*)(ws + o_spine);
+    fe* buckets = (fe*)(ws + o_buckets);
+    fe* head = (fe*)(ws + o_head);
+    fe* tail = (fe*)(ws + o_tail);
+    fe* A = (fe*)(ws + o_A);
+    fe* V = (fe*)(ws + o_V);
+    fe* red = (fe*)(ws + o_red);
+
+    // counts and fill are adjacent: one memset
+    BBG_CHECK(bbg_rt::dev_memset(counts, 0, (o_fill - o_counts) + (size_t)pl.total_buckets * 4, st));
+    BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars, n, pl.c, pl.W, pl.NB, digits, counts);
+    BBG_LAUNCH(scan_block_sums_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, spine);
+    BBG_LAUNCH(scan_spine_kernel, dim3(1), dim3(SCAN_BLOCK), 0, st, spine, scan_blocks);
+    BBG_LAUNCH(scan_apply_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, (const uint32_t*)spine, offsets);
+    BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, pl.num_points, pl.W, pl.NB,
+                      (const uint32_t*)offsets, fill, sorted);
+    BBG_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((unsigned)((pl.max_slices + 127) / 128)), dim3(128), st, (const uint32_t*)sorted, (const uint32_t*)offsets,
+                      pl.total_buckets, (const fe*)d_table, pl.S, buckets, head, tail);
+    BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, (const uint32_t*)offsets, pl.total_buckets, pl.S, buckets,
+                      (const fe*)head, (const fe*)tail);
+    BBG_LAUNCH_NOSYNC(msm_chunk_kernel, dim3((total_chunks + 127) / 128), dim3(128), st, (const fe*)buckets, total_chunks, pl.chunk_log, A, V);
+    BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.W), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V, pl.chunks_per_window,
+               pl.reduce_outputs - 2, red);
+    g_msm_launches += 9;
+    BBG_CHECK(bbg_rt::last_error());
+
+    // ---- 7. host finish -----------------------------------------------------------------------------
+    std::vector<hostg1::hxyzz> r(red_count);
+    BBG_CHECK(bbg_rt::d2h(r.data(), red, red_count * 128, st));
+    BBG_CHECK(bbg_rt::sync(st));
+    const int bits = pl.reduce_outputs - 2;
+    for (int w = pl.W - 1; w >= 0; --w)
+    {
+        const hostg1::hxyzz* rw = r.data() + (size_t)w * pl.reduce_outputs;
+        // sum_t t * A_t = sum_r 2^r T_r   (Horner from the top bit)
+        hostg1::hxyzz tsum = hostg1::infinity();
+        for (int b = bits - 1; b >= 0; --b)
+        {
+            tsum = hostg1::dbl(tsum);
+            tsum = hostg1::add(tsum, rw[b]);
+        }
+        for (int i = 0; i < pl.chunk_log; ++i) tsum = hostg1::dbl(tsum); // * chunk size
+        // bucket value = t * chunk + v + 1
+        hostg1::hxyzz sw = hostg1::add(hostg1::add(tsum, rw[bits]), rw[bits + 1]);
+        // result = 2^c * result + S_w   (reference :619-639, here with plain c-bit windows)
+        for (int i = 0; i < pl.c; ++i) result = hostg1::dbl(result);
+        result = hostg1::add(result, sw);
+    }
+    memcpy(out_xyzz_host, &result, sizeof result);
+    return 0;
+}
+
+int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    BBG_LAUNCH_NOSYNC(endo_table_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_points, (fe*)d_table, n);
+    ++g_msm_launches;
+    return bbg_rt::last_error();
+}
+} // namespace bbg

@@ -1,0 +1,64 @@
+// Thin runtime seam between the C-ABI driver code and CUDA.
+//
+// Product build (nvcc): real CUDA runtime calls and <<<>>> launches.
+// Emulation build (g++ -DBBG_EMULATE, tests/emul only): the same driver code runs its kernels on CPU
+// threads through tests/emul/cuda_emul.h so index logic can be checked without a GPU.  The emulation
+// is test infrastructure; libbbgpu.so is never built with BBG_EMULATE.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef BBG_EMULATE
+#include "cuda_emul.h"
+#include <stdio.h>
+
+#define BBG_LAUNCH(kernel, grid, block, smem, stream, ...) emul::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define BBG_LAUNCH_NOSYNC(kernel, grid, block, stream, ...) emul::launch_nosync((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#define BBG_DYN_SMEM(name) unsigned char* name = emul::t_dyn_smem
+#define BBG_CONSTANT static const
+
+namespace bbg_rt
+{
+inline int dev_alloc(void** p, size_t bytes) { *p = aligned_alloc(256, ((bytes + 255) / 256 + 1) * 256); return *p ? 0 : 2; }
+inline int dev_free(void* p) { free(p); return 0; }
+inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t) { memcpy(d, h, bytes); return 0; }
+inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t) { memcpy(h, d, bytes); return 0; }
+inline int d2d(void* d, const void* s, size_t bytes, cudaStream_t) { memmove(d, s, bytes); return 0; }
+inline int dev_memset(void* d, int v, size_t bytes, cudaStream_t) { memset(d, v, bytes); return 0; }
+inline int sync(cudaStream_t) { return 0; }
+inline int last_error() { return 0; }
+inline int num_sms() { return 4; }
+inline int set_smem_limit(const void*, size_t) { return 0; }
+} // namespace bbg_rt
+
+#else
+#include <cuda_runtime.h>
+
+#define BBG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define BBG_LAUNCH_NOSYNC(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define BBG_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define BBG_CONSTANT __device__ __constant__
+
+namespace bbg_rt
+{
+inline int dev_alloc(void** p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 256); }
+inline int dev_free(void* p) { return (int)cudaFree(p); }
+inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t s) { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s); }
+inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t s) { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s); }
+inline int d2d(void* d, const void* s_, size_t bytes, cudaStream_t s) { return (int)cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s); }
+inline int dev_memset(void* d, int v, size_t bytes, cudaStream_t s) { return (int)cudaMemsetAsync(d, v, bytes, s); }
+inline int sync(cudaStream_t s) { return (int)cudaStreamSynchronize(s); }
+inline int last_error() { return (int)cudaGetLastError(); }
+inline int num_sms()
+{
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+inline int set_smem_limit(const void* fn, size_t bytes)
+{
+    return (int)cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+} // namespace bbg_rt
+#endif

@@ -1,0 +1,116 @@
+/* bbgpu — C ABI of the B200-native MSM / NTT library (libbbgpu.so).
+ *
+ * This is the drop-in boundary for the two data-parallel hot paths of the Barretenberg "waffle" PLONK
+ * prover.  The reference has no FFI layer: its boundary is the set of free C++ functions below, which
+ * the shim sources under barretenberg_b200/shim/ re-define with identical signatures and forward here.
+ * Citations are relative to /root/reference/src/barretenberg/.
+ *
+ *   curves/bn254/scalar_multiplication.hpp:60-61   g1::element pippenger(fr::field_t*, g1::affine_element*, size_t, size_t)
+ *   curves/bn254/scalar_multiplication.hpp:88-96   void batched_scalar_multiplications(multiplication_state*, size_t)
+ *   curves/bn254/scalar_multiplication.hpp:41      void generate_pippenger_point_table(affine*, affine*, size_t)
+ *   polynomials/polynomial_arithmetic.hpp:28-39    fft / ifft / coset_fft / coset_ifft / fft_with_constant /
+ *                                                  ifft_with_constant / coset_fft_with_constant
+ *
+ * Data conventions (identical to the reference):
+ *   field element  = 4 x uint64 little-endian limbs, Montgomery form (R = 2^256), 32 bytes
+ *   affine point   = x, y                      (64 bytes); infinity <=> bit 63 of y limb 3
+ *   Jacobian point = x, y, z                   (96 bytes)
+ *   point table    = 2n affine entries [P_0, phi(P_0), P_1, phi(P_1), ...], phi(x,y) = (beta x, -y)
+ *   NTT            : natural order in/out, in place, outputs canonical in [0,p); inputs may be in [0,2p)
+ *   MSM            : scalars may be in [0,2p); output normalised (z = fq::one, x,y canonical) or the
+ *                    infinity flag set — the form batched_scalar_multiplications leaves in .output
+ *
+ * Every function returns 0 on success, a cudaError_t value (< 1000) or a BBG_E_* code otherwise.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point fails.
+ * The library is not re-entrant; calls are serialised by an internal mutex (the reference's callers are
+ * single-threaded, scalar_multiplication.cpp:731 keeps its OpenMP region inside the callee).
+ */
+#ifndef BBGPU_H
+#define BBGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBG_E_BAD_SIZE 1002      /* NTT: log2_n outside [1, 22] */
+#define BBG_E_BAD_OP 1003
+#define BBG_E_NULL_CONSTANT 1004
+#define BBG_E_NOT_INITIALISED 1005
+#define BBG_E_NO_DEVICE 1006
+#define BBG_E_BAD_ARGUMENT 1007
+#define BBG_E_TOO_LARGE 1008     /* MSM: more than 2^27 table entries */
+
+/* NTT operation selector == the reference entry point being replaced */
+enum bbg_ntt_op
+{
+    BBG_FFT = 0,                     /* polynomial_arithmetic.cpp:266-269 */
+    BBG_IFFT = 1,                    /* :271-277 */
+    BBG_COSET_FFT = 2,               /* :287-291 */
+    BBG_COSET_IFFT = 3,              /* :311-315 */
+    BBG_FFT_WITH_CONSTANT = 4,       /* :279-285 */
+    BBG_IFFT_WITH_CONSTANT = 5,      /* :301-309 */
+    BBG_COSET_FFT_WITH_CONSTANT = 6, /* :293-299 */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int bbg_init(int device);            /* select device, create the work stream; idempotent */
+int bbg_shutdown(void);              /* free tables, caches, workspace */
+int bbg_set_stream(void* cuda_stream); /* run on a caller-owned cudaStream_t (e.g. torch's current stream) */
+const char* bbg_error_string(int code);
+uint64_t bbg_launch_count(void);     /* kernels launched by this library so far (bench.py: gpu_launches) */
+
+/* ---- NTT, host buffers (what the shims call) ------------------------------------------------- */
+/* coeffs: n = 2^log2_n field elements, transformed in place.  constant: one field element, used by the
+ * *_WITH_CONSTANT ops, ignored (may be NULL) otherwise. */
+int bbg_ntt_fr(uint64_t* coeffs, unsigned log2_n, int op, const uint64_t* constant);
+/* batch independent polynomials of the same size (prover wire / permutation / quotient polynomials) */
+int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, int op, const uint64_t* constant);
+
+/* ---- NTT, device-resident --------------------------------------------------------------------- */
+/* d_coeffs: device pointer to `batch` polynomials, `stride_elems` field elements apart, in place */
+int bbg_ntt_fr_dev(void* d_coeffs, size_t stride_elems, size_t batch, unsigned log2_n, int op, const uint64_t* constant);
+
+/* ---- MSM ------------------------------------------------------------------------------------- */
+/* Register a 2n-entry point table (reference_string.cpp:20-23 owns it for the prover's lifetime): uploaded
+ * once; later MSM calls whose `points` pointer lies inside [table, table + 2n) reuse the device copy
+ * (batched_scalar_multiplications passes &points[2 * offset], scalar_multiplication.cpp:720-723). */
+int bbg_srs_register(const uint64_t* table_2n, size_t n);
+int bbg_srs_unregister(const uint64_t* table_2n);
+/* sum_i scalars[i] * P_i over table entries points_table[0 .. 2n); out_xyz = 12 limbs, normalised */
+int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, uint64_t out_xyz[12]);
+/* `batches` MSMs of the same size n (multiplication_state[], scalar_multiplication.hpp:88-94) */
+int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* points_tables, size_t n, size_t batches,
+                       uint64_t* out_xyz /* batches x 12 */);
+/* device-resident: d_scalars (n x 32 B) and d_table (2n x 64 B) already in HBM; result to host */
+int bbg_msm_g1_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyz[12]);
+/* multi-GPU building blocks: a rank's un-normalised partial (16 limbs: X, Y, ZZ, ZZZ with x = X/ZZ,
+ * y = Y/ZZZ; ZZ = 0 <=> infinity) and the final fold of gathered partials into a normalised point */
+int bbg_msm_g1_partial_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyzz[16]);
+int bbg_g1_fold_partials(const uint64_t* partials_xyzz /* count x 16 */, size_t count, uint64_t out_xyz[12]);
+/* table[2i] = points[i], table[2i+1] = (beta x_i, -y_i): the layout of generate_pippenger_point_table
+ * (scalar_multiplication.cpp:131-140) computed on the device; table may alias points */
+int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table_2n, size_t n);
+
+/* ---- device memory helpers (tests, bench, device-resident callers) ---------------------------- */
+int bbg_dev_alloc(void** d_ptr, size_t bytes);
+int bbg_dev_free(void* d_ptr);
+int bbg_copy_h2d(void* d_dst, const void* h_src, size_t bytes);
+int bbg_copy_d2h(void* h_dst, const void* d_src, size_t bytes);
+int bbg_sync(void);
+/* CUDA-event stopwatch on the library's work stream */
+int bbg_timer_start(void);
+int bbg_timer_stop(float* elapsed_ms);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* Dependency-free integer multiply-add throughput on all SMs: the IMAD roofline denominator.
+ * mode 0: mad.lo.u32   1: mad.wide.u32 (64-bit accumulate)   2: carry-chained mad.lo.cc/madc.hi.cc pairs
+ *      3: Fq Montgomery products (reports field products/s)   4: Fr Montgomery products
+ * ops_per_second: 32x32 multiply-adds (modes 0-2) or field products (3-4) per second. */
+int bbg_microbench(int mode, int iters, double* ops_per_second, float* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

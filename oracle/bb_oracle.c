@@ -573,6 +573,27 @@ void orc_g1_scalar_mul(const uint64_t* affine, const uint64_t* scalar_mont, uint
     memcpy(out, acc, 64);
 }
 
+void orc_g1_arith_progression(const uint64_t* start_mont, const uint64_t* step_mont, uint64_t* out, size_t n)
+{
+    if (n == 0) return;
+    uint64_t gen[8], base[8], step[8];
+    memcpy(gen, FQ->one, 32);
+    memcpy(gen + 4, G1_ONE_Y, 32);
+    orc_g1_scalar_mul(gen, start_mont, base);
+    orc_g1_scalar_mul(gen, step_mont, step);
+    uint64_t* acc = malloc(96 * n);
+    memcpy(acc, base, 64);
+    memcpy(acc + 8, FQ->one, 32);
+    for (size_t i = 1; i < n; ++i)
+    {
+        if (pt_is_inf(step)) memcpy(acc + 12 * i, acc + 12 * (i - 1), 96);
+        else orc_g1_mixed_add(acc + 12 * (i - 1), step, acc + 12 * i);
+    }
+    orc_g1_batch_normalize(acc, n);
+    for (size_t i = 0; i < n; ++i) memcpy(out + 8 * i, acc + 12 * i, 64);
+    free(acc);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* MSM: curves/bn254/scalar_multiplication.cpp                                                 */
 /* ------------------------------------------------------------------------------------------ */

@@ -9,7 +9,7 @@
  *   (1) the reference's own known-answer vectors (tests/golden/reference_kats.json, restated from
  *       /root/reference/test/test_fq.cpp, test_fr.cpp, test_g1.cpp, test_wnaf.cpp), and
  *   (2) the unmodified reference compiled by oracle/Makefile into oracle/_ref/libbb_ref.so, on
- *       seeded inputs, limb for limb (also frozen into tests/golden/*.npz by
+ *       seeded inputs, limb for limb (also frozen into tests/golden/ref_vectors.npz by
  *       tests/golden/make_golden.py so the check survives on machines without the reference).
  *
  * Conventions: field element = 4 x uint64 little-endian limbs, Montgomery form with
@@ -59,6 +59,9 @@ void orc_g1_batch_normalize(uint64_t* pts, size_t n);
 /* value-equivalent (plain double-and-add, NOT the reference's endo-wNAF ladder): affine k*P */
 void orc_g1_scalar_mul(const uint64_t affine[8], const uint64_t scalar_mont[4], uint64_t out_affine[8]);
 int  orc_g1_on_curve(const uint64_t affine[8]);
+/* out[i] = (start + i*step) * G, i < n, normalised affine — the synthetic point sets of SURVEY.md §8c-3
+ * (repeated mixed_add + one batch_normalize, like ref_g1_arith_progression in ref_capi.cpp) */
+void orc_g1_arith_progression(const uint64_t start_mont[4], const uint64_t step_mont[4], uint64_t* out_affine, size_t n);
 
 /* ---- MSM: curves/bn254/scalar_multiplication.cpp ------------------------------------------- */
 size_t orc_get_optimal_bucket_width(size_t n);                                             /* :21-81 */

@@ -64,6 +64,7 @@ def oracle():
         lib.orc_pow_small.argtypes = [C.c_int, u64p, C.c_uint64, u64p]
         lib.orc_g1_batch_normalize.argtypes = [u64p, C.c_size_t]
         lib.orc_poly_evaluate.argtypes = [u64p, u64p, C.c_size_t, u64p]
+        lib.orc_g1_arith_progression.argtypes = [u64p, u64p, u64p, C.c_size_t]
         _oracle = lib
     return _oracle
 
@@ -188,26 +189,35 @@ def generator_multiples_table(seed, n):
 
 def arithmetic_progression_points(a0, d, n):
     """(n,8) affine points (a0 + i d) G using oracle mixed adds + one batch normalisation."""
+    out = np.zeros((n, 8), dtype=np.uint64)
+    if n:
+        oracle().orc_g1_arith_progression(ptr(to_limbs(mont(a0))), ptr(to_limbs(mont(d))), ptr(out), n)
+    return out
+
+
+def closed_form_msm(scalars, a0, d):
+    """Normalised Jacobian of sum_i k_i (a0 + i d) G = ((sum_i k_i (a0 + i d)) mod r) G  (SURVEY.md §8c-3):
+    one Fr dot product and one oracle scalar multiplication — no CPU MSM needed at 2^20 / 2^26."""
     lib = oracle()
-    if n == 0:
-        return np.zeros((0, 8), dtype=np.uint64)
+    n = scalars.shape[0]
+    rinv = pow(R_MONT, -1, FR_MODULUS)
+    raw = np.ascontiguousarray(scalars).view(np.uint8).reshape(n, 32)
+    acc = 0
+    a = a0
+    for i in range(n):
+        acc += int.from_bytes(raw[i].tobytes(), "little") * a
+        a += d
+    s = (acc * rinv) % FR_MODULUS  # scalars are Montgomery residues: value = limbs * R^-1
     gen = np.zeros(8, dtype=np.uint64)
     tmp = np.zeros(4, dtype=np.uint64)
     lib.orc_constant(11, ptr(tmp)); gen[:4] = tmp
     lib.orc_constant(12, ptr(tmp)); gen[4:] = tmp
-    base = np.zeros(8, dtype=np.uint64)
-    step = np.zeros(8, dtype=np.uint64)
-    lib.orc_g1_scalar_mul(ptr(gen), ptr(to_limbs(mont(a0))), ptr(base))
-    lib.orc_g1_scalar_mul(ptr(gen), ptr(to_limbs(mont(d))), ptr(step))
-    jac = np.zeros((n, 12), dtype=np.uint64)
-    one = np.zeros(4, dtype=np.uint64)
-    lib.orc_constant(2, ptr(one))
-    jac[0, :8] = base
-    jac[0, 8:] = one
-    for i in range(1, n):
-        lib.orc_g1_mixed_add(ptr(jac[i - 1]), ptr(step), ptr(jac[i]))
-    lib.orc_g1_batch_normalize(ptr(jac), n)
-    return np.ascontiguousarray(jac[:, :8])
+    res = np.zeros(8, dtype=np.uint64)
+    lib.orc_g1_scalar_mul(ptr(gen), ptr(to_limbs(mont(s))), ptr(res))
+    out = np.zeros(12, dtype=np.uint64)
+    out[:8] = res
+    lib.orc_constant(2, ptr(tmp)); out[8:] = tmp
+    return out
 
 
 def is_infinity(pt):

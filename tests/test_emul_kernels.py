@@ -1,0 +1,147 @@
+"""CPU tests of the kernel logic: the SAME kernel sources as libbbgpu.so compiled with g++ -DBBG_EMULATE
+(tests/emul/cuda_emul.h runs each CUDA thread as an OS thread) and driven through the same C ABI, compared
+with the oracle.  This is test infrastructure for a GPU-less box — the product never loads this library."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import barretenberg_b200 as bb
+import helpers as H
+
+ROOT = H.ROOT
+EMUL_SO = os.path.join(ROOT, "tests", "emul", "libbbgpu_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(ROOT, "barretenberg_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src) if f.endswith((".cu", ".cuh", ".h")))
+    if not os.path.exists(EMUL_SO) or os.path.getmtime(EMUL_SO) < newest:
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.check_call(["make", "-C", src, "emul"], env=env, stdout=subprocess.DEVNULL)
+    return bb.Library(EMUL_SO)
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 7, 11, 12, 13, 15])
+def test_ntt_all_ops_vs_oracle(emu, log_n):
+    n = 1 << log_n
+    od = H.OracleDomain(n)
+    x = H.random_scalars_mont(100 + log_n, n)
+    x[0] = H.to_limbs(H.from_limbs(x[0]) + H.FR_MODULUS)  # lazily reduced input (SURVEY §8 note 2)
+    k = H.random_scalars_mont(7, 1)[0]
+    for name, op in H.NTT_OPS.items():
+        got = emu.ntt(name, x.copy(), k)
+        assert (got == od.ntt(op, x, k)).all(), name
+
+
+def test_ntt_batched_and_golden(emu):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+    x = g["ntt_in"]
+    for name in H.NTT_OPS:
+        batch = np.stack([x, x[::-1].copy(), x]).copy()
+        emu.ntt(name, batch, g["ntt_constant"])
+        assert (batch[0] == g["ntt_" + name]).all() and (batch[2] == g["ntt_" + name]).all(), name
+
+
+@pytest.mark.slow
+def test_ntt_two_pass_every_subtransform_length(emu):
+    """2^17 and 2^18 exercise sub-transform lengths 8 and 9 in both passes (2^19..2^22 run on the GPU only)."""
+    for log_n in (14, 16, 17, 18):
+        n = 1 << log_n
+        od = H.OracleDomain(n)
+        x = H.random_scalars_mont(log_n, n)
+        for name in ("coset_fft", "coset_ifft"):
+            assert (emu.ntt(name, x.copy()) == od.ntt(H.NTT_OPS[name], x)).all(), (log_n, name)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 300, 1000, 3000])
+def test_msm_vs_oracle(emu, n):
+    table, _, _ = H.generator_multiples_table(900 + n, max(n, 1))
+    sc = H.random_scalars_mont(33 + n, n)
+    if n > 4:
+        sc[1] = 0
+        sc[2] = sc[3]
+        sc[4] = H.to_limbs(H.from_limbs(sc[4]) + H.FR_MODULUS)
+    got = emu.msm(sc, table, n)
+    exp = H.oracle_msm(sc, table)
+    if H.is_infinity(exp):
+        assert H.is_infinity(got)
+    else:
+        assert (got == exp).all()
+
+
+def test_msm_edge_cases(emu):
+    n = 200
+    table, a0, d = H.generator_multiples_table(11, n)
+    one = np.zeros(4, dtype=np.uint64)
+    H.oracle().orc_constant(6, H.ptr(one))
+    # all-zero scalars -> infinity (test_scalar_multiplication.cpp:140-162)
+    assert H.is_infinity(emu.msm(np.zeros((n, 4), dtype=np.uint64), table))
+    # all scalars equal to one: a single giant bucket spanning many slices
+    ones = np.tile(one, (n, 1))
+    assert (emu.msm(ones, table) == H.oracle_msm(ones, table)).all()
+    # P and -P pairs with equal scalars cancel: table of [P, -P, P, -P, ...]
+    pts = np.ascontiguousarray(table[0::2]).copy()
+    neg = np.zeros(4, dtype=np.uint64)
+    for i in range(1, n, 2):
+        pts[i, :4] = pts[i - 1, :4]
+        H.oracle().orc_neg(H.FQ, H.ptr(pts[i - 1, 4:].copy()), H.ptr(neg))
+        pts[i, 4:] = neg
+    t2 = emu.generate_pippenger_point_table(pts)
+    ref_t2 = np.zeros_like(t2)
+    H.oracle().orc_generate_pippenger_point_table(H.ptr(pts), H.ptr(ref_t2), n)
+    assert (t2 == ref_t2).all()
+    sc = H.random_scalars_mont(5, n)
+    sc[1::2] = sc[0::2]
+    assert H.is_infinity(emu.msm(sc, t2))
+    # repeated points with different scalars (P + P doubling path inside a bucket is possible)
+    pts2 = np.tile(pts[0], (n, 1))
+    t3 = emu.generate_pippenger_point_table(pts2)
+    sc = H.random_scalars_mont(6, n)
+    sc[:50] = sc[0]
+    assert (emu.msm(sc, t3) == H.oracle_msm(sc, t3)).all()
+    # closed form on generator multiples
+    sc = H.random_scalars_mont(8, n)
+    assert (emu.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+
+
+def test_batched_msm_and_srs_cache(emu):
+    n = 256
+    table, _, _ = H.generator_multiples_table(21, n)
+    keep = emu.srs_register(table)
+    scs = [H.random_scalars_mont(40 + i, n) for i in range(3)]
+    states = [bb.scalar_multiplication.MultiplicationState(points=keep, scalars=s, num_elements=n) for s in scs]
+    bb.scalar_multiplication.batched_scalar_multiplications(states, library=emu)
+    for st, s in zip(states, scs):
+        assert (st.output == H.oracle_msm(s, table)).all()
+    # sub-range call: &points[2 * offset] with its own scalar range (scalar_multiplication.cpp:720-723)
+    off, m = 64, 100
+    sub = keep[2 * off:]
+    got = emu.msm(scs[0][off:off + m], sub, m)
+    assert (got == H.oracle_msm(np.ascontiguousarray(scs[0][off:off + m]), np.ascontiguousarray(table[2 * off:2 * (off + m)]))).all()
+    emu.srs_unregister(keep)
+    with pytest.raises(ValueError):
+        bad = [bb.scalar_multiplication.MultiplicationState(points=table, scalars=scs[0], num_elements=n),
+               bb.scalar_multiplication.MultiplicationState(points=table, scalars=scs[1], num_elements=n - 1)]
+        bb.scalar_multiplication.batched_scalar_multiplications(bad, library=emu)
+
+
+def test_partials_fold(emu):
+    """The multi-GPU plan on one process: point-range shards -> XYZZ partials -> fold == whole MSM."""
+    n = 512
+    table, _, _ = H.generator_multiples_table(31, n)
+    sc = H.random_scalars_mont(32, n)
+    parts = []
+    for r in range(4):
+        lo, hi = r * n // 4, (r + 1) * n // 4
+        d_s = emu.dev_alloc((hi - lo) * 32)
+        d_t = emu.dev_alloc((hi - lo) * 128)
+        emu.h2d(d_s, sc[lo:hi])
+        emu.h2d(d_t, table[2 * lo:2 * hi])
+        parts.append(emu.msm_partial_dev(d_s, d_t, hi - lo))
+        emu.dev_free(d_s)
+        emu.dev_free(d_t)
+    assert (emu.fold_partials(np.stack(parts)) == H.oracle_msm(sc, table)).all()

@@ -1,0 +1,256 @@
+"""Parity tests proper: the CUDA path through the C ABI on a real B200 vs the oracle, the committed golden
+vectors (frozen reference outputs), the compiled reference (oracle/_ref, prebuilt) at large sizes, and
+size-independent properties at BASELINE.json's full sizes.  Bit-exact: integer arithmetic."""
+import os
+
+import numpy as np
+import pytest
+
+import barretenberg_b200 as bb
+import helpers as H
+from helpers import ptr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(H.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return bb.default_library()  # raises BbgError if libbbgpu.so or the GPU is missing: no fallback
+
+
+def ref_ntt(op, x, k=None):
+    """Compiled-reference NTT (multithreaded x86 asm) on a copy of x."""
+    r = H.ref()
+    n = x.shape[0]
+    rd = r.ref_domain_new(n)
+    buf = r.ref_aligned_alloc(32 * n)
+    view = np.ctypeslib.as_array((H.C.c_uint64 * (4 * n)).from_address(buf)).reshape(n, 4)
+    view[:] = x
+    r.ref_ntt(rd, op, buf, ptr(np.ascontiguousarray(k)) if k is not None else None)
+    out = view.copy()
+    r.ref_aligned_free(buf)
+    r.ref_domain_free(rd)
+    return out
+
+
+def ref_threads_pow2():
+    r = H.ref()
+    t = r.ref_omp_threads()
+    p = 1
+    while p * 2 <= t:
+        p *= 2
+    r.ref_set_omp_threads(p)  # evaluation_domain silently requires a power of two (SURVEY §5 hazard)
+    return p
+
+
+@pytest.mark.parametrize("log_n", list(range(1, 17)))
+def test_ntt_all_ops_vs_oracle(lib, log_n):
+    n = 1 << log_n
+    od = H.OracleDomain(n)
+    x = H.random_scalars_mont(100 + log_n, n)
+    x[0] = H.to_limbs(H.from_limbs(x[0]) + H.FR_MODULUS)
+    x[n // 2] = 0
+    k = H.random_scalars_mont(7, 1)[0]
+    for name, op in H.NTT_OPS.items():
+        got = lib.ntt(name, x.copy(), k)
+        assert (got == od.ntt(op, x, k)).all(), name
+
+
+def test_ntt_golden_reference_vectors(lib):
+    g = np.load(os.path.join(GOLD, "ref_vectors.npz"))
+    for name in H.NTT_OPS:
+        batch = np.stack([g["ntt_in"]] * 3).copy()
+        lib.ntt(name, batch, g["ntt_constant"])
+        for b in batch:
+            assert (b == g["ntt_" + name]).all(), name
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("log_n", [17, 18, 19, 20, 21, 22])
+def test_ntt_large_vs_compiled_reference(lib, log_n):
+    ref_threads_pow2()
+    n = 1 << log_n
+    x = H.random_scalars_mont(log_n, n)
+    k = H.random_scalars_mont(8, 1)[0]
+    ops = ["fft", "ifft", "coset_fft", "coset_ifft"] if log_n >= 21 else list(H.NTT_OPS)
+    for name in ops:
+        got = lib.ntt(name, x.copy(), k)
+        assert (got == ref_ntt(H.NTT_OPS[name], x, k)).all(), (log_n, name)
+
+
+@pytest.mark.parametrize("log_n", [20, 22])
+def test_ntt_properties_full_size(lib, log_n):
+    """Round trips, linearity and canonical outputs at the BASELINE sizes (no reference needed)."""
+    n = 1 << log_n
+    x = H.random_scalars_mont(1, n)
+    y = H.random_scalars_mont(2, n)
+    fx = lib.ntt("fft", x.copy())
+    assert (lib.ntt("ifft", fx.copy()) == x).all()
+    assert (lib.ntt("coset_ifft", lib.ntt("coset_fft", x.copy())) == x).all()
+    # canonical: every output < p  (top limb first)
+    p = H.to_limbs(H.FR_MODULUS)
+    top = fx[:, 3]
+    assert (top <= p[3]).all()
+    # linearity on a sample: fft(x + y) == fft(x) + fft(y)
+    s = np.zeros_like(x[:4096])
+    o = H.oracle()
+    xs, ys = x.copy(), y.copy()
+    sum_xy = np.zeros_like(x)
+    # add mod p with python ints on a strided sample is too slow at full size: use the oracle's batched mul trick
+    # (x + y) computed limb-wise in numpy with carry
+    carry = np.zeros(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(4):
+            t = xs[:, i] + ys[:, i]
+            c1 = (t < xs[:, i]).astype(np.uint64)
+            t2 = t + carry
+            c2 = (t2 < t).astype(np.uint64)
+            sum_xy[:, i] = t2
+            carry = c1 | c2
+    fs = lib.ntt("fft", sum_xy)  # inputs in [0,2p) are allowed
+    fy = lib.ntt("fft", y.copy())
+    idx = np.arange(0, n, n // 512)
+    for i in idx:
+        a = (H.from_limbs(fx[i]) + H.from_limbs(fy[i])) % H.FR_MODULUS
+        assert H.from_limbs(fs[i]) == a
+    del s, o
+
+
+def test_ntt_prover_pattern_coset_4n(lib):
+    """prover.cpp:418-425: low n coefficients non-zero, rest zero, coset_fft on the 4n domain; checked against
+    the oracle at n = 2^12 (4n = 2^14)."""
+    n = 1 << 12
+    x = np.zeros((4 * n, 4), dtype=np.uint64)
+    x[:n] = H.random_scalars_mont(3, n)
+    od = H.OracleDomain(4 * n)
+    assert (lib.ntt("coset_fft", x.copy()) == od.ntt(H.NTT_OPS["coset_fft"], x)).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 300, 1000, 4096, 10000])
+def test_msm_vs_oracle(lib, n):
+    table, _, _ = H.generator_multiples_table(900 + n, max(n, 1))
+    sc = H.random_scalars_mont(33 + n, n)
+    if n > 4:
+        sc[1] = 0
+        sc[2] = sc[3]
+        sc[4] = H.to_limbs(H.from_limbs(sc[4]) + H.FR_MODULUS)
+    got = lib.msm(sc, table, n)
+    exp = H.oracle_msm(sc, table)
+    if H.is_infinity(exp):
+        assert H.is_infinity(got)
+    else:
+        assert (got == exp).all()
+
+
+def test_msm_golden_reference_vector(lib):
+    g = np.load(os.path.join(GOLD, "ref_vectors.npz"))
+    got = lib.msm(g["msm_scalars"], g["msm_table"])
+    assert (got == g["msm_out_normalized"]).all()
+
+
+def test_msm_edge_cases(lib):
+    n = 2000
+    table, a0, d = H.generator_multiples_table(11, n)
+    one = np.zeros(4, dtype=np.uint64)
+    H.oracle().orc_constant(6, ptr(one))
+    assert H.is_infinity(lib.msm(np.zeros((n, 4), dtype=np.uint64), table))
+    ones = np.tile(one, (n, 1))
+    assert (lib.msm(ones, table) == H.oracle_msm(ones, table)).all()
+    pts = np.ascontiguousarray(table[0::2]).copy()
+    neg = np.zeros(4, dtype=np.uint64)
+    for i in range(1, n, 2):
+        pts[i, :4] = pts[i - 1, :4]
+        H.oracle().orc_neg(H.FQ, ptr(pts[i - 1, 4:].copy()), ptr(neg))
+        pts[i, 4:] = neg
+    t2 = lib.generate_pippenger_point_table(pts)
+    ref_t2 = np.zeros_like(t2)
+    H.oracle().orc_generate_pippenger_point_table(ptr(pts), ptr(ref_t2), n)
+    assert (t2 == ref_t2).all()
+    sc = H.random_scalars_mont(5, n)
+    sc[1::2] = sc[0::2]
+    assert H.is_infinity(lib.msm(sc, t2))
+    pts2 = np.tile(pts[0], (n, 1))
+    t3 = lib.generate_pippenger_point_table(pts2)
+    sc = H.random_scalars_mont(6, n)
+    sc[:50] = sc[0]
+    assert (lib.msm(sc, t3) == H.oracle_msm(sc, t3)).all()
+    sc = H.random_scalars_mont(8, n)
+    assert (lib.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+
+
+def test_batched_msm_and_srs_cache(lib):
+    n = 4096
+    table, _, _ = H.generator_multiples_table(21, n)
+    keep = lib.srs_register(table)
+    scs = [H.random_scalars_mont(40 + i, n) for i in range(3)]
+    states = [bb.scalar_multiplication.MultiplicationState(points=keep, scalars=s, num_elements=n) for s in scs]
+    bb.scalar_multiplication.batched_scalar_multiplications(states, library=lib)
+    for st, s in zip(states, scs):
+        assert (st.output == H.oracle_msm(s, table)).all()
+    off, m = 640, 1000
+    got = lib.msm(scs[0][off:off + m], keep[2 * off:], m)
+    exp = H.oracle_msm(np.ascontiguousarray(scs[0][off:off + m]), np.ascontiguousarray(table[2 * off:2 * (off + m)]))
+    assert (got == exp).all()
+    lib.srs_unregister(keep)
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_msm_full_size_closed_form_and_reference(lib, log_n):
+    """BASELINE configs[0]: 2^20 points.  Points (a0 + i d) G, seeded scalars; expected value from the closed form
+    (one Fr dot product + one scalar multiplication) and, when oracle/_ref is present, from the compiled reference's
+    batched_scalar_multiplications (limb-equal normalised x, y — test_scalar_multiplication.cpp:315-323)."""
+    n = 1 << log_n
+    table, a0, d = H.generator_multiples_table(77, n)
+    sc = H.random_scalars_mont(78, n)
+    sc[5] = 0
+    got = lib.msm(sc, table)
+    assert (got == H.closed_form_msm(sc, a0, d)).all()
+    # bench recipe scalars: powers of one element (bench_barretenberg.cpp:196-206)
+    if H.have_ref():
+        r = H.ref()
+        out = np.zeros((1, 12), dtype=np.uint64)
+        sbuf = r.ref_aligned_alloc(32 * n)
+        tbuf = r.ref_aligned_alloc(128 * n)
+        sv = np.ctypeslib.as_array((H.C.c_uint64 * (4 * n)).from_address(sbuf)).reshape(n, 4)
+        tv = np.ctypeslib.as_array((H.C.c_uint64 * (16 * n)).from_address(tbuf)).reshape(2 * n, 8)
+        sv[:] = sc
+        tv[:] = table
+        ptrs = (H.C.c_void_p * 1)(sbuf)
+        r.ref_batched_scalar_multiplications(ptrs, tbuf, n, 1, ptr(out))
+        assert (out[0] == got).all()
+        r.ref_aligned_free(sbuf)
+        r.ref_aligned_free(tbuf)
+
+
+def test_msm_sharded_partials_fold(lib):
+    """configs[2] on one GPU: 8 point-range shards -> XYZZ partials -> host fold == whole MSM."""
+    n = 1 << 14
+    table, a0, d = H.generator_multiples_table(31, n)
+    sc = H.random_scalars_mont(32, n)
+    parts = []
+    for r in range(8):
+        lo, hi = r * n // 8, (r + 1) * n // 8
+        d_s = lib.dev_alloc((hi - lo) * 32)
+        d_t = lib.dev_alloc((hi - lo) * 128)
+        lib.h2d(d_s, sc[lo:hi])
+        lib.h2d(d_t, table[2 * lo:2 * hi])
+        parts.append(lib.msm_partial_dev(d_s, d_t, hi - lo))
+        lib.dev_free(d_s)
+        lib.dev_free(d_t)
+    assert (lib.fold_partials(np.stack(parts)) == H.closed_form_msm(sc, a0, d)).all()
+
+
+def test_device_resident_paths(lib):
+    log_n = 14
+    n = 1 << log_n
+    x = H.random_scalars_mont(9, 3 * n).reshape(3, n, 4)
+    d = lib.dev_alloc(x.nbytes)
+    lib.h2d(d, x)
+    lib.ntt_dev("coset_fft", d, log_n, batch=3)
+    out = np.zeros_like(x)
+    lib.d2h(out, d)
+    lib.dev_free(d)
+    od = H.OracleDomain(n)
+    for i in range(3):
+        assert (out[i] == od.ntt(H.NTT_OPS["coset_fft"], x[i])).all()
