@@ -61,6 +61,10 @@ class Library:
         L.bbg_copy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.bbg_timer_stop.argtypes = [C.POINTER(C.c_float)]
         L.bbg_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+        L.bbg_g1_generate_multiples_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.bbg_generate_pippenger_point_table_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.bbg_profile_name.restype = C.c_char_p
+        L.bbg_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         self.check(L.bbg_init(device))
 
     # ------------------------------------------------------------------ plumbing
@@ -105,6 +109,26 @@ class Library:
         ops, ms = C.c_double(), C.c_float()
         self.check(self.lib.bbg_microbench(mode, iters, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.bbg_profile_enable(1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (total_ms, launches)} accumulated since profile_enable()."""
+        out = {}
+        for i in range(self.lib.bbg_profile_count()):
+            ms, cnt = C.c_double(), C.c_uint64()
+            self.check(self.lib.bbg_profile_read(i, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[self.lib.bbg_profile_name(i).decode()] = (ms.value, int(cnt.value))
+        return out
+
+    def generate_multiples_dev(self, start_mont, step_mont, d_points, n):
+        a, b = _as_u64(start_mont, (4,)), _as_u64(step_mont, (4,))
+        self.check(self.lib.bbg_g1_generate_multiples_dev(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_void_p(d_points), n))
+
+    def generate_pippenger_point_table_dev(self, d_points, d_table, n):
+        self.check(self.lib.bbg_generate_pippenger_point_table_dev(C.c_void_p(d_points), C.c_void_p(d_table), n))
 
     # ------------------------------------------------------------------ NTT
     def ntt(self, op, coeffs, constant=None):

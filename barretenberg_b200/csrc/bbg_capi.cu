@@ -396,6 +396,43 @@ int bbg_timer_stop(float* elapsed_ms)
 #endif
 }
 
+int bbg_g1_generate_multiples_dev(const uint64_t start[4], const uint64_t step[4], void* d_points, size_t n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (start == nullptr || step == nullptr || (d_points == nullptr && n > 0)) return BBG_E_BAD_ARGUMENT;
+    return g1_generate_progression_device(start, step, d_points, n, g_stream);
+}
+
+int bbg_generate_pippenger_point_table_dev(const void* d_points, void* d_table, size_t n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (d_points == d_table) return BBG_E_BAD_ARGUMENT;
+    return g1_build_endo_table_device(d_points, d_table, n, g_stream);
+}
+
+int bbg_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    bbg_rt::sync(g_stream);
+    bbg_prof::reset();
+    bbg_prof::state().on = on != 0;
+    return 0;
+}
+int bbg_profile_count(void) { return (int)bbg_prof::NUM_IDS; }
+const char* bbg_profile_name(int id) { return bbg_prof::name(id); }
+int bbg_profile_read(int id, double* total_ms, uint64_t* launches)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (id < 0 || id >= (int)bbg_prof::NUM_IDS || total_ms == nullptr || launches == nullptr) return BBG_E_BAD_ARGUMENT;
+    bbg_prof::collect();
+    *total_ms = bbg_prof::state().total_ms[id];
+    *launches = bbg_prof::state().count[id];
+    return 0;
+}
+
 int bbg_microbench(int mode, int iters, double* ops_per_second, float* elapsed_ms)
 {
     std::lock_guard<std::mutex> lock(g_mutex);

@@ -35,6 +35,8 @@ size_t ntt_launch_count();
 int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t stream);
 int msm_release_workspace();
 size_t msm_launch_count();
+// d_points[i] = (start + i * step) * G (affine, canonical), i < n; start / step: Fr Montgomery limbs (host)
+int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* step_mont, void* d_points, size_t n, cudaStream_t stream);
 // table[2i] = P_i, table[2i+1] = (beta x_i, -y_i) on device (generate_pippenger_point_table layout)
 int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cudaStream_t stream);
 } // namespace bbg

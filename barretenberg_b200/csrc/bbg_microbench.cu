@@ -88,10 +88,12 @@ __global__ void __launch_bounds__(MB_THREADS) imad_chain_kernel(uint32_t* out, u
 template <typename F> __global__ void __launch_bounds__(MB_THREADS) field_mul_kernel(uint32_t* out, uint32_t seed, int iters)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    // every chain must depend on the thread id, or ptxas moves it to the uniform datapath (UIMAD) and the
+    // vector-pipe throughput is overstated
     fe a = F::one(), b = F::one(), m = F::one();
     a.v[0] ^= tid;
-    b.v[1] ^= seed;
-    m.v[0] += seed & 0xff;
+    b.v[1] ^= seed + tid * 2654435761u;
+    m.v[0] += (seed ^ tid) & 0xff;
     for (int it = 0; it < iters; ++it)
     {
         a = F::mul(a, m);

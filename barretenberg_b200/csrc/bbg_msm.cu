@@ -29,6 +29,7 @@
 #include "bbg_internal.h"
 #include "bbg_host_g1.h"
 
+#include <chrono>
 #include <vector>
 
 namespace bbg
@@ -389,6 +390,64 @@ __global__ void endo_table_kernel(const fe* points, fe* table, size_t n)
     store_affine(table + 4 * i, p);
     store_affine(table + 4 * i + 2, G1::endo_table_entry(p));
 }
+// ---- synthetic point sets: (start + i * step) * G  (BASELINE configs[3]: "random multiples of the G1 generator") ----
+constexpr int GEN_RUN = 32;
+BBG_HD xyzz_pt scalar_mul_generator(const fe& k_mont)
+{
+    affine_pt g;
+    g.x = Fq::one(); // generator (1, 2): g1.hpp:13-14
+    g.y = Fq::dbl(Fq::one());
+    const fe k = Fr::from_mont(k_mont);
+    xyzz_pt acc = G1::infinity();
+    for (int i = 253; i >= 0; --i)
+    {
+        acc = G1::dbl(acc);
+        if ((k.v[i >> 5] >> (i & 31)) & 1u) acc = G1::madd(acc, g);
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(64) g1_progression_kernel(fe a0, fe d, fe* points, size_t n)
+{
+    const size_t run = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t first = run * GEN_RUN;
+    if (first >= n) return;
+    const int count = (int)((n - first < (size_t)GEN_RUN) ? n - first : GEN_RUN);
+    // scalar of the run's first point: a0 + first * d
+    fe idx = Fr::zero();
+    idx.v[0] = (uint32_t)first;
+    idx.v[1] = (uint32_t)(first >> 32);
+    const fe s = Fr::reduce(Fr::add(a0, Fr::mul(Fr::to_mont(idx), d)));
+    const affine_pt step = G1::to_affine(scalar_mul_generator(d));
+    xyzz_pt cur = scalar_mul_generator(s);
+    // walk the run, remembering prefix products of zz * zzz for one shared inversion
+    xyzz_pt pts[GEN_RUN];
+    fe prefix[GEN_RUN];
+    fe acc = Fq::one();
+    for (int i = 0; i < count; ++i)
+    {
+        pts[i] = cur;
+        prefix[i] = acc;
+        if (!G1::is_infinity(cur)) acc = Fq::mul(acc, Fq::mul(cur.zz, cur.zzz));
+        if (i + 1 < count) cur = G1::affine_is_infinity(step) ? cur : G1::madd(cur, step);
+    }
+    fe inv = Fq::invert(acc);
+    for (int i = count - 1; i >= 0; --i)
+    {
+        affine_pt out;
+        if (G1::is_infinity(pts[i]))
+        {
+            G1::affine_set_infinity(out);
+        }
+        else
+        {
+            const fe zi = Fq::mul(inv, prefix[i]); // 1 / (zz * zzz)
+            out.x = Fq::mul_full(pts[i].x, Fq::mul(zi, pts[i].zzz));
+            out.y = Fq::mul_full(pts[i].y, Fq::mul(zi, pts[i].zz));
+            inv = Fq::mul(inv, Fq::mul(pts[i].zz, pts[i].zzz));
+        }
+        store_affine(points + 2 * (first + i), out);
+    }
+}
 } // namespace msmk
 
 // ================================================================================================
@@ -506,19 +565,39 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
 
     // counts and fill are adjacent: one memset
     BBG_CHECK(bbg_rt::dev_memset(counts, 0, (o_fill - o_counts) + (size_t)pl.total_buckets * 4, st));
-    BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars, n, pl.c, pl.W, pl.NB, digits, counts);
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_DIGITS, st);
+        BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars, n, pl.c, pl.W, pl.NB, digits, counts);
+    }
+    bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::MSM_SCAN, st);
     BBG_LAUNCH(scan_block_sums_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, spine);
     BBG_LAUNCH(scan_spine_kernel, dim3(1), dim3(SCAN_BLOCK), 0, st, spine, scan_blocks);
     BBG_LAUNCH(scan_apply_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, (const uint32_t*)spine, offsets);
-    BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, pl.num_points, pl.W, pl.NB,
-                      (const uint32_t*)offsets, fill, sorted);
-    BBG_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((unsigned)((pl.max_slices + 127) / 128)), dim3(128), st, (const uint32_t*)sorted, (const uint32_t*)offsets,
-                      pl.total_buckets, (const fe*)d_table, pl.S, buckets, head, tail);
-    BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, (const uint32_t*)offsets, pl.total_buckets, pl.S, buckets,
-                      (const fe*)head, (const fe*)tail);
-    BBG_LAUNCH_NOSYNC(msm_chunk_kernel, dim3((total_chunks + 127) / 128), dim3(128), st, (const fe*)buckets, total_chunks, pl.chunk_log, A, V);
-    BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.W), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V, pl.chunks_per_window,
-               pl.reduce_outputs - 2, red);
+    delete prof_scan;
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_SCATTER, st);
+        BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, pl.num_points, pl.W,
+                          pl.NB, (const uint32_t*)offsets, fill, sorted);
+    }
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_ACCUMULATE, st);
+        BBG_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((unsigned)((pl.max_slices + 127) / 128)), dim3(128), st, (const uint32_t*)sorted,
+                          (const uint32_t*)offsets, pl.total_buckets, (const fe*)d_table, pl.S, buckets, head, tail);
+    }
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_FIXUP, st);
+        BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, (const uint32_t*)offsets, pl.total_buckets, pl.S, buckets,
+                          (const fe*)head, (const fe*)tail);
+    }
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_CHUNK, st);
+        BBG_LAUNCH_NOSYNC(msm_chunk_kernel, dim3((total_chunks + 127) / 128), dim3(128), st, (const fe*)buckets, total_chunks, pl.chunk_log, A, V);
+    }
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_REDUCE, st);
+        BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.W), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V,
+                   pl.chunks_per_window, pl.reduce_outputs - 2, red);
+    }
     g_msm_launches += 9;
     BBG_CHECK(bbg_rt::last_error());
 
@@ -526,6 +605,7 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     std::vector<hostg1::hxyzz> r(red_count);
     BBG_CHECK(bbg_rt::d2h(r.data(), red, red_count * 128, st));
     BBG_CHECK(bbg_rt::sync(st));
+    const auto host_t0 = std::chrono::steady_clock::now();
     const int bits = pl.reduce_outputs - 2;
     for (int w = pl.W - 1; w >= 0; --w)
     {
@@ -545,7 +625,22 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
         result = hostg1::add(result, sw);
     }
     memcpy(out_xyzz_host, &result, sizeof result);
+    bbg_prof::add_host_ms(bbg_prof::MSM_HOST_FINISH, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
     return 0;
+}
+
+// points[i] = (start + i * step) * G, i < n, affine with canonical coordinates.  One thread per run of GEN_RUN
+// consecutive points: a 254-step double-and-add for the run's first point, mixed additions of step * G after
+// that, and Montgomery's trick to leave XYZZ with one inversion per run.
+int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* step_mont, void* d_points, size_t n, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    bbg_prof::Scope prof(bbg_prof::G1_GENERATE, st);
+    const fe a0 = load_fe(start_mont), d = load_fe(step_mont);
+    const size_t runs = (n + GEN_RUN - 1) / GEN_RUN;
+    BBG_LAUNCH_NOSYNC(g1_progression_kernel, dim3((unsigned)((runs + 63) / 64)), dim3(64), st, a0, d, (fe*)d_points, n);
+    ++g_msm_launches;
+    return bbg_rt::last_error();
 }
 
 int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cudaStream_t st)

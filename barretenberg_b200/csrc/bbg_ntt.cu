@@ -519,6 +519,7 @@ template <int L, bool COLS_LOW> int launch_pass_L(const PassParams& p, cudaStrea
     int grid = 2 * bbg_rt::num_sms();
     if (grid > p.total_work) grid = p.total_work;
     auto kernel = ntt_pass_kernel<L, COLS_LOW>; // (alias: the template's comma would split the macro argument)
+    bbg_prof::Scope prof(COLS_LOW ? bbg_prof::NTT_PASS_A : bbg_prof::NTT_PASS_B, st);
     BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT), SMEM_BYTES, st, p);
     ++g_ntt_launches;
     return bbg_rt::last_error();
@@ -610,6 +611,7 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
             BBG_CHECK(bbg_rt::set_smem_limit((const void*)ntt_small_kernel, SMEM_BYTES));
             g_tables.smem_configured = true;
         }
+        bbg_prof::Scope prof(bbg_prof::NTT_SMALL, st);
         BBG_LAUNCH(ntt_small_kernel, dim3((unsigned)batch), dim3(NT), SMEM_BYTES, st, sp);
         ++g_ntt_launches;
         return bbg_rt::last_error();

@@ -33,6 +33,7 @@ inline int set_smem_limit(const void*, size_t) { return 0; }
 
 #else
 #include <cuda_runtime.h>
+#include <vector>
 
 #define BBG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define BBG_LAUNCH_NOSYNC(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
@@ -62,3 +63,111 @@ inline int set_smem_limit(const void* fn, size_t bytes)
 }
 } // namespace bbg_rt
 #endif
+
+// ---------------------------------------------------------------------------------------------------
+// Optional per-kernel stopwatch (CUDA events on the launching stream), off by default.  bench.py switches it
+// on for a separate, untimed pass to attribute the step time to kernels (roofline.achieved).
+// ---------------------------------------------------------------------------------------------------
+namespace bbg_prof
+{
+enum id
+{
+    NTT_PASS_A = 0,
+    NTT_PASS_B,
+    NTT_SMALL,
+    NTT_TABLES,
+    MSM_DIGITS,
+    MSM_SCAN,
+    MSM_SCATTER,
+    MSM_ACCUMULATE,
+    MSM_FIXUP,
+    MSM_CHUNK,
+    MSM_REDUCE,
+    MSM_HOST_FINISH,
+    G1_GENERATE,
+    NUM_IDS
+};
+inline const char* name(int i)
+{
+    static const char* n[NUM_IDS] = { "ntt_pass_a", "ntt_pass_b", "ntt_small", "ntt_tables", "msm_digits", "msm_scan", "msm_scatter",
+                                      "msm_accumulate", "msm_fixup", "msm_chunk", "msm_reduce", "msm_host_finish", "g1_generate" };
+    return (i >= 0 && i < NUM_IDS) ? n[i] : "?";
+}
+struct State
+{
+    bool on = false;
+    double total_ms[NUM_IDS] = {};
+    unsigned long long count[NUM_IDS] = {};
+#ifndef BBG_EMULATE
+    struct Rec
+    {
+        int id;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> pending;
+#endif
+};
+inline State& state()
+{
+    static State s;
+    return s;
+}
+inline void collect()
+{
+#ifndef BBG_EMULATE
+    State& s = state();
+    for (auto& r : s.pending)
+    {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        s.total_ms[r.id] += ms;
+        s.count[r.id] += 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    s.pending.clear();
+#endif
+}
+inline void reset()
+{
+    collect();
+    State& s = state();
+    for (int i = 0; i < NUM_IDS; ++i)
+    {
+        s.total_ms[i] = 0;
+        s.count[i] = 0;
+    }
+}
+// RAII: everything launched on `st` during the scope's lifetime is attributed to `id`
+struct Scope
+{
+#ifndef BBG_EMULATE
+    int id_;
+    cudaStream_t st_;
+    cudaEvent_t a_ = nullptr, b_ = nullptr;
+    bool live_;
+    Scope(int i, cudaStream_t st) : id_(i), st_(st), live_(state().on)
+    {
+        if (!live_) return;
+        cudaEventCreate(&a_);
+        cudaEventCreate(&b_);
+        cudaEventRecord(a_, st_);
+    }
+    ~Scope()
+    {
+        if (!live_) return;
+        cudaEventRecord(b_, st_);
+        state().pending.push_back({ id_, a_, b_ });
+    }
+#else
+    Scope(int, cudaStream_t) {}
+#endif
+};
+inline void add_host_ms(int i, double ms)
+{
+    if (!state().on) return;
+    state().total_ms[i] += ms;
+    state().count[i] += 1;
+}
+} // namespace bbg_prof

@@ -93,6 +93,13 @@ int bbg_g1_fold_partials(const uint64_t* partials_xyzz /* count x 16 */, size_t 
  * (scalar_multiplication.cpp:131-140) computed on the device; table may alias points */
 int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table_2n, size_t n);
 
+/* device-resident variant (d_table must not alias d_points) */
+int bbg_generate_pippenger_point_table_dev(const void* d_points, void* d_table, size_t n);
+/* Synthetic point sets for sizes beyond the SRS (BASELINE configs[3], "random multiples of the G1 generator"):
+ * d_points[i] = (start + i * step) * G for i < n, affine, canonical Montgomery coordinates, written to device
+ * memory (n x 64 bytes).  start / step are Fr elements in Montgomery form. */
+int bbg_g1_generate_multiples_dev(const uint64_t start[4], const uint64_t step[4], void* d_points, size_t n);
+
 /* ---- device memory helpers (tests, bench, device-resident callers) ---------------------------- */
 int bbg_dev_alloc(void** d_ptr, size_t bytes);
 int bbg_dev_free(void* d_ptr);
@@ -104,10 +111,18 @@ int bbg_timer_start(void);
 int bbg_timer_stop(float* elapsed_ms);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
+/* Per-kernel stopwatch (CUDA events on the work stream), off by default: bench.py enables it for a separate
+ * untimed pass to attribute step time to kernels.  ids 0 .. bbg_profile_count()-1, names via bbg_profile_name. */
+int bbg_profile_enable(int on);           /* also resets the counters */
+int bbg_profile_count(void);
+const char* bbg_profile_name(int id);
+int bbg_profile_read(int id, double* total_ms, uint64_t* launches);
 /* Dependency-free integer multiply-add throughput on all SMs: the IMAD roofline denominator.
  * mode 0: mad.lo.u32   1: mad.wide.u32 (64-bit accumulate)   2: carry-chained mad.lo.cc/madc.hi.cc pairs
  *      3: Fq Montgomery products (reports field products/s)   4: Fr Montgomery products
- * ops_per_second: 32x32 multiply-adds (modes 0-2) or field products (3-4) per second. */
+ * ops_per_second: 32x32 multiply-adds (modes 0-2) or field products (3-4) per second.
+ * Measured on B200: mode 0 = 1.85e13/s (64 IMAD/clk/SM), modes 1-2 = 8.9e12/s: a 32x32->64 multiply-add
+ * (IMAD.WIDE) occupies the integer multiply pipe for two issue slots. */
 int bbg_microbench(int mode, int iters, double* ops_per_second, float* elapsed_ms);
 
 #ifdef __cplusplus

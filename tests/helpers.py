@@ -109,14 +109,13 @@ def ref():
     return _ref
 
 
-# ---------------------------------------------------------------- integers <-> limbs
-def to_limbs(x, n=4):
-    return np.array([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)], dtype=np.uint64)
+# ---------------------------------------------------------------- integers <-> limbs, seeded generators
+import sys  # noqa: E402
 
-
-def from_limbs(a):
-    a = np.asarray(a, dtype=np.uint64).reshape(-1)
-    return sum(int(v) << (64 * i) for i, v in enumerate(a))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from barretenberg_b200.synthetic import from_limbs, splitmix64, to_limbs  # noqa: E402,F401
+from barretenberg_b200.synthetic import random_field as _random_field  # noqa: E402
 
 
 def limbs_array(ints):
@@ -134,39 +133,9 @@ def unmont(x, field=FR):
     return (x * pow(R_MONT, -1, MODULUS[field])) % MODULUS[field]
 
 
-# ---------------------------------------------------------------- seeded generators
-def splitmix64(seed, count):
-    """Vectorised splitmix64 stream: `count` uint64 values from `seed` (numpy, wraps mod 2^64)."""
-    with np.errstate(over="ignore"):
-        idx = np.arange(1, count + 1, dtype=np.uint64)
-        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        return z ^ (z >> np.uint64(31))
-
-
 def random_field_raw(seed, n, field=FR):
-    """n uniform-ish canonical values < p as (n,4) uint64 limbs (raw, i.e. whatever form the caller deems)."""
-    raw = splitmix64(seed, 4 * n).reshape(n, 4).copy()
-    raw[:, 3] &= np.uint64(0x3FFFFFFFFFFFFFFF)  # < 2^254
-    p = to_limbs(MODULUS[field])
-    # conditional subtract p (values < 2^254 < 2p)
-    ge = np.zeros(n, dtype=bool)
-    eq = np.ones(n, dtype=bool)
-    for i in (3, 2, 1, 0):
-        ge |= eq & (raw[:, i] > p[i])
-        eq &= raw[:, i] == p[i]
-    ge |= eq
-    if ge.any():
-        borrow = np.zeros(n, dtype=np.uint64)
-        with np.errstate(over="ignore"):
-            for i in range(4):
-                a = raw[:, i]
-                d = a - p[i] - borrow
-                nb = ((a < p[i]) | ((a == p[i]) & (borrow == 1))).astype(np.uint64)
-                raw[:, i] = np.where(ge, d, a)
-                borrow = nb
-    return raw
+    """n uniform-ish canonical values < p as (n,4) uint64 limbs."""
+    return _random_field(seed, n, MODULUS[field])
 
 
 def random_scalars_mont(seed, n):

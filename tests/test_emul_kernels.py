@@ -145,3 +145,22 @@ def test_partials_fold(emu):
         emu.dev_free(d_s)
         emu.dev_free(d_t)
     assert (emu.fold_partials(np.stack(parts)) == H.oracle_msm(sc, table)).all()
+
+
+def test_device_point_generator(emu):
+    """bbg_g1_generate_multiples_dev == the oracle's (a0 + i d) G progression, including a run boundary."""
+    n, a0, d = 70, 12345, 777
+    dp = emu.dev_alloc(n * 64)
+    emu.generate_multiples_dev(H.to_limbs(H.mont(a0)), H.to_limbs(H.mont(d)), dp, n)
+    out = np.zeros((n, 8), dtype=np.uint64)
+    emu.d2h(out, dp)
+    assert (out == H.arithmetic_progression_points(a0, d, n)).all()
+    dt = emu.dev_alloc(n * 128)
+    emu.generate_pippenger_point_table_dev(dp, dt, n)
+    tab = np.zeros((2 * n, 8), dtype=np.uint64)
+    emu.d2h(tab, dt)
+    exp = np.zeros_like(tab)
+    H.oracle().orc_generate_pippenger_point_table(H.ptr(out), H.ptr(exp), n)
+    assert (tab == exp).all()
+    emu.dev_free(dp)
+    emu.dev_free(dt)

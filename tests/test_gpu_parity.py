@@ -254,3 +254,23 @@ def test_device_resident_paths(lib):
     od = H.OracleDomain(n)
     for i in range(3):
         assert (out[i] == od.ntt(H.NTT_OPS["coset_fft"], x[i])).all()
+
+
+def test_device_point_generator(lib):
+    n, a0, d = 5000, 12345, 777
+    dp = lib.dev_alloc(n * 64)
+    lib.generate_multiples_dev(H.to_limbs(H.mont(a0)), H.to_limbs(H.mont(d)), dp, n)
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib.d2h(out, dp)
+    assert (out == H.arithmetic_progression_points(a0, d, n)).all()
+    lib.dev_free(dp)
+
+
+def test_profile_counters(lib):
+    lib.profile_enable(True)
+    n = 1 << 13
+    x = H.random_scalars_mont(1, n)
+    lib.ntt("fft", x)
+    prof = lib.profile_read()
+    lib.profile_enable(False)
+    assert prof["ntt_pass_a"][1] == 1 and prof["ntt_pass_b"][1] == 1
