@@ -397,6 +397,15 @@ def run_b200(args, rank, local_rank, world):
         ops_ms["ifft_2p%d_per_poly" % log_n] = time_op(lambda: lib.ntt_dev("ifft", d_poly_n, log_n, batch=P)) / P
         ops_ms["coset_fft_2p%d_per_poly" % (log_n + 2)] = time_op(lambda: lib.ntt_dev("coset_fft", d_poly_4n, log_n + 2, batch=P)) / P
 
+    if args.device_only:
+        if rank == 0:
+            print(json.dumps({"metric": "ms_per_step_msm2p%d_plus_ntt_batch" % log_n, "value": value, "unit": "ms", "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "components_ms": ops_ms, "gpu_launches": int(launches), "device_only": True}))
+        barrier()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e through the host-buffer ABI ----------------------------------------------------------------------
     for _ in range(min(args.warmup, 2)):
         step_host()
@@ -498,6 +507,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="log2 of the MSM / NTT size (BASELINE: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="skip the e2e, microbench and CPU-baseline legs (short runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
