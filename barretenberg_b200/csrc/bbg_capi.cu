@@ -53,8 +53,32 @@ struct SrsEntry
     const uint64_t* host_base;
     size_t n; // original points; table has 2n entries of 8 uint64
     void* d_table;
+    uint64_t fingerprint; // of sampled host entries, re-checked on every cache hit
+    bool automatic;       // created by the auto cache (may be evicted)
 };
 std::vector<SrsEntry> g_srs;
+bool g_auto_srs = false;
+constexpr size_t AUTO_SRS_MIN_POINTS = 1024; // below this an upload per call is cheaper than bookkeeping
+constexpr size_t AUTO_SRS_MAX_ENTRIES = 4;
+
+// FNV-1a over 32 table entries spread across [0, 2n): cheap enough to recompute on every call, and enough to
+// notice that a host buffer was freed / rewritten behind a cached address
+uint64_t table_fingerprint(const uint64_t* table, size_t n)
+{
+    const size_t entries = 2 * n;
+    uint64_t h = 1469598103934665603ULL ^ (uint64_t)n;
+    for (size_t s = 0; s < 32; ++s)
+    {
+        const size_t idx = entries <= 32 ? (s < entries ? s : entries - 1) : (s * (entries - 1)) / 31;
+        const uint64_t* e = table + 8 * idx;
+        for (int w = 0; w < 8; ++w)
+        {
+            h ^= e[w];
+            h *= 1099511628211ULL;
+        }
+    }
+    return h;
+}
 
 #ifndef BBG_EMULATE
 cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
@@ -77,13 +101,53 @@ int ensure_ready()
 // device pointer for a host point-table pointer: registered SRS (sub-range allowed) or a fresh upload
 int resolve_table(const uint64_t* points, size_t n, const void** d_table)
 {
-    for (const SrsEntry& s : g_srs)
+    for (size_t i = 0; i < g_srs.size(); ++i)
     {
+        SrsEntry& s = g_srs[i];
         if (points >= s.host_base && points + 16 * n <= s.host_base + 16 * s.n)
         {
+            if (table_fingerprint(s.host_base, s.n) != s.fingerprint)
+            {
+                // the host buffer changed under a cached address: drop the stale copy and fall through
+                bbg_rt::sync(g_stream);
+                bbg_rt::dev_free(s.d_table);
+                g_srs.erase(g_srs.begin() + (long)i);
+                break;
+            }
             *d_table = (const char*)s.d_table + ((const char*)points - (const char*)s.host_base);
             return 0;
         }
+    }
+    if (g_auto_srs && n >= AUTO_SRS_MIN_POINTS)
+    {
+        // first sight of a large table: keep it on the device (prover.cpp calls the MSM 9 times per proof on the same
+        // ReferenceString::monomials buffer; copies of a ReferenceString get their own entry)
+        size_t autos = 0;
+        for (const SrsEntry& s : g_srs) autos += s.automatic ? 1 : 0;
+        if (autos >= AUTO_SRS_MAX_ENTRIES)
+        {
+            for (size_t i = 0; i < g_srs.size(); ++i)
+            {
+                if (g_srs[i].automatic)
+                {
+                    bbg_rt::sync(g_stream);
+                    bbg_rt::dev_free(g_srs[i].d_table);
+                    g_srs.erase(g_srs.begin() + (long)i);
+                    break;
+                }
+            }
+        }
+        SrsEntry s;
+        s.host_base = points;
+        s.n = n;
+        s.d_table = nullptr;
+        s.automatic = true;
+        s.fingerprint = table_fingerprint(points, n);
+        BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
+        BBG_CHECK(bbg_rt::h2d(s.d_table, points, n * 128, g_stream));
+        g_srs.push_back(s);
+        *d_table = s.d_table;
+        return 0;
     }
     BBG_CHECK(g_stage_table.ensure(n * 128));
     BBG_CHECK(bbg_rt::h2d(g_stage_table.p, points, n * 128, g_stream));
@@ -245,10 +309,19 @@ int bbg_srs_register(const uint64_t* table_2n, size_t n)
     s.host_base = table_2n;
     s.n = n;
     s.d_table = nullptr;
+    s.automatic = false;
+    s.fingerprint = table_fingerprint(table_2n, n);
     BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
     BBG_CHECK(bbg_rt::h2d(s.d_table, table_2n, n * 128, g_stream));
     BBG_CHECK(bbg_rt::sync(g_stream));
     g_srs.push_back(s);
+    return 0;
+}
+
+int bbg_set_auto_srs_cache(int enable)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_auto_srs = enable != 0;
     return 0;
 }
 

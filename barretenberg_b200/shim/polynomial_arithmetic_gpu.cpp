@@ -1,0 +1,66 @@
+// Drop-in replacement for the radix-2 NTT entry points of the reference's
+//   src/barretenberg/polynomials/polynomial_arithmetic.cpp
+// Same namespace and signatures (polynomial_arithmetic.hpp:28-39): fft, ifft, fft_with_constant, ifft_with_constant,
+// coset_fft, coset_fft_with_constant, coset_ifft — in place on `coeffs`, length domain.size, natural order in and
+// out, canonical outputs.  barretenberg::polynomial (polynomial.cpp:246-313), the prover and the widgets call these.
+//
+// How to link: build the reference's polynomial_arithmetic.cpp with
+//   -Dfft=cpu_reference_fft -Difft=cpu_reference_ifft -Dfft_with_constant=cpu_reference_fft_with_constant
+//   -Difft_with_constant=cpu_reference_ifft_with_constant -Dcoset_fft=cpu_reference_coset_fft
+//   -Dcoset_fft_with_constant=cpu_reference_coset_fft_with_constant -Dcoset_ifft=cpu_reference_coset_ifft
+// (its element-wise helpers — evaluate, divide_by_pseudo_vanishing_polynomial, compute_kate_opening_coefficients,
+// ... — keep their reference CPU bodies) and add this file for the seven names above.
+// evaluation_domain.cpp is unchanged: only domain.log2_size crosses the boundary; root, 1/n, the coset generator
+// and every twiddle are derived on the device from the curve constants.
+#include <cstdio>
+#include <cstdlib>
+
+#include <barretenberg/polynomials/polynomial_arithmetic.hpp>
+
+#include "bbgpu.h"
+
+namespace
+{
+void run(barretenberg::fr::field_t* coeffs, const barretenberg::evaluation_domain& domain, int op, const barretenberg::fr::field_t* constant,
+         const char* what)
+{
+    static bool ready = false;
+    int e = 0;
+    if (!ready)
+    {
+        const char* dev = getenv("BBG_DEVICE");
+        e = bbg_init(dev ? atoi(dev) : 0);
+        if (e == 0) bbg_set_auto_srs_cache(1);
+        ready = (e == 0);
+    }
+    if (e == 0) e = bbg_ntt_fr((uint64_t*)coeffs, (unsigned)domain.log2_size, op, (const uint64_t*)constant);
+    if (e != 0)
+    {
+        fprintf(stderr, "bbgpu shim: %s failed: %s (no CPU fallback)\n", what, bbg_error_string(e));
+        abort();
+    }
+}
+} // namespace
+
+namespace barretenberg
+{
+namespace polynomial_arithmetic
+{
+void fft(fr::field_t* coeffs, const evaluation_domain& domain) { run(coeffs, domain, BBG_FFT, nullptr, "fft"); }
+void ifft(fr::field_t* coeffs, const evaluation_domain& domain) { run(coeffs, domain, BBG_IFFT, nullptr, "ifft"); }
+void fft_with_constant(fr::field_t* coeffs, const evaluation_domain& domain, const fr::field_t& value)
+{
+    run(coeffs, domain, BBG_FFT_WITH_CONSTANT, &value, "fft_with_constant");
+}
+void ifft_with_constant(fr::field_t* coeffs, const evaluation_domain& domain, const fr::field_t& value)
+{
+    run(coeffs, domain, BBG_IFFT_WITH_CONSTANT, &value, "ifft_with_constant");
+}
+void coset_fft(fr::field_t* coeffs, const evaluation_domain& domain) { run(coeffs, domain, BBG_COSET_FFT, nullptr, "coset_fft"); }
+void coset_fft_with_constant(fr::field_t* coeffs, const evaluation_domain& domain, const fr::field_t& constant)
+{
+    run(coeffs, domain, BBG_COSET_FFT_WITH_CONSTANT, &constant, "coset_fft_with_constant");
+}
+void coset_ifft(fr::field_t* coeffs, const evaluation_domain& domain) { run(coeffs, domain, BBG_COSET_IFFT, nullptr, "coset_ifft"); }
+} // namespace polynomial_arithmetic
+} // namespace barretenberg

@@ -1,0 +1,107 @@
+// Drop-in replacement for the GPU-backed entry points of the reference's
+//   src/barretenberg/curves/bn254/scalar_multiplication.cpp
+// Same namespace, same signatures (scalar_multiplication.hpp:41, :60-61, :88-96), so the waffle prover, the
+// widgets, preprocess.hpp, the verifier and ReferenceString link against these unchanged.  Compiled against the
+// reference's own headers (-I<reference>/src); everything heavy happens behind the C ABI of include/bbgpu.h.
+//
+// How to link (INTEGRATION.md has the CMake lines): build the reference's scalar_multiplication.cpp with
+//   -Dpippenger=cpu_reference_pippenger -Dbatched_scalar_multiplications=cpu_reference_batched_scalar_multiplications
+//   -Dgenerate_pippenger_point_table=cpu_reference_generate_pippenger_point_table
+// so its ten experimental / helper symbols (pippenger_low_memory, alt_pippenger, pippenger_precomputed, ...) keep
+// their reference CPU bodies, and add this file for the three names above.  Replace pippenger and
+// batched_scalar_multiplications TOGETHER (the reference's batched version calls pippenger from inside an OpenMP
+// region with sub-range pointers, scalar_multiplication.cpp:731-738).
+//
+// Error behaviour: the reference has no error returns (size mismatch prints and returns, :677-685; everything
+// else is an ASSERT compiled out in release).  A CUDA failure here prints the bbgpu error and abort()s — there
+// is deliberately no CPU fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include <barretenberg/curves/bn254/scalar_multiplication.hpp>
+
+#include "bbgpu.h"
+
+namespace
+{
+[[noreturn]] void die(const char* what, int code)
+{
+    fprintf(stderr, "bbgpu shim: %s failed: %s (no CPU fallback)\n", what, bbg_error_string(code));
+    abort();
+}
+void ensure_init()
+{
+    static bool done = false;
+    if (done) return;
+    const char* dev = getenv("BBG_DEVICE");
+    int e = bbg_init(dev ? atoi(dev) : 0);
+    if (e != 0) die("bbg_init", e);
+    bbg_set_auto_srs_cache(1);
+    done = true;
+}
+static_assert(sizeof(barretenberg::fr::field_t) == 32, "field_t layout");
+static_assert(sizeof(barretenberg::g1::affine_element) == 64, "affine_element layout");
+static_assert(sizeof(barretenberg::g1::element) == 96, "element layout");
+} // namespace
+
+namespace barretenberg
+{
+namespace scalar_multiplication
+{
+// scalar_multiplication.cpp:131-140 — table may alias points (reference_string.cpp:23 calls it in place)
+void generate_pippenger_point_table(g1::affine_element* points, g1::affine_element* table, size_t num_points)
+{
+    ensure_init();
+    int e = bbg_generate_pippenger_point_table((const uint64_t*)points, (uint64_t*)table, num_points);
+    if (e != 0) die("generate_pippenger_point_table", e);
+    // the table just written is the SRS the prover will commit against: keep it on the device
+    if (num_points >= 1024)
+    {
+        e = bbg_srs_register((const uint64_t*)table, num_points);
+        if (e != 0) die("bbg_srs_register", e);
+    }
+}
+
+// scalar_multiplication.cpp:457-476.  forced_bucket_width does not change the value (SURVEY.md §8 note 3) and is
+// ignored.  The returned point is already normalised (z = fq::one), a valid representative of the same group
+// element the reference returns un-normalised; n == 0 and all-zero scalars give the infinity flag.
+g1::element pippenger(fr::field_t* scalars, g1::affine_element* points, size_t num_initial_points, size_t /*forced_bucket_width*/)
+{
+    ensure_init();
+    g1::element out;
+    int e = bbg_msm_g1((const uint64_t*)scalars, (const uint64_t*)points, num_initial_points, (uint64_t*)&out);
+    if (e != 0) die("pippenger", e);
+    return out;
+}
+
+// scalar_multiplication.cpp:650-772: writes only mul_state[i].output, normalised
+void batched_scalar_multiplications(multiplication_state* mul_state, size_t num_batches)
+{
+    if (num_batches == 0) return;
+    const size_t num_elements = mul_state[0].num_elements;
+    for (size_t i = 1; i < num_batches; ++i)
+    {
+        if (mul_state[i].num_elements != num_elements)
+        {
+            printf("batched_scalar_multiplications err: each scalar mul must be same size.\n");
+            return;
+        }
+    }
+    ensure_init();
+    const uint64_t** scalars = (const uint64_t**)malloc(sizeof(uint64_t*) * num_batches * 2);
+    const uint64_t** tables = scalars + num_batches;
+    uint64_t* outs = (uint64_t*)malloc(96 * num_batches);
+    for (size_t i = 0; i < num_batches; ++i)
+    {
+        scalars[i] = (const uint64_t*)mul_state[i].scalars;
+        tables[i] = (const uint64_t*)mul_state[i].points;
+    }
+    int e = bbg_msm_g1_batched(scalars, tables, num_elements, num_batches, outs);
+    if (e != 0) die("batched_scalar_multiplications", e);
+    for (size_t i = 0; i < num_batches; ++i) memcpy((void*)&mul_state[i].output, outs + 12 * i, 96);
+    free(outs);
+    free((void*)scalars);
+}
+} // namespace scalar_multiplication
+} // namespace barretenberg

@@ -233,6 +233,7 @@ def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
     import barretenberg_b200 as bb
+    from barretenberg_b200 import parallel
     from barretenberg_b200 import synthetic as S
 
     if not torch.cuda.is_available():
@@ -257,9 +258,9 @@ def run_b200(args, rank, local_rank, world):
 
     log_n, n = args.log_n, 1 << args.log_n
     # ---- shards --------------------------------------------------------------------------------------
-    lo, hi = rank * n // world, (rank + 1) * n // world
+    lo, hi = parallel.shard_range(n, rank, world)
     n_loc = hi - lo
-    polys = [i for i in range(BATCH) if i % world == rank]  # batch sharded by polynomial; may be empty for world > 8
+    polys = parallel.shard_batch(BATCH, rank, world)  # batch sharded by polynomial; empty for ranks beyond the batch
     P = len(polys)
 
     # ---- MSM inputs: points generated on the GPU, scalars seeded on the host -------------------------------
@@ -292,15 +293,9 @@ def run_b200(args, rank, local_rank, world):
     lib.h2d(d_poly_n, h_poly_n)
     lib.h2d(d_poly_4n, h_poly_4n)
 
-    gather_buf = torch.zeros((world, 16), dtype=torch.int64, device="cuda") if world > 1 else None
-
     def fold(partial16):
-        """Tiny NCCL all-gather of the 128-byte partials, then the host-side fold."""
-        if world == 1:
-            return lib.fold_partials(partial16.reshape(1, 16))
-        mine = torch.from_numpy(partial16.view(np.int64)).cuda()
-        dist.all_gather_into_tensor(gather_buf.view(-1), mine)
-        return lib.fold_partials(gather_buf.cpu().numpy().view(np.uint64))
+        """Tiny NCCL all-gather of the 128-byte partials over NVLink, then the host-side fold."""
+        return lib.fold_partials(parallel.gather_partials(partial16, world, device="cuda"))
 
     def step_device():
         part = lib.msm_partial_dev(d_scalars, d_table, n_loc)
@@ -311,16 +306,12 @@ def run_b200(args, rank, local_rank, world):
             lib.ntt_dev("coset_fft", d_poly_4n, log_n + 2, batch=P)
         return res
 
-    one16 = np.zeros(16, dtype=np.uint64)
-
     def step_host():
         """The call a user of the reference signatures makes: host buffers in, host buffers out."""
-        jac = lib.msm(h_scalars[:n_loc], h_table, n_loc) if n_loc else np.zeros(12, dtype=np.uint64)
-        part = one16.copy()
-        if n_loc and not (int(jac[7]) >> 63):
-            part[:8] = jac[:8]
-            part[8:12] = jac[8:12]
-            part[12:16] = jac[8:12]
+        if n_loc:
+            part = parallel.normalized_to_partial(lib.msm(h_scalars[:n_loc], h_table, n_loc))
+        else:
+            part = np.zeros(16, dtype=np.uint64)
         res = fold(part)
         if P:
             lib.ntt("fft", h_poly_n[:P])

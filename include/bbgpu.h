@@ -78,6 +78,10 @@ int bbg_ntt_fr_dev(void* d_coeffs, size_t stride_elems, size_t batch, unsigned l
  * (batched_scalar_multiplications passes &points[2 * offset], scalar_multiplication.cpp:720-723). */
 int bbg_srs_register(const uint64_t* table_2n, size_t n);
 int bbg_srs_unregister(const uint64_t* table_2n);
+/* Auto cache (off by default, the shims switch it on): an unregistered table of >= 1024 points is kept on the device
+ * the first time an MSM sees it; every hit re-checks a fingerprint of sampled host entries, so a buffer that was
+ * freed and rewritten behind the same address is re-uploaded, never trusted. */
+int bbg_set_auto_srs_cache(int enable);
 /* sum_i scalars[i] * P_i over table entries points_table[0 .. 2n); out_xyz = 12 limbs, normalised */
 int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, uint64_t out_xyz[12]);
 /* `batches` MSMs of the same size n (multiplication_state[], scalar_multiplication.hpp:88-94) */
