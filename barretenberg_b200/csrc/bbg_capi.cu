@@ -82,6 +82,9 @@ uint64_t table_fingerprint(const uint64_t* table, size_t n)
 
 #ifndef BBG_EMULATE
 cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+// copy engines for the host-buffer NTT path: uploads, kernels and downloads of different polynomials overlap
+cudaStream_t g_copy_in = nullptr, g_copy_out = nullptr;
+std::vector<cudaEvent_t> g_pipe_events;
 #endif
 
 int ensure_ready()
@@ -190,6 +193,8 @@ int bbg_init(int device)
     }
     BBG_CHECK(cudaEventCreate(&g_ev_start));
     BBG_CHECK(cudaEventCreate(&g_ev_stop));
+    BBG_CHECK(cudaStreamCreateWithFlags(&g_copy_in, cudaStreamNonBlocking));
+    BBG_CHECK(cudaStreamCreateWithFlags(&g_copy_out, cudaStreamNonBlocking));
 #else
     (void)device;
 #endif
@@ -213,6 +218,11 @@ int bbg_shutdown(void)
     if (g_ev_start) cudaEventDestroy(g_ev_start);
     if (g_ev_stop) cudaEventDestroy(g_ev_stop);
     g_ev_start = g_ev_stop = nullptr;
+    for (cudaEvent_t ev : g_pipe_events) cudaEventDestroy(ev);
+    g_pipe_events.clear();
+    if (g_copy_in) cudaStreamDestroy(g_copy_in);
+    if (g_copy_out) cudaStreamDestroy(g_copy_out);
+    g_copy_in = g_copy_out = nullptr;
     if (g_own_stream && g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
     g_own_stream = false;
@@ -277,8 +287,38 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
     for (size_t i = 0; i < batch; ++i)
     {
         if (coeffs[i] == nullptr) return BBG_E_BAD_ARGUMENT;
-        BBG_CHECK(bbg_rt::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_stream));
     }
+#ifndef BBG_EMULATE
+    if (batch > 1)
+    {
+        // three-stage pipeline over polynomials: upload i+1 | transform i | download i-1 (PCIe is full duplex)
+        while (g_pipe_events.size() < 2 * batch + 1)
+        {
+            cudaEvent_t ev;
+            BBG_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            g_pipe_events.push_back(ev);
+        }
+        // uploads may start once everything already queued on the work stream is done with the staging buffer
+        BBG_CHECK(cudaEventRecord(g_pipe_events[2 * batch], g_stream));
+        BBG_CHECK(cudaStreamWaitEvent(g_copy_in, g_pipe_events[2 * batch], 0));
+        for (size_t i = 0; i < batch; ++i)
+        {
+            BBG_CHECK(bbg_rt::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_copy_in));
+            BBG_CHECK(cudaEventRecord(g_pipe_events[i], g_copy_in));
+        }
+        for (size_t i = 0; i < batch; ++i)
+        {
+            BBG_CHECK(cudaStreamWaitEvent(g_stream, g_pipe_events[i], 0));
+            BBG_CHECK(ntt_device((char*)g_stage_coeffs.p + i * bytes, n, 1, log2_n, op, constant, g_stream));
+            BBG_CHECK(cudaEventRecord(g_pipe_events[batch + i], g_stream));
+            BBG_CHECK(cudaStreamWaitEvent(g_copy_out, g_pipe_events[batch + i], 0));
+            BBG_CHECK(bbg_rt::d2h(coeffs[i], (char*)g_stage_coeffs.p + i * bytes, bytes, g_copy_out));
+        }
+        BBG_CHECK(bbg_rt::sync(g_copy_out));
+        return bbg_rt::sync(g_stream);
+    }
+#endif
+    for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_rt::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_stream));
     BBG_CHECK(ntt_device(g_stage_coeffs.p, n, batch, log2_n, op, constant, g_stream));
     for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_rt::d2h(coeffs[i], (char*)g_stage_coeffs.p + i * bytes, bytes, g_stream));
     return bbg_rt::sync(g_stream);

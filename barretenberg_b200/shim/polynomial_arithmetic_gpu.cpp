@@ -18,6 +18,7 @@
 #include <barretenberg/polynomials/polynomial_arithmetic.hpp>
 
 #include "bbgpu.h"
+#include "shim_stats.h"
 
 namespace
 {
@@ -33,6 +34,7 @@ void run(barretenberg::fr::field_t* coeffs, const barretenberg::evaluation_domai
         if (e == 0) bbg_set_auto_srs_cache(1);
         ready = (e == 0);
     }
+    bbg_shim::Timer timer(what);
     if (e == 0) e = bbg_ntt_fr((uint64_t*)coeffs, (unsigned)domain.log2_size, op, (const uint64_t*)constant);
     if (e != 0)
     {

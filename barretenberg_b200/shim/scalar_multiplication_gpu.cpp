@@ -22,6 +22,7 @@
 #include <barretenberg/curves/bn254/scalar_multiplication.hpp>
 
 #include "bbgpu.h"
+#include "shim_stats.h"
 
 namespace
 {
@@ -53,6 +54,7 @@ namespace scalar_multiplication
 void generate_pippenger_point_table(g1::affine_element* points, g1::affine_element* table, size_t num_points)
 {
     ensure_init();
+    bbg_shim::Timer timer("generate_pippenger_point_table");
     int e = bbg_generate_pippenger_point_table((const uint64_t*)points, (uint64_t*)table, num_points);
     if (e != 0) die("generate_pippenger_point_table", e);
     // the table just written is the SRS the prover will commit against: keep it on the device
@@ -69,6 +71,7 @@ void generate_pippenger_point_table(g1::affine_element* points, g1::affine_eleme
 g1::element pippenger(fr::field_t* scalars, g1::affine_element* points, size_t num_initial_points, size_t /*forced_bucket_width*/)
 {
     ensure_init();
+    bbg_shim::Timer timer("pippenger");
     g1::element out;
     int e = bbg_msm_g1((const uint64_t*)scalars, (const uint64_t*)points, num_initial_points, (uint64_t*)&out);
     if (e != 0) die("pippenger", e);
@@ -89,6 +92,7 @@ void batched_scalar_multiplications(multiplication_state* mul_state, size_t num_
         }
     }
     ensure_init();
+    bbg_shim::Timer timer("batched_scalar_multiplications", num_batches);
     const uint64_t** scalars = (const uint64_t**)malloc(sizeof(uint64_t*) * num_batches * 2);
     const uint64_t** tables = scalars + num_batches;
     uint64_t* outs = (uint64_t*)malloc(96 * num_batches);

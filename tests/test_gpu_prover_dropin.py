@@ -35,7 +35,7 @@ def run(binary, log_gates):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("log_gates", [4, 8, 12, 14])
+@pytest.mark.parametrize("log_gates", [5, 8, 12, 14])  # 2^4 gives the recipe zero gates: the reference itself throws bad_alloc
 def test_prover_gpu_matches_cpu_reference(srs, log_gates):
     cpu = run("prover_cpu", log_gates)
     gpu = run("prover_gpu", log_gates)

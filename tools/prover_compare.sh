@@ -8,7 +8,7 @@ N=$((1 << LG))
 mkdir -p build/srs gpurun_out
 need=$((64 * (N - 1) + 28 + 256 + 64))
 have=$(stat -c %s build/srs/transcript.dat 2>/dev/null || echo 0)
-if [ "$have" -lt "$need" ]; then ./build/make_srs $N build/srs/transcript.dat; fi
+if [ "$have" -lt "$need" ]; then ./build/make_srs $N build/srs/transcript.dat 1>&2; fi
 export OMP_NUM_THREADS=$(python3 -c "import os;c=os.cpu_count();p=1
 while p*2<=c:p*=2
 print(p)")
