@@ -322,7 +322,15 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* sor
 }
 
 // ---- 5. fix-up of buckets that span slices; empty buckets become infinity ----------------------------
-__global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets, uint32_t S, fe* buckets, const fe* head, const fe* tail)
+// A bucket cut by slice edges = tail[s0] + head[s0+1] + ... + head[s1].  Short spans are summed by the bucket's own
+// thread; long ones (one digit value shared by very many scalars: constant or highly repetitive polynomials do
+// occur in the prover) are queued and reduced by a whole block each, so the cost of a giant bucket is
+// O(span / 128 + log 128) additions instead of O(span).
+constexpr uint32_t FIXUP_SERIAL_SPAN = 16;
+constexpr int FIXUP_LARGE_GRID = 592; // 4 x 148: each block loops over queued buckets
+constexpr int FIXUP_BLOCK = 128;
+__global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets, uint32_t S, fe* buckets, const fe* head, const fe* tail,
+                                 uint32_t* work_count, uint32_t* work_list)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
@@ -334,9 +342,38 @@ __global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets
     }
     const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
     if (s0 == s1) return;
+    if (s1 - s0 > FIXUP_SERIAL_SPAN)
+    {
+        work_list[atomicAdd(work_count, 1u)] = b;
+        return;
+    }
     xyzz_pt sum = load_xyzz(tail + 4 * (size_t)s0);
     for (uint32_t s = s0 + 1; s <= s1; ++s) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
     store_xyzz(buckets + 4 * (size_t)b, sum);
+}
+__global__ void __launch_bounds__(FIXUP_BLOCK) msm_fixup_large_kernel(const uint32_t* offsets, uint32_t S, fe* buckets, const fe* head, const fe* tail,
+                                                                      const uint32_t* work_count, const uint32_t* work_list)
+{
+    __shared__ uint32_t sm[FIXUP_BLOCK * 32];
+    const uint32_t count = *work_count;
+    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x)
+    {
+        const uint32_t b = work_list[item];
+        const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+        const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
+        xyzz_pt sum = G1::infinity();
+        if (threadIdx.x == 0) sum = load_xyzz(tail + 4 * (size_t)s0);
+        for (uint32_t s = s0 + 1 + threadIdx.x; s <= s1; s += FIXUP_BLOCK) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
+        for (int off = FIXUP_BLOCK / 2; off > 0; off >>= 1)
+        {
+            __syncthreads();
+            if ((int)threadIdx.x >= off && (int)threadIdx.x < 2 * off) store_xyzz(sm + 32 * (threadIdx.x - off), sum);
+            __syncthreads();
+            if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
+        }
+        if (threadIdx.x == 0) store_xyzz(buckets + 4 * (size_t)b, sum);
+        __syncthreads();
+    }
 }
 
 // ---- 6a. chunk running sums: A_t = sum_v B, V_t = sum_v v * B  (v = 0 .. 2^chunk_log - 1) ---------------
@@ -537,12 +574,14 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     const size_t o_sorted = carve(pl.max_entries * 4 + 16);
     const size_t o_counts = carve((size_t)pl.total_buckets * 4);
     const size_t o_fill = carve((size_t)pl.total_buckets * 4);
+    const size_t o_work_count = carve(256); // directly after fill: zeroed by the same memset
     const size_t o_offsets = carve(((size_t)pl.total_buckets + 1) * 4);
     const uint32_t scan_blocks = (pl.total_buckets + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
     const size_t o_spine = carve(((size_t)scan_blocks + 1) * 4);
     const size_t o_buckets = carve((size_t)pl.total_buckets * 128);
     const size_t o_head = carve(pl.max_slices * 128);
     const size_t o_tail = carve(pl.max_slices * 128);
+    const size_t o_work_list = carve((pl.max_slices / FIXUP_SERIAL_SPAN + 2) * 4);
     const uint32_t total_chunks = pl.chunks_per_window * (uint32_t)pl.W;
     const size_t o_A = carve((size_t)total_chunks * 128);
     const size_t o_V = carve((size_t)total_chunks * 128);
@@ -559,12 +598,14 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     fe* buckets = (fe*)(ws + o_buckets);
     fe* head = (fe*)(ws + o_head);
     fe* tail = (fe*)(ws + o_tail);
+    uint32_t* work_count = (uint32_t*)(ws + o_work_count);
+    uint32_t* work_list = (uint32_t*)(ws + o_work_list);
     fe* A = (fe*)(ws + o_A);
     fe* V = (fe*)(ws + o_V);
     fe* red = (fe*)(ws + o_red);
 
-    // counts and fill are adjacent: one memset
-    BBG_CHECK(bbg_rt::dev_memset(counts, 0, (o_fill - o_counts) + (size_t)pl.total_buckets * 4, st));
+    // counts, fill and the fix-up work counter are adjacent: one memset
+    BBG_CHECK(bbg_rt::dev_memset(counts, 0, (o_work_count - o_counts) + 256, st));
     {
         bbg_prof::Scope prof(bbg_prof::MSM_DIGITS, st);
         BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars, n, pl.c, pl.W, pl.NB, digits, counts);
@@ -587,7 +628,9 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     {
         bbg_prof::Scope prof(bbg_prof::MSM_FIXUP, st);
         BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, (const uint32_t*)offsets, pl.total_buckets, pl.S, buckets,
-                          (const fe*)head, (const fe*)tail);
+                          (const fe*)head, (const fe*)tail, work_count, work_list);
+        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, (const uint32_t*)offsets, pl.S, buckets, (const fe*)head,
+                   (const fe*)tail, (const uint32_t*)work_count, (const uint32_t*)work_list);
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_CHUNK, st);
@@ -598,7 +641,7 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
         BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.W), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V,
                    pl.chunks_per_window, pl.reduce_outputs - 2, red);
     }
-    g_msm_launches += 9;
+    g_msm_launches += 10;
     BBG_CHECK(bbg_rt::last_error());
 
     // ---- 7. host finish -----------------------------------------------------------------------------

@@ -14,7 +14,7 @@
 //               coset factors) read coalesced in the same pattern as the data.
 //       pass B  (row tiles, scratch -> out): for each row i1, N2-point DIF over j2, output transposed
 //               to natural order X[i1 + N1 i2], canonical reduction fused into the store.
-//     A tile is 2048 elements (64 KiB as eight 32-bit limb planes, padded against bank conflicts)
+//     A tile is 2048 elements (64 KiB as eight 32-bit limb planes, XOR-swizzled against bank conflicts)
 //     processed by 256 threads holding 8 elements each: radix-8 butterflies in registers, one shared
 //     memory exchange per 3 stages.  Sub-transform twiddles live in shared memory (33 KiB image);
 //     2 CTAs/SM (2 x 99 KiB smem, <=128 regs).  Work per element: (log2 n)/2 products + 1 for the
@@ -35,22 +35,26 @@ namespace nttk
 constexpr int TILE_LOG = 11;
 constexpr int TILE = 1 << TILE_LOG;
 constexpr int NT = 256;
-constexpr int PLANE = TILE + (TILE >> 5);  // words per limb plane (padded)
+constexpr int PLANE = TILE;                 // words per limb plane
 constexpr int TWP = (TILE >> 1) + (TILE >> 6); // words per twiddle limb plane (padded)
 constexpr size_t SMEM_BYTES = (size_t)(8 * PLANE + 8 * TWP) * 4;
 constexpr int LO_TABLE_LOG = 11; // w^e = Thi[e >> 11] * Tlo[e & 2047] when generating matrices
 
-BBG_HD int pad(int q) { return q + (q >> 5); }
+BBG_HD int pad(int q) { return q + (q >> 5); }          // twiddle planes: power-of-two strides
+// data planes: XOR swizzle of the bank bits with tile-slot bits 3..7.  A bijection on [0, TILE) that makes every
+// access pattern of every radix step conflict-free (checked exhaustively for all sub-transform lengths and both
+// tile layouts; the padded layout q + q/32 left 2- and 4-way conflicts in the low-bit steps, ncu r01).
+BBG_HD int dswz(int q) { return q ^ ((q >> 3) & 31); }
 
 BBG_D void sm_store(uint32_t* data, int q, const fe& x)
 {
-    const int p = pad(q);
+    const int p = dswz(q);
 #pragma unroll
     for (int l = 0; l < 8; ++l) data[l * PLANE + p] = x.v[l];
 }
 BBG_D fe sm_load(const uint32_t* data, int q)
 {
-    const int p = pad(q);
+    const int p = dswz(q);
     fe r;
 #pragma unroll
     for (int l = 0; l < 8; ++l) r.v[l] = data[l * PLANE + p];

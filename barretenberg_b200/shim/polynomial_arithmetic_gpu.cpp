@@ -32,6 +32,7 @@ void run(barretenberg::fr::field_t* coeffs, const barretenberg::evaluation_domai
         const char* dev = getenv("BBG_DEVICE");
         e = bbg_init(dev ? atoi(dev) : 0);
         if (e == 0) bbg_set_auto_srs_cache(1);
+        if (e == 0) bbg_shim::stats().after_init();
         ready = (e == 0);
     }
     bbg_shim::Timer timer(what);

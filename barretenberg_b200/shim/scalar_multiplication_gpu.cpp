@@ -39,12 +39,16 @@ void ensure_init()
     int e = bbg_init(dev ? atoi(dev) : 0);
     if (e != 0) die("bbg_init", e);
     bbg_set_auto_srs_cache(1);
+    bbg_shim::stats().after_init();
     done = true;
 }
 static_assert(sizeof(barretenberg::fr::field_t) == 32, "field_t layout");
 static_assert(sizeof(barretenberg::g1::affine_element) == 64, "affine_element layout");
 static_assert(sizeof(barretenberg::g1::element) == 96, "element layout");
 } // namespace
+
+// Optional: print the BBG_SHIM_STATS=1 call / kernel statistics (call before main returns).
+extern "C" void bbg_shim_report(void) { bbg_shim::stats().report(); }
 
 namespace barretenberg
 {

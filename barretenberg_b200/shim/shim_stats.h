@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "bbgpu.h"
+
 namespace bbg_shim
 {
 struct Stats
@@ -22,13 +24,27 @@ struct Stats
         const char* e = getenv("BBG_SHIM_STATS");
         enabled = e != nullptr && e[0] == '1';
     }
-    ~Stats()
+    // Printed on request only (bbg_shim_report(), called from main): the CUDA runtime may already be torn down
+    // when static destructors run, so nothing here happens at process exit.
+    void report()
     {
         if (!enabled) return;
         double total = 0;
         for (int i = 0; i < count; ++i) total += ms[i];
         fprintf(stderr, "bbgpu shim stats: %.1f ms behind the boundary\n", total);
         for (int i = 0; i < count; ++i) fprintf(stderr, "  %-32s calls %5lu  units %5lu  %10.2f ms\n", name[i], calls[i], units[i], ms[i]);
+        fprintf(stderr, "bbgpu kernel profile (CUDA events):\n");
+        for (int i = 0; i < bbg_profile_count(); ++i)
+        {
+            double t = 0;
+            uint64_t n = 0;
+            if (bbg_profile_read(i, &t, &n) == 0 && n > 0) fprintf(stderr, "  %-32s launches %5lu  %10.2f ms\n", bbg_profile_name(i), (unsigned long)n, t);
+        }
+    }
+    // call once the library is initialised: switches the per-kernel stopwatch on when statistics are requested
+    void after_init()
+    {
+        if (enabled) bbg_profile_enable(1);
     }
     void add(const char* n, double t, unsigned long u)
     {

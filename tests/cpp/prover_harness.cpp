@@ -21,6 +21,9 @@
 
 using namespace barretenberg;
 
+// present only in the shim build (barretenberg_b200/shim/scalar_multiplication_gpu.cpp)
+extern "C" void bbg_shim_report(void) __attribute__((weak));
+
 static uint64_t sm_state = 0x853c49e6748fea9bULL;
 static uint64_t splitmix()
 {
@@ -115,5 +118,6 @@ int main(int argc, char** argv)
     print_fe("z_1_shifted_eval", proof.z_1_shifted_eval.data);
     print_fe("linear_eval", proof.linear_eval.data, true);
     printf("}}\n");
+    if (bbg_shim_report) bbg_shim_report();
     return ok ? 0 : 1;
 }

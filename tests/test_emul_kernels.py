@@ -108,6 +108,18 @@ def test_msm_edge_cases(emu):
     assert (emu.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
 
 
+def test_msm_giant_bucket_block_fixup(emu):
+    """One digit value shared by every scalar -> a bucket spanning > 16 slices -> the block-reduction fix-up path."""
+    n = 1500
+    table, a0, d = H.generator_multiples_table(13, n)
+    sc = np.tile(H.random_scalars_mont(99, 1)[0], (n, 1))
+    assert (emu.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+    # a few distinct values only: several large buckets per window
+    vals = H.random_scalars_mont(98, 3)
+    sc = vals[np.arange(n) % 3]
+    assert (emu.msm(np.ascontiguousarray(sc), table) == H.closed_form_msm(np.ascontiguousarray(sc), a0, d)).all()
+
+
 def test_batched_msm_and_srs_cache(emu):
     n = 256
     table, _, _ = H.generator_multiples_table(21, n)

@@ -179,6 +179,23 @@ def test_msm_edge_cases(lib):
     assert (lib.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
 
 
+@pytest.mark.parametrize("distinct", [1, 3, 1000])
+def test_msm_repetitive_scalars_giant_buckets(lib, distinct):
+    """Constant / highly repetitive scalar vectors (they occur in the prover) give buckets spanning thousands of
+    slices: exercises the block-reduction fix-up path and must stay fast."""
+    import time
+    n = 1 << 18
+    table, a0, d = H.generator_multiples_table(13, n)
+    vals = H.random_scalars_mont(97, distinct)
+    sc = np.ascontiguousarray(vals[np.arange(n) % distinct])
+    lib.msm(sc, table)
+    t0 = time.perf_counter()
+    got = lib.msm(sc, table)
+    ms = (time.perf_counter() - t0) * 1e3
+    assert (got == H.closed_form_msm(sc, a0, d)).all()
+    assert ms < 100, "degenerate digit distribution took %.1f ms" % ms
+
+
 def test_batched_msm_and_srs_cache(lib):
     n = 4096
     table, _, _ = H.generator_multiples_table(21, n)
