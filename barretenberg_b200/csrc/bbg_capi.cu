@@ -4,6 +4,7 @@
 #include "../../include/bbgpu.h"
 #include "bbg_internal.h"
 #include "bbg_host_g1.h"
+#include "bbg_hostcopy.h"
 
 #include <mutex>
 #include <vector>
@@ -147,13 +148,13 @@ int resolve_table(const uint64_t* points, size_t n, const void** d_table)
         s.automatic = true;
         s.fingerprint = table_fingerprint(points, n);
         BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
-        BBG_CHECK(bbg_rt::h2d(s.d_table, points, n * 128, g_stream));
+        BBG_CHECK(bbg_hostcopy::h2d(s.d_table, points, n * 128, g_stream));
         g_srs.push_back(s);
         *d_table = s.d_table;
         return 0;
     }
     BBG_CHECK(g_stage_table.ensure(n * 128));
-    BBG_CHECK(bbg_rt::h2d(g_stage_table.p, points, n * 128, g_stream));
+    BBG_CHECK(bbg_hostcopy::h2d(g_stage_table.p, points, n * 128, g_stream));
     *d_table = g_stage_table.p;
     return 0;
 }
@@ -169,7 +170,7 @@ int msm_host(const uint64_t* scalars, const uint64_t* points, size_t n, hostg1::
     const void* d_table = nullptr;
     BBG_CHECK(resolve_table(points, n, &d_table));
     BBG_CHECK(g_stage_scalars.ensure(n * 32));
-    BBG_CHECK(bbg_rt::h2d(g_stage_scalars.p, scalars, n * 32, g_stream));
+    BBG_CHECK(bbg_hostcopy::h2d(g_stage_scalars.p, scalars, n * 32, g_stream));
     return msm_device(g_stage_scalars.p, d_table, n, out, g_stream);
 }
 } // namespace
@@ -220,6 +221,7 @@ int bbg_shutdown(void)
     g_ev_start = g_ev_stop = nullptr;
     for (cudaEvent_t ev : g_pipe_events) cudaEventDestroy(ev);
     g_pipe_events.clear();
+    bbg_hostcopy::ring().release();
     if (g_copy_in) cudaStreamDestroy(g_copy_in);
     if (g_copy_out) cudaStreamDestroy(g_copy_out);
     g_copy_in = g_copy_out = nullptr;
@@ -289,7 +291,9 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
         if (coeffs[i] == nullptr) return BBG_E_BAD_ARGUMENT;
     }
 #ifndef BBG_EMULATE
-    if (batch > 1)
+    bool all_pinned = batch > 1;
+    for (size_t i = 0; i < batch && all_pinned; ++i) all_pinned = bbg_hostcopy::is_pinned(coeffs[i]);
+    if (all_pinned)
     {
         // three-stage pipeline over polynomials: upload i+1 | transform i | download i-1 (PCIe is full duplex)
         while (g_pipe_events.size() < 2 * batch + 1)
@@ -318,9 +322,9 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
         return bbg_rt::sync(g_stream);
     }
 #endif
-    for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_rt::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_stream));
+    for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_hostcopy::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_stream));
     BBG_CHECK(ntt_device(g_stage_coeffs.p, n, batch, log2_n, op, constant, g_stream));
-    for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_rt::d2h(coeffs[i], (char*)g_stage_coeffs.p + i * bytes, bytes, g_stream));
+    for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_hostcopy::d2h(coeffs[i], (char*)g_stage_coeffs.p + i * bytes, bytes, g_stream));
     return bbg_rt::sync(g_stream);
 }
 
@@ -352,7 +356,7 @@ int bbg_srs_register(const uint64_t* table_2n, size_t n)
     s.automatic = false;
     s.fingerprint = table_fingerprint(table_2n, n);
     BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
-    BBG_CHECK(bbg_rt::h2d(s.d_table, table_2n, n * 128, g_stream));
+    BBG_CHECK(bbg_hostcopy::h2d(s.d_table, table_2n, n * 128, g_stream));
     BBG_CHECK(bbg_rt::sync(g_stream));
     g_srs.push_back(s);
     return 0;
@@ -443,9 +447,9 @@ int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table
     void *d_pts = nullptr, *d_tab = nullptr;
     BBG_CHECK(bbg_rt::dev_alloc(&d_pts, n * 64));
     int e = bbg_rt::dev_alloc(&d_tab, n * 128);
-    if (e == 0) e = bbg_rt::h2d(d_pts, points_n, n * 64, g_stream);
+    if (e == 0) e = bbg_hostcopy::h2d(d_pts, points_n, n * 64, g_stream);
     if (e == 0) e = g1_build_endo_table_device(d_pts, d_tab, n, g_stream);
-    if (e == 0) e = bbg_rt::d2h(table_2n, d_tab, n * 128, g_stream);
+    if (e == 0) e = bbg_hostcopy::d2h(table_2n, d_tab, n * 128, g_stream);
     if (e == 0) e = bbg_rt::sync(g_stream);
     bbg_rt::dev_free(d_pts);
     if (d_tab) bbg_rt::dev_free(d_tab);

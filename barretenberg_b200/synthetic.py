@@ -61,11 +61,23 @@ def mont(x, modulus=FR_MODULUS):
 
 
 def dot_mod_r(scalars_mont, a0, d):
-    """(sum_i k_i * (a0 + i d)) mod r for Montgomery-form scalar limbs (value k_i = limbs * R^-1)."""
+    """(sum_i k_i * (a0 + i d)) mod r for Montgomery-form scalar limbs (value k_i = limbs * R^-1).
+
+    Exact and vectorised: sum_i k_i (a0 + i d) = a0 * sum k_i + d * sum i k_i, with k_i cut into 16-bit columns and i
+    into bytes so every partial dot product fits a uint64 (n <= 2^26: 2^26 * 2^16 * 2^8 = 2^50)."""
     n = scalars_mont.shape[0]
-    raw = np.ascontiguousarray(scalars_mont).view(np.uint8).reshape(n, 32)
-    acc, a = 0, a0
-    for i in range(n):
-        acc += int.from_bytes(raw[i].tobytes(), "little") * a
-        a += d
-    return (acc * pow(R_MONT, -1, FR_MODULUS)) % FR_MODULUS
+    if n == 0:
+        return 0
+    if n > (1 << 32):
+        raise ValueError("dot_mod_r supports n <= 2^32")
+    cols = np.ascontiguousarray(scalars_mont).view(np.uint16).reshape(n, 16)
+    idx = np.arange(n, dtype=np.uint64)
+    idx_bytes = [((idx >> np.uint64(8 * t)) & np.uint64(0xFF)) for t in range(4)]
+    s0 = 0
+    s1 = 0
+    for c in range(16):
+        col = cols[:, c].astype(np.uint64)
+        s0 += int(col.sum(dtype=np.uint64)) << (16 * c)
+        for t in range(4):
+            s1 += int(np.dot(idx_bytes[t], col)) << (8 * t + 16 * c)
+    return ((a0 * s0 + d * s1) * pow(R_MONT, -1, FR_MODULUS)) % FR_MODULUS

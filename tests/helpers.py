@@ -168,15 +168,9 @@ def closed_form_msm(scalars, a0, d):
     """Normalised Jacobian of sum_i k_i (a0 + i d) G = ((sum_i k_i (a0 + i d)) mod r) G  (SURVEY.md §8c-3):
     one Fr dot product and one oracle scalar multiplication — no CPU MSM needed at 2^20 / 2^26."""
     lib = oracle()
-    n = scalars.shape[0]
-    rinv = pow(R_MONT, -1, FR_MODULUS)
-    raw = np.ascontiguousarray(scalars).view(np.uint8).reshape(n, 32)
-    acc = 0
-    a = a0
-    for i in range(n):
-        acc += int.from_bytes(raw[i].tobytes(), "little") * a
-        a += d
-    s = (acc * rinv) % FR_MODULUS  # scalars are Montgomery residues: value = limbs * R^-1
+    from barretenberg_b200.synthetic import dot_mod_r
+
+    s = dot_mod_r(np.ascontiguousarray(scalars), a0, d)
     gen = np.zeros(8, dtype=np.uint64)
     tmp = np.zeros(4, dtype=np.uint64)
     lib.orc_constant(11, ptr(tmp)); gen[:4] = tmp
