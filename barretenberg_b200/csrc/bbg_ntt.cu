@@ -40,6 +40,13 @@ constexpr int TWP = (TILE >> 1) + (TILE >> 6); // words per twiddle limb plane (
 constexpr size_t SMEM_BYTES = (size_t)(8 * PLANE + 8 * TWP) * 4;
 constexpr int LO_TABLE_LOG = 11; // w^e = Thi[e >> 11] * Tlo[e & 2047] when generating matrices
 
+#if defined(__CUDA_ARCH__) && defined(BBG_NTT_NOINLINE_MUL)
+// one shared copy of the Montgomery product for the pass kernels (instruction-cache footprint)
+__device__ __noinline__ fe fr_mul_shared(const fe a, const fe b) { return Fr::mul(a, b); }
+#define NTT_MUL(a, b) fr_mul_shared((a), (b))
+#else
+#define NTT_MUL(a, b) Fr::mul((a), (b))
+#endif
 BBG_HD int pad(int q) { return q + (q >> 5); }          // twiddle planes: power-of-two strides
 // data planes: XOR swizzle of the bank bits with tile-slot bits 3..7.  A bijection on [0, TILE) that makes every
 // access pattern of every radix step conflict-free (checked exhaustively for all sub-transform lengths and both
@@ -109,7 +116,7 @@ template <int L, int B, int R> BBG_D void radix_step(fe (&x)[8], int base_low, c
             else
             {
                 const int e = (base_low | (jm << B)) << (L - 1 - s);
-                x[m | half] = Fr::mul(d, tw_load(tw, e));
+                x[m | half] = NTT_MUL(d, tw_load(tw, e));
             }
         }
     }
@@ -146,7 +153,7 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             if (COLS_LOW) g = ((size_t)k << rest) + ((size_t)tile << TM::CLOG) + c;
             else g = ((((size_t)tile << TM::CLOG) + c) << L) + k;
             x[m] = load_fe(src + g);
-            if (COLS_LOW && p.vec != nullptr) x[m] = Fr::mul(x[m], load_fe(p.vec + k));
+            if (COLS_LOW && p.vec != nullptr) x[m] = NTT_MUL(x[m], load_fe(p.vec + k));
         }
     }
     else
@@ -170,15 +177,15 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             if (COLS_LOW)
             {
                 const size_t o = ((size_t)isub << rest) + ((size_t)tile << TM::CLOG) + c;
-                store_fe(dst + o, Fr::mul(x[m], load_fe(p.mat + o)));
+                store_fe(dst + o, NTT_MUL(x[m], load_fe(p.mat + o)));
             }
             else
             {
                 const size_t row = ((size_t)tile << TM::CLOG) + c;
                 const size_t o = row + ((size_t)isub << rest);
                 fe y = x[m];
-                if (p.vec != nullptr) y = Fr::mul(y, load_fe(p.vec + isub));
-                if (p.has_post_const) y = Fr::mul(y, p.post_const);
+                if (p.vec != nullptr) y = NTT_MUL(y, load_fe(p.vec + isub));
+                if (p.has_post_const) y = NTT_MUL(y, p.post_const);
                 store_fe(dst + o, Fr::reduce(y));
             }
         }
