@@ -503,10 +503,26 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_b200(args, rank, local_rank, world)
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on
+    # stdout): point fd 1 at stderr while working and restore it only for the final line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import contextlib
+    import io
+
+    captured = io.StringIO()
+    with contextlib.redirect_stdout(captured):
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_b200(args, rank, local_rank, world)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    out = captured.getvalue().strip()
+    if out:
+        os.write(1, (out.splitlines()[-1] + "\n").encode())
 
 
 if __name__ == "__main__":

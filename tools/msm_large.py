@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="add the per-kernel CUDA-event breakdown of one MSM")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -85,6 +86,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         times.append(dt)
+    prof = None
+    if args.profile:
+        lib.profile_enable(True)
+        run()
+        prof = {k: round(v[0] / v[1], 3) for k, v in lib.profile_read().items()}
+        lib.profile_enable(False)
     ok = None
     if rank == 0 and not args.no_check:
         t0 = time.perf_counter()
@@ -104,7 +111,7 @@ def main():
         check_s = time.perf_counter() - t0
     if rank == 0:
         print(json.dumps({"msm_log_n": args.log_n, "n_gpus": world, "ms": min(times), "ms_all": times, "points_per_rank": n_loc,
-                          "closed_form_ok": ok, "point_generation_s": gen_s, "check_s": None if ok is None else check_s}))
+                          "closed_form_ok": ok, "kernels_ms": prof, "point_generation_s": gen_s, "check_s": None if ok is None else check_s}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
