@@ -259,6 +259,7 @@ const char* bbg_error_string(int code)
     case BBG_E_BAD_ARGUMENT: return "bbgpu: bad argument";
     case BBG_E_TOO_LARGE: return "bbgpu: MSM too large";
     case 1001: return "bbgpu: internal: unsupported sub-transform size";
+    case 1009: return "bbgpu: internal: MSM window planner produced an invalid plan";
     }
 #ifndef BBG_EMULATE
     if (code > 0 && code < 1000) return cudaGetErrorString((cudaError_t)code);

@@ -521,8 +521,14 @@ void pick_windows(size_t n, int& c_out, int& W_out)
     int lg = 0;
     while (((size_t)1 << lg) < 2 * n) ++lg;
     const int target = lg - 5;
+    int c_lo = target - 4 < 5 ? 5 : target - 4;
+    if (c_lo > 22) c_lo = 22;
+    int c_hi = target + 3 > 22 ? 22 : target + 3;
+    if (c_hi < c_lo) c_hi = c_lo; // tiny n: the range collapses to the smallest window
     double best = -1;
-    for (int c = (target - 4 < 5 ? 5 : target - 4); c <= (target + 3 > 22 ? 22 : target + 3); ++c)
+    c_out = c_lo;
+    W_out = (128 + c_lo - 1) / c_lo;
+    for (int c = c_lo; c <= c_hi; ++c)
     {
         int W = (128 + c - 1) / c;
         while ((W - 1) * c >= 127) --W;
@@ -580,6 +586,7 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     }
     if (2 * n > ((size_t)1 << 28)) return 1008;
     const Plan pl = make_plan(n);
+    if (pl.c < 2 || pl.c > 22 || pl.W < 1 || pl.W > 64 || (pl.W - 1) * pl.c >= 127 || pl.W * pl.c < 128) return 1009; // planner invariant
     if (pl.max_entries >= ((size_t)1 << 32)) return 1008;
 
     // carve the workspace
