@@ -104,6 +104,32 @@ template <typename F> __global__ void __launch_bounds__(MB_THREADS) field_mul_ke
     for (int i = 0; i < 8; ++i) s ^= a.v[i] ^ b.v[i];
     out[tid] = s;
 }
+// modes 5-7: CHAINS independent product chains per thread at the NTT kernel's occupancy (2 x 256 threads per SM)
+template <int CHAINS> __global__ void __launch_bounds__(MB_THREADS, 2) field_mul_ilp_kernel(uint32_t* out, uint32_t seed, int iters)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    fe a[CHAINS], m = Fr::one();
+    m.v[0] += (seed ^ tid) & 0xff;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+    {
+        a[c] = Fr::one();
+        a[c].v[c & 7] ^= tid + c;
+    }
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) a[c] = Fr::mul(a[c], m);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= a[c].v[i];
+    }
+    out[tid] = s;
+}
 } // namespace
 
 // returns ops (32x32 multiply-adds, or field products) issued by the whole grid
@@ -132,6 +158,18 @@ int microbench_launch(int mode, int iters, uint32_t* d_out, int blocks, double* 
         BBG_LAUNCH_NOSYNC(field_mul_kernel<Fr>, dim3(blocks), dim3(MB_THREADS), st, d_out, 12345u, iters);
         *ops = threads * iters * 2.0;
         break;
+    case 5:
+    case 6:
+    case 7:
+    {
+        // 2 resident CTAs per SM exactly: grid = 2 x #SM, the 16 warps/SM the NTT pass kernels run at
+        const int sm2 = 2 * bbg_rt::num_sms();
+        const double thr = (double)sm2 * MB_THREADS;
+        if (mode == 5) { BBG_LAUNCH_NOSYNC(field_mul_ilp_kernel<1>, dim3(sm2), dim3(MB_THREADS), st, d_out, 12345u, iters * 8); *ops = thr * iters * 8.0; }
+        if (mode == 6) { BBG_LAUNCH_NOSYNC(field_mul_ilp_kernel<2>, dim3(sm2), dim3(MB_THREADS), st, d_out, 12345u, iters * 4); *ops = thr * iters * 8.0; }
+        if (mode == 7) { BBG_LAUNCH_NOSYNC(field_mul_ilp_kernel<4>, dim3(sm2), dim3(MB_THREADS), st, d_out, 12345u, iters * 2); *ops = thr * iters * 8.0; }
+        break;
+    }
     default: return 1007;
     }
     return bbg_rt::last_error();

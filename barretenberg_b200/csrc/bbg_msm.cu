@@ -19,10 +19,10 @@
 //               additions acc += +-P (XYZZ coordinates, 10 field products) and flushes at bucket boundaries;
 //               runs cut by a slice boundary go to per-slice head/tail slots.
 //   5. fix-up   one thread per bucket that spans slices: tail + heads.
-//   6. reduce   window sum = sum_b (b+1) * B_b: threads take chunks of 16 buckets (local running sums, the
+//   6. reduce   window sum = sum_b (b+1) * B_b: threads take chunks of 8 buckets (local running sums, the
 //               reference's :628-640 loop in miniature), then block-wide tree reductions produce per window the
 //               plain sums and the log2(chunks) bit-sliced sums T_r = sum_{t: bit r of t} A_t.
-//   7. finish   host: S_w = sum V + sum A + 16 * sum_r 2^r T_r, fold windows, normalise (bbg_host_g1.h).
+//   7. finish   host: S_w = sum V + sum A + 8 * sum_r 2^r T_r, fold windows, normalise (bbg_host_g1.h).
 //
 // Work at n = 2^20 (c = 16, W = 8): 2^24 mixed adds (1.68e8 Fq products) + ~2^20 full adds; HBM: 64 MiB digits
 // written + read, 64 MiB sorted entries, ~1 GiB of 64-byte point gathers mostly served from L2.
@@ -37,7 +37,7 @@ namespace bbg
 namespace msmk
 {
 constexpr uint32_t NO_DIGIT = 0xffffffffu;
-constexpr int CHUNK_LOG = 4; // buckets per running-sum thread in stage 6
+constexpr int CHUNK_LOG = 3; // buckets per running-sum thread in stage 6 (serial depth 2 * 2^CHUNK_LOG - 1 additions)
 
 struct Plan
 {
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(128) msm_chunk_kernel(const fe* buckets, uint3
 // ---- 6b. block tree reductions: out[w][r] -------------------------------------------------------------
 // r < chunk_bits : sum of A_t over chunks t of window w with bit r set
 // r = chunk_bits : sum of V_t;   r = chunk_bits + 1 : sum of A_t
-constexpr int RED_BLOCK = 128;
+constexpr int RED_BLOCK = 256;
 __global__ void __launch_bounds__(RED_BLOCK) msm_reduce_kernel(const fe* A, const fe* V, uint32_t chunks_per_window, int chunk_bits, fe* out)
 {
     __shared__ uint32_t sm[RED_BLOCK * 32];
@@ -511,11 +511,13 @@ struct Workspace
     }
 } g_ws;
 
-// Window plan.  Cost model in units of one mixed addition (measured on B200 at 2^20: accumulate 0.16 ns per entry,
-// bucket phases ~1.9 ns per bucket ~= 12 entries): W * (2n + 12 * 2^(c-1)), W = windows needed for 127-bit half
-// scalars.  A narrow top window (few real bits left over) funnels all 2n of its entries into 2^top buckets —
-// atomic contention in the histogram / scatter and giant buckets — so it is penalised; e.g. c = 21 at 2^25 points
-// left a 1-bit top window and cost 158 ms against 108 ms for c = 19.
+// Window plan.  Cost model in units of one mixed addition, fitted to B200 measurements (r01, 2^17 .. 2^26 points):
+//   per entry  1.13  (accumulate 0.16 ns + histogram / scatter atomics), + 0.15 when there are fewer than 2^16 buckets
+//              in total (few distinct counters: the L2 atomic units serialise);
+//   per bucket 11 (chunk + reduce + fix-up, ~1.8 ns) + 0.3 * avg_bucket_size / 64 (buckets cut by slice edges).
+// A narrow top window (few real bits left over) funnels all 2n of its entries into 2^top buckets — heavy atomic
+// contention and giant buckets — so it is penalised; e.g. c = 21 at 2^25 points left a 1-bit top window and cost
+// 158 ms against 88 ms for c = 19.
 void pick_windows(size_t n, int& c_out, int& W_out)
 {
     int lg = 0;
@@ -533,7 +535,10 @@ void pick_windows(size_t n, int& c_out, int& W_out)
         int W = (128 + c - 1) / c;
         while ((W - 1) * c >= 127) --W;
         const int top_bits = 127 - (W - 1) * c;
-        double cost = (double)W * 2.0 * (double)n + 12.0 * W * (double)((size_t)1 << (c - 1));
+        const double buckets = (double)((size_t)1 << (c - 1));
+        const double avg = 2.0 * (double)n / buckets;
+        const double per_entry = 1.13 + ((double)W * buckets < 65536.0 ? 0.15 : 0.0);
+        double cost = (double)W * 2.0 * (double)n * per_entry + (double)W * buckets * (11.0 + 0.3 * avg / 64.0);
         if (top_bits < 10) cost += 2.0 * (double)n * (10 - top_bits) / 4.0;
         if (best < 0 || cost < best)
         {
