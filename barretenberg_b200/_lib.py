@@ -63,6 +63,7 @@ class Library:
         L.bbg_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
         L.bbg_g1_generate_multiples_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.bbg_generate_pippenger_point_table_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.bbg_compute_lagrange_polynomial_fft.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
         L.bbg_profile_name.restype = C.c_char_p
         L.bbg_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         self.check(L.bbg_init(device))
@@ -152,6 +153,11 @@ class Library:
             ptrs = (C.c_void_p * batch)(*[a[i].ctypes.data for i in range(batch)])
             self.check(self.lib.bbg_ntt_fr_batched(ptrs, batch, log_n, opc, kp))
         return a
+
+    def compute_lagrange_polynomial_fft(self, log2_src, log2_target):
+        out = np.zeros((1 << log2_target, 4), dtype=np.uint64)
+        self.check(self.lib.bbg_compute_lagrange_polynomial_fft(out.ctypes.data_as(C.c_void_p), log2_src, log2_target))
+        return out
 
     def ntt_dev(self, op, d_ptr, log_n, batch=1, stride=None, constant=None):
         opc = self.OPS[op] if isinstance(op, str) else int(op)

@@ -335,6 +335,27 @@ int bbg_ntt_fr(uint64_t* coeffs, unsigned log2_n, int op, const uint64_t* consta
     return bbg_ntt_fr_batched(one, 1, log2_n, op, constant);
 }
 
+int bbg_compute_lagrange_polynomial_fft(uint64_t* l_1_coefficients, unsigned log2_src, unsigned log2_target)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (l_1_coefficients == nullptr) return BBG_E_BAD_ARGUMENT;
+    if (log2_target < log2_src || log2_target > 24) return BBG_E_BAD_SIZE;
+    const size_t bytes = ((size_t)32) << log2_target;
+    BBG_CHECK(g_stage_coeffs.ensure(bytes));
+    BBG_CHECK(lagrange_fft_device(g_stage_coeffs.p, log2_src, log2_target, g_stream));
+    BBG_CHECK(bbg_hostcopy::d2h(l_1_coefficients, g_stage_coeffs.p, bytes, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+
+int bbg_compute_lagrange_polynomial_fft_dev(void* d_out, unsigned log2_src, unsigned log2_target)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (d_out == nullptr) return BBG_E_BAD_ARGUMENT;
+    return lagrange_fft_device(d_out, log2_src, log2_target, g_stream);
+}
+
 // ---- MSM ----------------------------------------------------------------------------------------
 int bbg_srs_register(const uint64_t* table_2n, size_t n)
 {

@@ -318,6 +318,38 @@ __global__ void gen_matrix_kernel(fe* M, const fe* lo, const fe* hi, const fe* r
     if (cf != nullptr) w = Fr::mul(w, load_fe(cf + j2));
     store_fe(M + idx, w);
 }
+// compute_lagrange_polynomial_fft (polynomial_arithmetic.cpp:381-476): the target-domain coset evaluations of
+// L_1(X) = (X^n - 1) / (n (X - 1)):  out[i] = numer[i mod S] / (g * w_T^i - 1),  numer[j] = (g^n * w_S^j - 1) / n,
+// S = T / n.  The reference inverts all T denominators with one serial Montgomery-trick sweep; here every thread
+// owns a run of LAGRANGE_RUN consecutive i (denominators by repeated multiplication with w_T, prefix products, ONE
+// Fermat inversion, back-substitution): ~15 products per element instead of a serial chain.
+constexpr int LAGRANGE_RUN = 32;
+__global__ void __launch_bounds__(64) lagrange_fft_kernel(fe* out, fe root_T, fe generator, const fe* numer, unsigned S_mask, unsigned T)
+{
+    const unsigned run = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first = run * LAGRANGE_RUN;
+    if (first >= T) return;
+    const int count = (int)((T - first < (unsigned)LAGRANGE_RUN) ? T - first : LAGRANGE_RUN);
+    const fe one = Fr::one();
+    fe x = Fr::mul(generator, Fr::pow_u64(root_T, first)); // g * w_T^first
+    fe den[LAGRANGE_RUN], prefix[LAGRANGE_RUN];
+    fe acc = one;
+    for (int i = 0; i < count; ++i)
+    {
+        den[i] = Fr::sub(x, one);
+        prefix[i] = acc;
+        acc = Fr::mul(acc, den[i]);
+        x = Fr::mul(x, root_T);
+    }
+    fe inv = Fr::invert(acc);
+    for (int i = count - 1; i >= 0; --i)
+    {
+        const fe d_inv = Fr::mul(inv, prefix[i]);
+        inv = Fr::mul(inv, den[i]);
+        store_fe(out + first + i, Fr::mul_full(d_inv, load_fe(numer + ((first + i) & S_mask))));
+    }
+}
+
 // out[i] = in[i] * k
 __global__ void scale_vector_kernel(fe* out, const fe* in, fe k, unsigned count)
 {
@@ -551,6 +583,33 @@ template <bool COLS_LOW> int launch_pass(int L, const PassParams& p, cudaStream_
 } // namespace
 
 size_t ntt_launch_count() { return g_ntt_launches; }
+
+// d_out: T = 2^log_target field elements on the device
+int lagrange_fft_device(void* d_out, unsigned log_src, unsigned log_target, cudaStream_t st)
+{
+    if (log_target < log_src || log_target > 28 || log_target - log_src > 10) return 1002;
+    const unsigned T = 1u << log_target, S = 1u << (log_target - log_src);
+    // numer[j] = (g^n * w_S^j - 1) / n on the host: S is 2 or 4 in the prover (compute_multiplicative_subgroup, :104-127)
+    fe gn = COSET_GEN;
+    for (unsigned i = 0; i < log_src; ++i) gn = Fr::reduce(Fr::sqr(gn));
+    const fe w_S = host_root_of_unity(log_target - log_src);
+    const fe n_inv = host_domain_inverse(log_src);
+    std::vector<fe> numer(S);
+    fe cur = gn;
+    for (unsigned j = 0; j < S; ++j)
+    {
+        numer[j] = Fr::mul_full(Fr::sub(cur, Fr::one()), n_inv);
+        cur = Fr::mul_full(cur, w_S);
+    }
+    BBG_CHECK(g_tables.tmp_vec.ensure((size_t)S * 32));
+    BBG_CHECK(bbg_rt::h2d(g_tables.tmp_vec.p, numer.data(), (size_t)S * 32, st));
+    BBG_CHECK(bbg_rt::sync(st)); // numer is a stack-lifetime host buffer
+    const unsigned runs = (T + LAGRANGE_RUN - 1) / LAGRANGE_RUN;
+    BBG_LAUNCH_NOSYNC(lagrange_fft_kernel, dim3((runs + 63) / 64), dim3(64), st, (fe*)d_out, host_root_of_unity(log_target), COSET_GEN,
+                      (const fe*)g_tables.tmp_vec.p, S - 1, T);
+    ++g_ntt_launches;
+    return bbg_rt::last_error();
+}
 
 int ntt_release_tables()
 {

@@ -59,3 +59,8 @@ def coset_fft_with_constant(coeffs, domain, constant):
 
 def coset_ifft(coeffs, domain):
     return _run("coset_ifft", coeffs, domain)
+
+
+def compute_lagrange_polynomial_fft(src_domain, target_domain):
+    """The target-domain coset evaluations of L_1 (polynomial_arithmetic.cpp:381-476) as a new (target.size, 4) array."""
+    return target_domain._lib().compute_lagrange_polynomial_fft(src_domain.log2_size, target_domain.log2_size)

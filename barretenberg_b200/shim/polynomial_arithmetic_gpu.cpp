@@ -8,6 +8,7 @@
 //   -Dfft=cpu_reference_fft -Difft=cpu_reference_ifft -Dfft_with_constant=cpu_reference_fft_with_constant
 //   -Difft_with_constant=cpu_reference_ifft_with_constant -Dcoset_fft=cpu_reference_coset_fft
 //   -Dcoset_fft_with_constant=cpu_reference_coset_fft_with_constant -Dcoset_ifft=cpu_reference_coset_ifft
+//   -Dcompute_lagrange_polynomial_fft=cpu_reference_compute_lagrange_polynomial_fft
 // (its element-wise helpers — evaluate, divide_by_pseudo_vanishing_polynomial, compute_kate_opening_coefficients,
 // ... — keep their reference CPU bodies) and add this file for the seven names above.
 // evaluation_domain.cpp is unchanged: only domain.log2_size crosses the boundary; root, 1/n, the coset generator
@@ -65,5 +66,30 @@ void coset_fft_with_constant(fr::field_t* coeffs, const evaluation_domain& domai
     run(coeffs, domain, BBG_COSET_FFT_WITH_CONSTANT, &constant, "coset_fft_with_constant");
 }
 void coset_ifft(fr::field_t* coeffs, const evaluation_domain& domain) { run(coeffs, domain, BBG_COSET_IFFT, nullptr, "coset_ifft"); }
+
+// polynomial_arithmetic.cpp:381-476 (first widening into SURVEY.md §8f): output-only, so no upload is needed.
+// Build the reference file with -Dcompute_lagrange_polynomial_fft=cpu_reference_compute_lagrange_polynomial_fft as well.
+void compute_lagrange_polynomial_fft(fr::field_t* l_1_coefficients, const evaluation_domain& src_domain, const evaluation_domain& target_domain)
+{
+    fr::field_t probe; // run() initialises the library; reuse it through a no-op sized call guard
+    (void)probe;
+    static bool ready = false;
+    int e = 0;
+    if (!ready)
+    {
+        const char* dev = getenv("BBG_DEVICE");
+        e = bbg_init(dev ? atoi(dev) : 0);
+        if (e == 0) bbg_set_auto_srs_cache(1);
+        if (e == 0) bbg_shim::stats().after_init();
+        ready = (e == 0);
+    }
+    bbg_shim::Timer timer("compute_lagrange_polynomial_fft");
+    if (e == 0) e = bbg_compute_lagrange_polynomial_fft((uint64_t*)l_1_coefficients, (unsigned)src_domain.log2_size, (unsigned)target_domain.log2_size);
+    if (e != 0)
+    {
+        fprintf(stderr, "bbgpu shim: compute_lagrange_polynomial_fft failed: %s (no CPU fallback)\n", bbg_error_string(e));
+        abort();
+    }
+}
 } // namespace polynomial_arithmetic
 } // namespace barretenberg

@@ -72,6 +72,13 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
 /* d_coeffs: device pointer to `batch` polynomials, `stride_elems` field elements apart, in place */
 int bbg_ntt_fr_dev(void* d_coeffs, size_t stride_elems, size_t batch, unsigned log2_n, int op, const uint64_t* constant);
 
+/* ---- element-wise helpers next to the NTT (widened one at a time) ---------------- */
+/* polynomial_arithmetic::compute_lagrange_polynomial_fft (polynomials/polynomial_arithmetic.hpp:54,
+ * polynomial_arithmetic.cpp:381-476; caller prover.cpp:351): writes the 2^log2_target coset evaluations of
+ * L_1(X) = (X^n - 1) / (n (X - 1)), n = 2^log2_src, canonical Montgomery limbs.  Output only. */
+int bbg_compute_lagrange_polynomial_fft(uint64_t* l_1_coefficients, unsigned log2_src, unsigned log2_target);
+int bbg_compute_lagrange_polynomial_fft_dev(void* d_out, unsigned log2_src, unsigned log2_target);
+
 /* ---- MSM ------------------------------------------------------------------------------------- */
 /* Register a 2n-entry point table (reference_string.cpp:20-23 owns it for the prover's lifetime): uploaded
  * once; later MSM calls whose `points` pointer lies inside [table, table + 2n) reuse the device copy

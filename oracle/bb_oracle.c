@@ -910,3 +910,33 @@ void orc_poly_evaluate(const uint64_t* coeffs, const uint64_t* z, size_t n, uint
     }
     fe_copy(out, acc);
 }
+
+/* polynomial_arithmetic.cpp:381-476: l_1[i] = numer[i mod S] / (g w_T^i - 1), numer[j] = (g^n w_S^j - 1) / n
+ * (compute_multiplicative_subgroup :104-127 supplies g^n w_S^j).  Value-equivalent: canonical outputs. */
+void orc_compute_lagrange_polynomial_fft(uint64_t* l_1, size_t log2_src, size_t log2_target)
+{
+    size_t T = (size_t)1 << log2_target, S = (size_t)1 << (log2_target - log2_src);
+    orc_domain* src = orc_domain_new((size_t)1 << log2_src);
+    orc_domain* tgt = orc_domain_new(T);
+    uint64_t root_S[4], gn[4], numer[1024][4], x[4], den[4], inv[4];
+    fe_copy(root_S, FR_ROOT_OF_UNITY);
+    for (size_t i = 28; i > log2_target - log2_src; --i) f_sqr(FRP, root_S, root_S);
+    fe_copy(gn, FR_GENERATOR);
+    for (size_t i = 0; i < log2_src; ++i) f_sqr(FRP, gn, gn);
+    for (size_t j = 0; j < S; ++j)
+    {
+        f_sub(FRP, gn, FRP->one, numer[j]);
+        f_mul(FRP, numer[j], src->domain_inverse, numer[j]);
+        f_mul(FRP, gn, root_S, gn);
+    }
+    fe_copy(x, FR_GENERATOR);
+    for (size_t i = 0; i < T; ++i)
+    {
+        f_sub(FRP, x, FRP->one, den);
+        f_invert(FRP, den, inv);
+        f_mul(FRP, inv, numer[i & (S - 1)], l_1 + 4 * i);
+        f_mul(FRP, x, tgt->root, x);
+    }
+    orc_domain_free(src);
+    orc_domain_free(tgt);
+}

@@ -80,6 +80,8 @@ void orc_domain_constant(const orc_domain* d, int which, uint64_t r[4]); /* 0 ro
 /* op: 0 fft, 1 ifft, 2 coset_fft, 3 coset_ifft, 4 fft_with_constant, 5 ifft_with_constant, 6 coset_fft_with_constant
  * (polynomial_arithmetic.cpp:266-315); coeffs in place, length d->size */
 void orc_ntt(const orc_domain* d, int op, uint64_t* coeffs, const uint64_t* constant);
+/* polynomial_arithmetic.cpp:381-476 (value-equivalent: one inversion per element instead of the batched sweep) */
+void orc_compute_lagrange_polynomial_fft(uint64_t* l_1, size_t log2_src, size_t log2_target);
 void orc_poly_evaluate(const uint64_t* coeffs, const uint64_t z[4], size_t n, uint64_t out[4]); /* :337-373, Horner-equivalent */
 
 #ifdef __cplusplus

@@ -284,6 +284,13 @@ void ref_poly_evaluate(const uint64_t* coeffs, const uint64_t* z, size_t n, uint
     free(c);
 }
 
+// polynomial_arithmetic.cpp:381-476; l_1 must hold target_n elements (caller-aligned)
+void ref_compute_lagrange_polynomial_fft(uint64_t* l_1, size_t src_n, size_t target_n)
+{
+    evaluation_domain s(src_n), t(target_n);
+    polynomial_arithmetic::compute_lagrange_polynomial_fft((fr::field_t*)l_1, s, t);
+}
+
 void* ref_aligned_alloc(size_t bytes) { return aligned_alloc(64, (bytes + 63) & ~(size_t)63); }
 void ref_aligned_free(void* p) { free(p); }
 

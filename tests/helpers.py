@@ -65,6 +65,7 @@ def oracle():
         lib.orc_g1_batch_normalize.argtypes = [u64p, C.c_size_t]
         lib.orc_poly_evaluate.argtypes = [u64p, u64p, C.c_size_t, u64p]
         lib.orc_g1_arith_progression.argtypes = [u64p, u64p, u64p, C.c_size_t]
+        lib.orc_compute_lagrange_polynomial_fft.argtypes = [u64p, C.c_size_t, C.c_size_t]
         _oracle = lib
     return _oracle
 
@@ -98,6 +99,7 @@ def ref():
         lib.ref_g1_batch_normalize.argtypes = [u64p, C.c_size_t]
         lib.ref_poly_evaluate.argtypes = [u64p, u64p, C.c_size_t, u64p]
         lib.ref_r_inv.restype = C.c_uint64
+        lib.ref_compute_lagrange_polynomial_fft.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
         lib.ref_aligned_alloc.restype = C.c_void_p
         lib.ref_aligned_alloc.argtypes = [C.c_size_t]
         lib.ref_aligned_free.argtypes = [C.c_void_p]

@@ -176,3 +176,12 @@ def test_device_point_generator(emu):
     assert (tab == exp).all()
     emu.dev_free(dp)
     emu.dev_free(dt)
+
+
+@pytest.mark.parametrize("log_src,log_tgt", [(2, 3), (3, 5), (6, 7), (10, 11), (10, 12)])
+def test_compute_lagrange_polynomial_fft(emu, log_src, log_tgt):
+    """polynomial_arithmetic.cpp:381-476 on the device vs the oracle restatement (canonical limbs)."""
+    got = emu.compute_lagrange_polynomial_fft(log_src, log_tgt)
+    exp = np.zeros_like(got)
+    H.oracle().orc_compute_lagrange_polynomial_fft(H.ptr(exp), log_src, log_tgt)
+    assert (got == exp).all()

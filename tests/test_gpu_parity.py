@@ -291,3 +291,23 @@ def test_profile_counters(lib):
     prof = lib.profile_read()
     lib.profile_enable(False)
     assert prof["ntt_pass_a"][1] == 1 and prof["ntt_pass_b"][1] == 1
+
+
+@pytest.mark.parametrize("log_src,log_tgt", [(2, 3), (6, 7), (10, 11), (12, 14), (20, 21)])
+def test_compute_lagrange_polynomial_fft(lib, log_src, log_tgt):
+    """§8f widening: compute_lagrange_polynomial_fft (polynomial_arithmetic.cpp:381-476) vs the oracle (small sizes)
+    and the compiled reference (prover size 2^20 -> 2^21)."""
+    got = lib.compute_lagrange_polynomial_fft(log_src, log_tgt)
+    t = 1 << log_tgt
+    if log_tgt <= 14:
+        exp = np.zeros_like(got)
+        H.oracle().orc_compute_lagrange_polynomial_fft(ptr(exp), log_src, log_tgt)
+        assert (got == exp).all()
+    if H.have_ref():
+        r = H.ref()
+        ref_threads_pow2()
+        p = r.ref_aligned_alloc(32 * t)
+        exp = np.ctypeslib.as_array((H.C.c_uint64 * (4 * t)).from_address(p)).reshape(t, 4)
+        r.ref_compute_lagrange_polynomial_fft(p, 1 << log_src, t)
+        assert (got == exp).all()
+        r.ref_aligned_free(p)

@@ -373,3 +373,17 @@ def test_ntt_roundtrips():
         x = H.random_scalars_mont(n, n)
         assert (od.ntt(1, od.ntt(0, x)) == x).all()
         assert (od.ntt(3, od.ntt(2, x)) == x).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("log_src,log_tgt", [(2, 3), (4, 5), (8, 9), (8, 10)])
+def test_lagrange_fft_matches_reference(log_src, log_tgt):
+    o, r = H.oracle(), H.ref()
+    t = 1 << log_tgt
+    exp_ptr = r.ref_aligned_alloc(32 * t)
+    exp = np.ctypeslib.as_array((H.C.c_uint64 * (4 * t)).from_address(exp_ptr)).reshape(t, 4)
+    r.ref_compute_lagrange_polynomial_fft(exp_ptr, 1 << log_src, t)
+    got = np.zeros((t, 4), dtype=np.uint64)
+    o.orc_compute_lagrange_polynomial_fft(ptr(got), log_src, log_tgt)
+    assert (got == exp).all()
+    r.ref_aligned_free(exp_ptr)
