@@ -351,6 +351,18 @@ template <typename FP> struct Field
         for (int i = 0; i < 8; ++i) r.v[i] = borrow ? t.v[i] : d.v[i];
         return r;
     }
+    // a - b + 2p without the conditional correction: result in (0, 4p) for a, b in [0, 2p).  Only valid as the
+    // multiplicand of a product whose other factor is canonical (< p): then (4p * p) / 2^256 + p < 2p still holds.
+    static BBG_HD fe sub_lazy(const fe& a, const fe& b)
+    {
+        fe t, r;
+        uint32_t p2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p2[i] = FP::P2(i);
+        cc::add8(t.v, a.v, p2);
+        cc::sub8(r.v, t.v, b.v);
+        return r;
+    }
     static BBG_HD fe dbl(const fe& a) { return add(a, a); }
     // -a in [0,2p): 2p - a  (a in [0,2p]);  maps 0 -> 2p?  no: 0 stays 0
     static BBG_HD fe neg(const fe& a)

@@ -108,15 +108,15 @@ template <int L, int B, int R> BBG_D void radix_step(fe (&x)[8], int base_low, c
             const fe u = x[m];
             const fe v = x[m | half];
             x[m] = Fr::add(u, v);
-            const fe d = Fr::sub(u, v);
             if (B == 0 && jm == 0)
             {
-                x[m | half] = d; // twiddle w^0
+                x[m | half] = Fr::sub(u, v); // twiddle w^0
             }
             else
             {
+                // the sub-transform twiddles are canonical (< p), so the difference may stay in (0, 4p)
                 const int e = (base_low | (jm << B)) << (L - 1 - s);
-                x[m | half] = NTT_MUL(d, tw_load(tw, e));
+                x[m | half] = NTT_MUL(Fr::sub_lazy(u, v), tw_load(tw, e));
             }
         }
     }
@@ -270,8 +270,7 @@ __global__ void __launch_bounds__(NT) ntt_small_kernel(SmallParams p)
             const int q0 = ((i >> s) << (s + 1)) | j;
             const fe u = sm_load(data, q0), v = sm_load(data, q0 | h);
             sm_store(data, q0, Fr::add(u, v));
-            fe d = Fr::sub(u, v);
-            if (j != 0) d = Fr::mul(d, tw_load(tw, j << (L - 1 - s)));
+            const fe d = j != 0 ? Fr::mul(Fr::sub_lazy(u, v), tw_load(tw, j << (L - 1 - s))) : Fr::sub(u, v);
             sm_store(data, q0 | h, d);
         }
     }
@@ -301,7 +300,7 @@ __global__ void gen_subtw_image_kernel(uint32_t* img, fe root, unsigned half)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= half) return;
-    const fe w = Fr::pow_u64(root, e);
+    const fe w = Fr::reduce(Fr::pow_u64(root, e)); // canonical: the butterflies rely on w < p (Fr::sub_lazy)
     const int p = pad((int)e);
 #pragma unroll
     for (int l = 0; l < 8; ++l) img[l * TWP + p] = w.v[l];
