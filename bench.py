@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -103,6 +103,7 @@ def workload_config(args, world):
         "ntt_batch": BATCH,
         "ntt_sizes": [1 << args.log_n, 1 << args.log_n, 1 << (args.log_n + 2)],
         "sharding": "msm by point range, ntt batch by polynomial (no data-path collective; %d-rank gather of 128-byte partials)" % world,
+        "untimed_steps": "warm-up W + 10 more while the clock sampler spins up",
         "l2": "inputs larger than L2 (polynomial batch %d MiB, point table %d MiB), no flush" % (
             BATCH * 32 * (1 << args.log_n) * 5 // (1 << 20) // 1, 128 * (1 << args.log_n) // (1 << 20)),
     }
@@ -346,12 +347,14 @@ def run_b200(args, rank, local_rank, world):
         lib.h2d(d_poly_4n, h_poly_4n)
 
     # ---- device-resident timing ----------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    # the clock sampler runs from the warm-up through the timed region (a 5-step region lasts only ~75 ms, fewer than
+    # two nvidia-smi periods): every sample is taken under this workload's load
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3) + 10):
+        step_device()
+    barrier()
     launches0 = lib.launch_count()
     lib.timer_start()
     t0 = time.perf_counter()
