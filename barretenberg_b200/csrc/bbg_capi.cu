@@ -5,6 +5,7 @@
 #include "bbg_internal.h"
 #include "bbg_host_g1.h"
 #include "bbg_hostcopy.h"
+#include "bbg_plonk.h"
 
 #include <mutex>
 #include <vector>
@@ -267,7 +268,10 @@ const char* bbg_error_string(int code)
     return "bbgpu: unknown error";
 }
 
-uint64_t bbg_launch_count(void) { return (uint64_t)ntt_launch_count() + (uint64_t)msm_launch_count() + g_misc_launches; }
+uint64_t bbg_launch_count(void)
+{
+    return (uint64_t)ntt_launch_count() + (uint64_t)msm_launch_count() + (uint64_t)plonk::launch_count() + g_misc_launches;
+}
 
 // ---- NTT ----------------------------------------------------------------------------------------
 int bbg_ntt_fr_dev(void* d_coeffs, size_t stride_elems, size_t batch, unsigned log2_n, int op, const uint64_t* constant)
@@ -476,6 +480,103 @@ int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table
     bbg_rt::dev_free(d_pts);
     if (d_tab) bbg_rt::dev_free(d_tab);
     return e;
+}
+
+// ---- HBM-resident PLONK prover rounds (bbg_plonk.cu) -------------------------------------------------
+int bbg_plonk_create(unsigned log2_n, bbg_plonk_prover** out)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (out == nullptr) return BBG_E_BAD_ARGUMENT;
+    plonk::Prover* p = nullptr;
+    BBG_CHECK(plonk::create(log2_n, &p));
+    *out = (bbg_plonk_prover*)p;
+    return 0;
+}
+int bbg_plonk_destroy(bbg_plonk_prover* p)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (p == nullptr) return 0;
+    bbg_rt::sync(g_stream);
+    plonk::destroy((plonk::Prover*)p);
+    return 0;
+}
+int bbg_plonk_set_witness(bbg_plonk_prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::set_witness((plonk::Prover*)p, w_l, w_r, w_o, g_stream);
+}
+int bbg_plonk_set_permutation(bbg_plonk_prover* p, const uint32_t* sigma_1_mapping, const uint32_t* sigma_2_mapping, const uint32_t* sigma_3_mapping)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::set_permutation((plonk::Prover*)p, sigma_1_mapping, sigma_2_mapping, sigma_3_mapping, g_stream);
+}
+int bbg_plonk_set_arithmetic_selectors(bbg_plonk_prover* p, const uint64_t* q_m, const uint64_t* q_l, const uint64_t* q_r, const uint64_t* q_o,
+                                       const uint64_t* q_c)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr) return BBG_E_BAD_ARGUMENT;
+    const uint64_t* q[5] = { q_m, q_l, q_r, q_o, q_c };
+    return plonk::set_arithmetic_selectors((plonk::Prover*)p, q, g_stream);
+}
+int bbg_plonk_set_srs(bbg_plonk_prover* p, const uint64_t* points_table, size_t n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || points_table == nullptr) return BBG_E_BAD_ARGUMENT;
+    const void* d_table = nullptr;
+    BBG_CHECK(resolve_table(points_table, n, &d_table));
+    return plonk::set_srs((plonk::Prover*)p, d_table);
+}
+int bbg_plonk_round_wires(bbg_plonk_prover* p, uint64_t* out_xyz)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || out_xyz == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::round_wires((plonk::Prover*)p, out_xyz, g_stream);
+}
+int bbg_plonk_round_grand_product(bbg_plonk_prover* p, const uint64_t beta[4], const uint64_t gamma[4], uint64_t out_xyz[12])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || beta == nullptr || gamma == nullptr || out_xyz == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::round_grand_product((plonk::Prover*)p, beta, gamma, out_xyz, g_stream);
+}
+int bbg_plonk_round_quotient(bbg_plonk_prover* p, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4], const uint64_t alpha_base[4],
+                             uint64_t* out_xyz)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || beta == nullptr || gamma == nullptr || alpha == nullptr || alpha_base == nullptr || out_xyz == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::round_quotient((plonk::Prover*)p, beta, gamma, alpha, alpha_base, out_xyz, g_stream);
+}
+int bbg_plonk_round_evaluations(bbg_plonk_prover* p, const uint64_t zeta[4], const uint64_t zeta_omega[4], uint64_t* out_evals)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || zeta == nullptr || zeta_omega == nullptr || out_evals == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::round_evaluations((plonk::Prover*)p, zeta, zeta_omega, out_evals, g_stream);
+}
+int bbg_plonk_round_linearise(bbg_plonk_prover* p, const uint64_t* scalars, const uint64_t zeta[4], uint64_t out_linear_eval[4])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || scalars == nullptr || zeta == nullptr || out_linear_eval == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::round_linearise((plonk::Prover*)p, scalars, zeta, out_linear_eval, g_stream);
+}
+int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, const uint64_t beta_inv[4], const uint64_t zeta[4],
+                             const uint64_t zeta_omega[4], uint64_t* out_xyz)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (p == nullptr || nu_powers == nullptr || beta_inv == nullptr || zeta == nullptr || zeta_omega == nullptr || out_xyz == nullptr)
+        return BBG_E_BAD_ARGUMENT;
+    return plonk::round_openings((plonk::Prover*)p, nu_powers, beta_inv, zeta, zeta_omega, out_xyz, g_stream);
 }
 
 // ---- device memory helpers ------------------------------------------------------------------------

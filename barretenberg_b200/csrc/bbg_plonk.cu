@@ -1,0 +1,861 @@
+// HBM-resident standard-PLONK prover rounds for sm_100a (device-resident polynomials,
+// the prover's element-wise loops, and its two serial recurrences as parallel scans).
+//
+// Replaces the data-parallel body of waffle::Prover::construct_proof for circuits built from the arithmetic widget
+//   waffle/proof_system/prover/prover.cpp:65-690, widgets/arithmetic_widget.cpp:60-122, permutation.hpp:13-88,
+//   polynomials/polynomial_arithmetic.cpp:337-373 (evaluate), :478-560 (divide_by_pseudo_vanishing_polynomial),
+//   :562-591 (compute_kate_opening_coefficients), fields/field.hpp:503-522 (batch_invert)
+// The Fiat-Shamir transcript (keccak, challenge.hpp) and the handful of scalar formulas (linearizer.hpp,
+// get_lagrange_evaluations) stay in the host shim (barretenberg_b200/shim/prover_gpu.cpp), which runs the reference's
+// own header code for them; everything that touches n field elements happens here, between rounds nothing but
+// commitments (12 limbs each) and evaluations cross PCIe.
+//
+// Value contract: the proof is a deterministic function of (witness, circuit, SRS); every quantity below is the same
+// field element / group element the reference computes, so the proof is identical limb for limb
+// (tests/test_gpu_prover_dropin.py, tests/test_emul_prover.py).  Intermediate polynomials live in [0, 2p) ("coarse");
+// everything that leaves the device is canonical.
+//
+// Layout in HBM for a circuit of n = 2^k gates (field element = 32 B; n = 2^20 -> 2.3 GB in total):
+//   w_lag[3][n]  witness, Lagrange form          w_coef[3][n]   coefficient form       w4[3][4n]  coset evaluations
+//   sigma[3][n]  permutation polys (Lagrange -> beta-scaled coefficients in place)     s4[3][4n]
+//   z[n], z4[4n] grand product                   q[5][n], q2[5][2n]  selectors         l1[2n]
+//   quot_large[4n], quot_mid[2n], r[n], tmp[2][n] (scan inputs / opening polynomials)
+#include "bbg_internal.h"
+#include "bbg_host_g1.h"
+#include "bbg_hostcopy.h"
+#include "bbg_plonk.h"
+
+#include <vector>
+
+namespace bbg
+{
+namespace plonkk
+{
+// fr.hpp:66-69 multiplicative_generator (5) and :76-79 alternate_multiplicative_generator, Montgomery form
+BBG_HD fe gen_k1()
+{
+    return fe{ { 0x9FFFFFE6u, 0x1B0D0EF9u, 0xA32A913Fu, 0xEABA68A3u, 0xD8DD0689u, 0x47D8EB76u, 0x20F5BBC3u, 0x15D00855u } };
+}
+BBG_HD fe gen_k2()
+{
+    return fe{ { 0x4FFFFFDBu, 0x3057819Eu, 0x6832BB01u, 0x307F6D86u, 0x484E3A89u, 0x5C65EC9Fu, 0x73D3D9F8u, 0x0180A965u } };
+}
+
+// w^e for e < domain size as lo[e & mask] * hi[e >> lo_log] (hi == nullptr for domains that fit the low table)
+struct PowTable
+{
+    const fe* lo;
+    const fe* hi;
+    int lo_log;
+};
+BBG_D fe root_pow(const PowTable& t, uint32_t e)
+{
+    fe a = load_fe(t.lo + (e & ((1u << t.lo_log) - 1)));
+    if (t.hi != nullptr) a = Fr::mul(a, load_fe(t.hi + (e >> t.lo_log)));
+    return a;
+}
+
+// out[i] = base^i, canonical
+__global__ void powers_kernel(fe* out, fe base, unsigned count)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    store_fe(out + i, Fr::reduce(Fr::pow_u64(base, i)));
+}
+
+// permutation.hpp:13-88: sigma_k[i] = K_col * w_n^idx for mapping entry (col << 30 | idx).  (The reference looks w^idx up
+// as +-roots[idx mod n/2]; w^(n/2) = -1 makes that the plain power.)
+__global__ void sigma_from_mapping_kernel(fe* out, const uint32_t* map, PowTable small, unsigned n, unsigned total)
+{
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    {
+        const uint32_t m = map[idx];
+        const uint32_t raw = (m & ((1u << 29) - 1u)) & (n - 1);
+        fe v = root_pow(small, raw);
+        switch ((m >> 30) & 3u)
+        {
+        case 2u: v = Fr::mul(v, gen_k2()); break;
+        case 1u: v = Fr::mul(v, gen_k1()); break;
+        default: break;
+        }
+        store_fe(out + idx, v);
+    }
+}
+
+// prover.cpp:146-186: the six accumulator inputs of the grand product, already multiplied three by three:
+//   num[i] = (w_l + beta w^i + gamma)(w_r + beta k1 w^i + gamma)(w_o + beta k2 w^i + gamma)
+//   den[i] = (w_l + beta sigma_1 + gamma)(w_r + beta sigma_2 + gamma)(w_o + beta sigma_3 + gamma)
+__global__ void z_terms_kernel(fe* num, fe* den, const fe* w_lag, const fe* sigma, PowTable small, fe beta, fe gamma, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const fe wl = Fr::add(load_fe(w_lag + i), gamma);
+        const fe wr = Fr::add(load_fe(w_lag + n + i), gamma);
+        const fe wo = Fr::add(load_fe(w_lag + 2 * (size_t)n + i), gamma);
+        const fe rb = Fr::mul(root_pow(small, i), beta);
+        fe t = Fr::add(wl, rb);
+        t = Fr::mul(t, Fr::add(wr, Fr::mul(rb, gen_k1())));
+        t = Fr::mul(t, Fr::add(wo, Fr::mul(rb, gen_k2())));
+        store_fe(num + i, t);
+        fe d = Fr::add(wl, Fr::mul(load_fe(sigma + i), beta));
+        d = Fr::mul(d, Fr::add(wr, Fr::mul(load_fe(sigma + n + i), beta)));
+        d = Fr::mul(d, Fr::add(wo, Fr::mul(load_fe(sigma + 2 * (size_t)n + i), beta)));
+        store_fe(den + i, d);
+    }
+}
+
+// ---- exclusive prefix product (prover.cpp:188-201 "6 non-parallelizable processes") ------------------------------
+// level 0: every thread owns `run` consecutive elements; level 1: one CTA scans the per-run products.
+constexpr int SCAN_THREADS = 1024;
+__global__ void prod_reduce_kernel(const fe* in, fe* aggs, unsigned n, unsigned run, size_t in_stride, unsigned aggs_stride)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first = k * run;
+    if (first >= n) return;
+    const fe* src = in + blockIdx.y * in_stride;
+    const unsigned count = n - first < run ? n - first : run;
+    fe acc = load_fe(src + first);
+    for (unsigned j = 1; j < count; ++j) acc = Fr::mul(acc, load_fe(src + first + j));
+    store_fe(aggs + (size_t)blockIdx.y * aggs_stride + k, acc);
+}
+// in place: aggs[k] <- prod_{m<k} aggs[m]
+__global__ void __launch_bounds__(SCAN_THREADS) prod_spine_kernel(fe* aggs_all, unsigned count, unsigned aggs_stride)
+{
+    __shared__ fe sh[SCAN_THREADS];
+    fe* aggs = aggs_all + (size_t)blockIdx.x * aggs_stride;
+    const unsigned t = threadIdx.x, T = blockDim.x;
+    const unsigned per = (count + T - 1) / T;
+    const unsigned lo = t * per, hi = (lo + per < count) ? lo + per : count;
+    fe a = Fr::one();
+    for (unsigned k = lo; k < hi; ++k) a = Fr::mul(a, load_fe(aggs + k));
+    sh[t] = a;
+    __syncthreads();
+    for (unsigned d = 1; d < T; d <<= 1)
+    {
+        fe v = sh[t];
+        if (t >= d) v = Fr::mul(v, sh[t - d]);
+        __syncthreads();
+        sh[t] = v;
+        __syncthreads();
+    }
+    fe carry = t == 0 ? Fr::one() : sh[t - 1];
+    for (unsigned k = lo; k < hi; ++k)
+    {
+        const fe c = load_fe(aggs + k);
+        store_fe(aggs + k, carry);
+        carry = Fr::mul(carry, c);
+    }
+}
+// prover.cpp:203-222 fused with the final scan level: z[i] = P_num[i] / P_den[i], P[i] = prod_{k<i} (exclusive).  The
+// reference inverts all n denominators with one serial Montgomery-trick sweep (field.hpp:503-522); here every thread
+// inverts its own run (one Fermat inversion per run).
+constexpr int ZRUN = 32;
+__global__ void __launch_bounds__(64) z_finish_kernel(fe* z, const fe* num, const fe* den, const fe* num_carry, const fe* den_carry, unsigned n)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first = k * ZRUN;
+    if (first >= n) return;
+    const int count = (int)(n - first < (unsigned)ZRUN ? n - first : ZRUN);
+    fe pd[ZRUN], prefix[ZRUN];
+    fe acc = Fr::one();
+    fe dcarry = load_fe(den_carry + k);
+    for (int i = 0; i < count; ++i)
+    {
+        pd[i] = dcarry; // exclusive prefix product of the denominators at first + i
+        prefix[i] = acc;
+        acc = Fr::mul(acc, dcarry);
+        dcarry = Fr::mul(dcarry, load_fe(den + first + i));
+    }
+    fe inv = Fr::invert(acc);
+    // numerators: exclusive prefix products at first + i, needed from the top down
+    fe pn[ZRUN];
+    fe ncarry = load_fe(num_carry + k);
+    for (int i = 0; i < count; ++i)
+    {
+        pn[i] = ncarry;
+        ncarry = Fr::mul(ncarry, load_fe(num + first + i));
+    }
+    for (int i = count - 1; i >= 0; --i)
+    {
+        const fe d_inv = Fr::mul(inv, prefix[i]);
+        inv = Fr::mul(inv, pd[i]);
+        store_fe(z + first + i, Fr::mul(pn[i], d_inv));
+    }
+}
+
+// dst[b][i] = i < n_src ? src[b][i] : 0
+__global__ void pad_copy_kernel(fe* dst, const fe* src, unsigned n_src, unsigned n_dst, size_t src_stride, size_t dst_stride)
+{
+    const fe* s = src + blockIdx.y * src_stride;
+    fe* d = dst + blockIdx.y * dst_stride;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += gridDim.x * blockDim.x)
+        store_fe(d + i, i < n_src ? load_fe(s + i) : Fr::zero());
+}
+// prover.cpp:246-262: s4[b] = beta sigma_b(X) + w_b(X) + gamma in coefficient form, zero padded to 4n
+__global__ void sigma_combine_pad_kernel(fe* s4, const fe* sigma_coef, const fe* w_coef, fe gamma, unsigned n, unsigned n4)
+{
+    const fe* s = sigma_coef + (size_t)blockIdx.y * n;
+    const fe* w = w_coef + (size_t)blockIdx.y * n;
+    fe* d = s4 + (size_t)blockIdx.y * n4;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    {
+        fe v = Fr::zero();
+        if (i < n)
+        {
+            v = Fr::add(load_fe(s + i), load_fe(w + i));
+            if (i == 0) v = Fr::add(v, gamma);
+        }
+        store_fe(d + i, v);
+    }
+}
+
+struct QuotientConsts
+{
+    fe g;          // coset generator
+    fe g_beta;     // g * beta
+    fe beta, gamma, alpha, alpha_sqr;
+    fe neg_root_inv; // -w_n^-1 = -w_n^(n-1)  (divide_by_pseudo_vanishing_polynomial "numerator_constant")
+    fe vinv[4];      // 1 / ((g w_S^j)^n - 1), j < S = 2 (mid domain) or 4 (large domain)
+};
+
+// prover.cpp:279-285 (permutation term), :296-323 (identity term), polynomial_arithmetic.cpp:478-560 (the division by
+// Z_H*(X) on the large domain), one pass:
+//   q[i] = ( (w_l + b x + c)(w_r + b k1 x + c)(w_o + b k2 x + c) aZ(x)  -  s1 s2 s3 aZ(x w) ) (x - w^(n-1)) / (x^n - 1),
+//   x = g w_4n^i
+__global__ void quotient_large_kernel(fe* q, const fe* s4, const fe* w4, const fe* z4, PowTable large, QuotientConsts c, unsigned n4)
+{
+    const unsigned mask = n4 - 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    {
+        const fe root = root_pow(large, i);
+        const fe bx = Fr::mul(root, c.g_beta);
+        fe id = Fr::add(Fr::add(load_fe(w4 + i), c.gamma), bx);
+        id = Fr::mul(id, Fr::add(Fr::add(load_fe(w4 + (size_t)n4 + i), c.gamma), Fr::mul(bx, gen_k1())));
+        id = Fr::mul(id, Fr::add(Fr::add(load_fe(w4 + 2 * (size_t)n4 + i), c.gamma), Fr::mul(bx, gen_k2())));
+        id = Fr::mul(id, load_fe(z4 + i));
+        fe pm = Fr::mul(load_fe(s4 + i), load_fe(s4 + (size_t)n4 + i));
+        pm = Fr::mul(pm, load_fe(s4 + 2 * (size_t)n4 + i));
+        pm = Fr::mul(pm, load_fe(z4 + ((i + 4) & mask)));
+        fe v = Fr::mul(Fr::sub(id, pm), c.vinv[i & 3]);
+        v = Fr::mul(v, Fr::add(Fr::mul(root, c.g), c.neg_root_inv));
+        store_fe(q + i, v);
+    }
+}
+
+// prover.cpp:325-391 (the two L_1 boundary terms), arithmetic_widget.cpp:60-97 (gate identity) and the division by
+// Z_H*(X) on the mid domain, one pass over i < 2n (aZ = alpha Z: z4 was transformed with the constant alpha):
+//   q[i] = ( (aZ(x w) - a) a L1[i+4] + (aZ(x) - a) a^2 L1[i] + qm wl wr + ql wl + qr wr + qo wo + qc ) (x - w^(n-1)) / (x^n - 1)
+__global__ void quotient_mid_kernel(fe* q, const fe* z4, const fe* l1, const fe* w4, const fe* q2, PowTable mid, QuotientConsts c, unsigned n2)
+{
+    const unsigned n4 = 2 * n2, mask2 = n2 - 1, mask4 = n4 - 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+    {
+        fe t6 = Fr::sub(load_fe(z4 + ((2 * i + 4) & mask4)), c.alpha);
+        t6 = Fr::mul(Fr::mul(t6, c.alpha), load_fe(l1 + ((i + 4) & mask2)));
+        fe t4 = Fr::sub(load_fe(z4 + 2 * i), c.alpha);
+        t4 = Fr::mul(Fr::mul(t4, c.alpha_sqr), load_fe(l1 + i));
+        const fe wl = load_fe(w4 + 2 * i), wr = load_fe(w4 + (size_t)n4 + 2 * i), wo = load_fe(w4 + 2 * (size_t)n4 + 2 * i);
+        fe a = Fr::mul(Fr::mul(wl, load_fe(q2 + i)), wr);
+        a = Fr::add(a, Fr::mul(wl, load_fe(q2 + (size_t)n2 + i)));
+        fe b = Fr::mul(wr, load_fe(q2 + 2 * (size_t)n2 + i));
+        b = Fr::add(b, Fr::mul(wo, load_fe(q2 + 3 * (size_t)n2 + i)));
+        a = Fr::add(Fr::add(a, b), load_fe(q2 + 4 * (size_t)n2 + i));
+        fe v = Fr::add(Fr::add(t4, t6), a);
+        v = Fr::mul(v, c.vinv[i & 1]);
+        const fe x = Fr::mul(root_pow(mid, i), c.g);
+        v = Fr::mul(v, Fr::add(x, c.neg_root_inv));
+        store_fe(q + i, v);
+    }
+}
+
+// a[i] += b[i]
+__global__ void add_into_kernel(fe* a, const fe* b, unsigned count)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        store_fe(a + i, Fr::add(load_fe(a + i), load_fe(b + i)));
+}
+
+// ---- polynomial evaluation (polynomial_arithmetic.cpp:337-373), batched over (polynomial, point) jobs -------------
+constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_RUN = 16;
+constexpr int EVAL_SPAN = EVAL_THREADS * EVAL_RUN;
+constexpr int MAX_EVAL_JOBS = 8;
+struct EvalJobs
+{
+    const fe* poly[MAX_EVAL_JOBS];
+    unsigned len[MAX_EVAL_JOBS];
+    fe point[MAX_EVAL_JOBS];
+};
+// sum over the CTA of val_t * mult^t  (mult = per-thread step); result valid in thread 0
+BBG_D fe block_horner_reduce(fe val, fe mult, fe* sh)
+{
+    const unsigned t = threadIdx.x, T = blockDim.x;
+    for (unsigned d = 1; d < T; d <<= 1)
+    {
+        sh[t] = val;
+        __syncthreads();
+        if ((t & (2 * d - 1)) == 0 && t + d < T) val = Fr::add(val, Fr::mul(sh[t + d], mult));
+        __syncthreads();
+        mult = Fr::sqr(mult);
+    }
+    return val;
+}
+// partial[job][block] = sum_{j in block span} f_j z^(j - span start)
+__global__ void __launch_bounds__(EVAL_THREADS) eval_partial_kernel(EvalJobs jobs, fe* partial, unsigned partial_stride)
+{
+    __shared__ fe sh[EVAL_THREADS];
+    const int job = blockIdx.y;
+    const unsigned len = jobs.len[job];
+    if ((size_t)blockIdx.x * EVAL_SPAN >= len) return;
+    const fe* f = jobs.poly[job];
+    const fe z = jobs.point[job];
+    const unsigned first = blockIdx.x * EVAL_SPAN + threadIdx.x * EVAL_RUN;
+    fe acc = Fr::zero();
+    for (int j = EVAL_RUN - 1; j >= 0; --j)
+    {
+        acc = Fr::mul(acc, z);
+        if (first + j < len) acc = Fr::add(acc, load_fe(f + first + j));
+    }
+    const fe r = block_horner_reduce(acc, Fr::pow_u64(z, EVAL_RUN), sh);
+    if (threadIdx.x == 0) store_fe(partial + (size_t)job * partial_stride + blockIdx.x, r);
+}
+// out[job] = sum_b partial[job][b] (z^SPAN)^b, canonical
+__global__ void __launch_bounds__(SCAN_THREADS) eval_final_kernel(EvalJobs jobs, const fe* partial, unsigned partial_stride, fe* out)
+{
+    __shared__ fe sh[SCAN_THREADS];
+    const int job = blockIdx.x;
+    const unsigned len = jobs.len[job];
+    const unsigned nb = (len + EVAL_SPAN - 1) / EVAL_SPAN;
+    const unsigned t = threadIdx.x, T = blockDim.x;
+    const unsigned per = (nb + T - 1) / T;
+    const fe step = Fr::pow_u64(jobs.point[job], EVAL_SPAN);
+    const fe* p = partial + (size_t)job * partial_stride;
+    fe acc = Fr::zero();
+    for (int j = (int)per - 1; j >= 0; --j)
+    {
+        acc = Fr::mul(acc, step);
+        const unsigned b = t * per + (unsigned)j;
+        if (b < nb) acc = Fr::add(acc, load_fe(p + b));
+    }
+    const fe r = block_horner_reduce(acc, Fr::pow_u64(step, per), sh);
+    if (t == 0) store_fe(out + job, Fr::reduce(r));
+}
+
+// prover.cpp:479-493 + arithmetic_widget.cpp:99-122: r[i] = c_z z[i] + c_s3 sigma_3[i] + (wlr qm + wl ql + wr qr + wo qo + qc) a
+struct LinearConsts
+{
+    fe c_z, c_sigma3; // linear_terms.z_1 ; linear_terms.sigma_3 * beta^-1
+    fe w_lr, w_l, w_r, w_o, alpha_base;
+};
+__global__ void linearise_kernel(fe* r, const fe* z, const fe* sigma3, const fe* q, LinearConsts c, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        fe v = Fr::add(Fr::mul(load_fe(z + i), c.c_z), Fr::mul(load_fe(sigma3 + i), c.c_sigma3));
+        fe a = Fr::add(Fr::mul(load_fe(q + i), c.w_lr), Fr::mul(load_fe(q + (size_t)n + i), c.w_l));
+        fe b = Fr::add(Fr::mul(load_fe(q + 2 * (size_t)n + i), c.w_r), Fr::mul(load_fe(q + 3 * (size_t)n + i), c.w_o));
+        a = Fr::add(Fr::add(a, b), load_fe(q + 4 * (size_t)n + i));
+        store_fe(r + i, Fr::add(v, Fr::mul(a, c.alpha_base)));
+    }
+}
+
+// prover.cpp:552-590: the two batched opening polynomials before the division
+struct OpeningConsts
+{
+    fe nu[7];           // nu^1 .. nu^7
+    fe beta_inv;
+    fe z_pow_n, z_pow_2n;
+};
+__global__ void opening_combine_kernel(fe* opening, fe* shifted, const fe* quot, const fe* r, const fe* w_coef, const fe* sigma, const fe* z,
+                                       OpeningConsts c, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        fe t8 = Fr::add(Fr::mul(load_fe(quot + (size_t)n + i), c.z_pow_n), Fr::mul(load_fe(quot + 2 * (size_t)n + i), c.z_pow_2n));
+        fe t1 = Fr::add(Fr::mul(load_fe(r + i), c.nu[0]), Fr::mul(load_fe(w_coef + i), c.nu[1]));
+        fe t3 = Fr::add(Fr::mul(load_fe(w_coef + (size_t)n + i), c.nu[2]), Fr::mul(load_fe(w_coef + 2 * (size_t)n + i), c.nu[3]));
+        fe t4 = Fr::add(Fr::mul(load_fe(sigma + i), c.nu[4]), Fr::mul(load_fe(sigma + (size_t)n + i), c.nu[5]));
+        t4 = Fr::mul(t4, c.beta_inv);
+        fe v = Fr::add(Fr::add(t3, t1), Fr::add(t4, t8));
+        store_fe(opening + i, Fr::add(v, load_fe(quot + i)));
+        store_fe(shifted + i, Fr::mul(load_fe(z + i), c.nu[6]));
+    }
+}
+
+// ---- (F(X) - F(z)) / (X - z) (polynomial_arithmetic.cpp:562-591) --------------------------------------------------
+// The reference walks the recurrence w_i = (f_i - w_{i-1}) / (-z) upwards, serially.  The same quotient read from
+// the top is w_{i-1} = f_i + z w_i (w_{n-1} = 0): a suffix scan with the affine maps x -> f_i + z x.
+// blockIdx.y selects the polynomial (stride n) and its point.
+struct KatePoints
+{
+    fe z[2];
+    fe z_run[2];  // z^run
+    fe z_span[2]; // (z^run)^per  (per = aggregates per spine thread)
+};
+__global__ void kate_reduce_kernel(const fe* in, fe* aggs, KatePoints pts, unsigned n, unsigned run, unsigned aggs_stride)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first = k * run;
+    if (first >= n) return;
+    const fe* f = in + (size_t)blockIdx.y * n;
+    const fe z = pts.z[blockIdx.y];
+    fe acc = Fr::zero();
+    for (int j = (int)run - 1; j >= 0; --j)
+    {
+        acc = Fr::mul(acc, z);
+        if (first + j < n) acc = Fr::add(acc, load_fe(f + first + j));
+    }
+    store_fe(aggs + (size_t)blockIdx.y * aggs_stride + k, acc);
+}
+// in place: aggs[k] <- sum_{m>k} aggs[m] (z^run)^(m-k-1)
+__global__ void __launch_bounds__(SCAN_THREADS) kate_spine_kernel(fe* aggs_all, KatePoints pts, unsigned count, unsigned aggs_stride)
+{
+    __shared__ fe sh[SCAN_THREADS];
+    fe* aggs = aggs_all + (size_t)blockIdx.x * aggs_stride;
+    const fe M = pts.z_run[blockIdx.x];
+    const unsigned t = threadIdx.x, T = blockDim.x;
+    const unsigned per = (count + T - 1) / T;
+    const unsigned lo = t * per, hi = (lo + per < count) ? lo + per : count;
+    fe a = Fr::zero();
+    for (unsigned k = hi; k > lo; --k) a = Fr::add(Fr::mul(a, M), load_fe(aggs + k - 1));
+    // a = sum_{k in [lo, hi)} c_k M^(k - lo); ranges that end early (hi < lo + per) only occur above every non-zero aggregate
+    fe mult = pts.z_span[blockIdx.x];
+    sh[t] = a;
+    __syncthreads();
+    for (unsigned d = 1; d < T; d <<= 1)
+    {
+        fe v = sh[t];
+        if (t + d < T) v = Fr::add(v, Fr::mul(sh[t + d], mult));
+        __syncthreads();
+        sh[t] = v;
+        __syncthreads();
+        mult = Fr::sqr(mult);
+    }
+    fe carry = (t + 1 < T) ? sh[t + 1] : Fr::zero();
+    // a thread whose range is cut short by `count` sits at the top: its carry is zero and stays aligned
+    if (lo < count && hi < lo + per) carry = Fr::zero();
+    for (unsigned k = hi; k > lo; --k)
+    {
+        const fe c = load_fe(aggs + k - 1);
+        store_fe(aggs + k - 1, carry);
+        carry = Fr::add(c, Fr::mul(carry, M));
+    }
+}
+__global__ void kate_apply_kernel(fe* data, const fe* aggs, KatePoints pts, unsigned n, unsigned run, unsigned aggs_stride)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first = k * run;
+    if (first >= n) return;
+    fe* f = data + (size_t)blockIdx.y * n;
+    const fe z = pts.z[blockIdx.y];
+    fe carry = load_fe(aggs + (size_t)blockIdx.y * aggs_stride + k);
+    const unsigned last = (first + run < n) ? first + run : n;
+    for (unsigned j = last; j > first; --j)
+    {
+        const fe c = load_fe(f + j - 1);
+        store_fe(f + j - 1, carry);
+        carry = Fr::add(c, Fr::mul(carry, z));
+    }
+}
+} // namespace plonkk
+
+// =================================================================================================================
+// Host driver
+// =================================================================================================================
+namespace plonk
+{
+using namespace plonkk;
+
+namespace
+{
+size_t g_plonk_launches = 0;
+const fe ROOT_2_28 = { { 0x80D13D9Cu, 0x636E7355u, 0x2445FFD6u, 0xA22BF374u, 0x1EB203D8u, 0x56452AC0u, 0x2963F9E7u, 0x1860EF94u } };
+
+fe host_root_of_unity(unsigned log_n) // field.hpp:487-494
+{
+    fe r = ROOT_2_28;
+    for (unsigned i = 28; i > log_n; --i) r = Fr::reduce(Fr::sqr(r));
+    return r;
+}
+fe host_pow(fe base, uint64_t e) { return Fr::reduce(Fr::pow_u64(base, e)); }
+fe from_u64(const uint64_t* p)
+{
+    fe r;
+    memcpy(r.v, p, 32);
+    return r;
+}
+unsigned grid_for(size_t count, unsigned block)
+{
+    size_t g = (count + block - 1) / block;
+    const size_t cap = (size_t)bbg_rt::num_sms() * 8;
+    if (g > cap) g = cap;
+    return g == 0 ? 1u : (unsigned)g;
+}
+} // namespace
+
+struct Prover
+{
+    unsigned log_n = 0;
+    size_t n = 0;
+    void* arena = nullptr;
+    fe *w_lag = nullptr, *w_coef = nullptr, *w4 = nullptr;
+    fe *sigma = nullptr, *s4 = nullptr;
+    fe *z = nullptr, *z4 = nullptr;
+    fe *q = nullptr, *q2 = nullptr, *l1 = nullptr;
+    fe *quot_large = nullptr, *quot_mid = nullptr, *r = nullptr, *tmp = nullptr;
+    fe *aggs = nullptr, *eval_partial = nullptr, *eval_out = nullptr;
+    uint32_t* map = nullptr;
+    fe* pow_mem = nullptr;
+    PowTable pow_small{}, pow_mid{}, pow_large{};
+    unsigned aggs_stride = 0, partial_stride = 0;
+    const void* d_srs = nullptr;
+    bool have_witness = false, have_perm = false, have_selectors = false, tables_ready = false;
+};
+
+static int build_pow_table(Prover* p, unsigned log_size, fe*& cursor, PowTable* out, cudaStream_t st)
+{
+    const int lo_log = (int)(log_size < 11 ? log_size : 11);
+    const fe w = host_root_of_unity(log_size);
+    out->lo = cursor;
+    out->lo_log = lo_log;
+    BBG_LAUNCH_NOSYNC(powers_kernel, dim3(((1u << lo_log) + 127) / 128), dim3(128), st, cursor, w, 1u << lo_log);
+    cursor += (size_t)1 << lo_log;
+    ++g_plonk_launches;
+    if (log_size > (unsigned)lo_log)
+    {
+        const unsigned hi_count = 1u << (log_size - lo_log);
+        out->hi = cursor;
+        BBG_LAUNCH_NOSYNC(powers_kernel, dim3((hi_count + 127) / 128), dim3(128), st, cursor, host_pow(w, (uint64_t)1 << lo_log), hi_count);
+        cursor += hi_count;
+        ++g_plonk_launches;
+    }
+    else out->hi = nullptr;
+    (void)p;
+    return bbg_rt::last_error();
+}
+
+int create(unsigned log_n, Prover** out)
+{
+    // the 4n domain has to fit the NTT (<= 2^22) and every domain needs at least 4 points for the Z(X w) index shifts
+    if (log_n < 2 || log_n > 20) return 1002;
+    Prover* p = new Prover();
+    p->log_n = log_n;
+    p->n = (size_t)1 << log_n;
+    const size_t n = p->n;
+    const unsigned run_aggs = (unsigned)((n + ZRUN - 1) / ZRUN);
+    p->aggs_stride = (run_aggs + 7) & ~7u;
+    p->partial_stride = (unsigned)((4 * n + EVAL_SPAN - 1) / EVAL_SPAN + 8);
+    const size_t pow_elems = 3 * ((size_t)2 << 11) + 64;
+    // element counts, in the order of the header comment
+    const size_t counts[] = { 3 * n, 3 * n, 12 * n, 3 * n, 12 * n, n, 4 * n, 5 * n, 10 * n, 2 * n, 4 * n, 2 * n, n, 2 * n,
+                              2 * (size_t)p->aggs_stride, (size_t)MAX_EVAL_JOBS * p->partial_stride, MAX_EVAL_JOBS, pow_elems };
+    size_t total = 0;
+    for (size_t c : counts) total += (c + 7) & ~(size_t)7;
+    const size_t bytes = total * 32 + 3 * n * 4 + 256;
+    int e = bbg_rt::dev_alloc(&p->arena, bytes);
+    if (e != 0)
+    {
+        delete p;
+        return e;
+    }
+    fe* cur = (fe*)p->arena;
+    auto take = [&](size_t c) { fe* r = cur; cur += (c + 7) & ~(size_t)7; return r; };
+    p->w_lag = take(counts[0]);
+    p->w_coef = take(counts[1]);
+    p->w4 = take(counts[2]);
+    p->sigma = take(counts[3]);
+    p->s4 = take(counts[4]);
+    p->z = take(counts[5]);
+    p->z4 = take(counts[6]);
+    p->q = take(counts[7]);
+    p->q2 = take(counts[8]);
+    p->l1 = take(counts[9]);
+    p->quot_large = take(counts[10]);
+    p->quot_mid = take(counts[11]);
+    p->r = take(counts[12]);
+    p->tmp = take(counts[13]);
+    p->aggs = take(counts[14]);
+    p->eval_partial = take(counts[15]);
+    p->eval_out = take(counts[16]);
+    p->pow_mem = take(counts[17]);
+    p->map = (uint32_t*)cur;
+    *out = p;
+    return 0;
+}
+
+void destroy(Prover* p)
+{
+    if (p == nullptr) return;
+    if (p->arena) bbg_rt::dev_free(p->arena);
+    delete p;
+}
+
+static int ensure_tables(Prover* p, cudaStream_t st)
+{
+    if (p->tables_ready) return 0;
+    fe* cursor = p->pow_mem;
+    BBG_CHECK(build_pow_table(p, p->log_n, cursor, &p->pow_small, st));
+    BBG_CHECK(build_pow_table(p, p->log_n + 1, cursor, &p->pow_mid, st));
+    BBG_CHECK(build_pow_table(p, p->log_n + 2, cursor, &p->pow_large, st));
+    p->tables_ready = true;
+    return 0;
+}
+
+int set_witness(Prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o, cudaStream_t st)
+{
+    const uint64_t* src[3] = { w_l, w_r, w_o };
+    for (int k = 0; k < 3; ++k)
+    {
+        if (src[k] == nullptr) return 1007;
+        BBG_CHECK(bbg_hostcopy::h2d(p->w_lag + (size_t)k * p->n, src[k], p->n * 32, st));
+    }
+    p->have_witness = true;
+    return 0;
+}
+
+int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uint32_t* m3, cudaStream_t st)
+{
+    const uint32_t* src[3] = { m1, m2, m3 };
+    for (int k = 0; k < 3; ++k)
+    {
+        if (src[k] == nullptr) return 1007;
+        BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * p->n, src[k], p->n * 4, st));
+    }
+    p->have_perm = true;
+    return 0;
+}
+
+int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t st)
+{
+    for (int k = 0; k < 5; ++k)
+    {
+        if (q_lagrange[k] == nullptr) return 1007;
+        BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * p->n, q_lagrange[k], p->n * 32, st));
+    }
+    p->have_selectors = true;
+    return 0;
+}
+
+int set_srs(Prover* p, const void* d_table)
+{
+    p->d_srs = d_table;
+    return 0;
+}
+
+static int commit(Prover* p, const fe* d_scalars, uint64_t out_xyz[12], cudaStream_t st)
+{
+    hostg1::hxyzz r;
+    BBG_CHECK(msm_device(d_scalars, p->d_srs, p->n, &r, st));
+    hostg1::to_normalized_jacobian(r, out_xyz);
+    return 0;
+}
+
+// prover.cpp:126-135 compute_wire_coefficients + :65-89 compute_wire_commitments (and, off the critical path of the
+// transcript, permutation.hpp's sigma polynomials)
+int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
+{
+    if (!p->have_witness || !p->have_perm || !p->have_selectors || p->d_srs == nullptr) return 1007;
+    BBG_CHECK(ensure_tables(p, st));
+    const size_t n = p->n;
+    BBG_CHECK(bbg_rt::d2d(p->w_coef, p->w_lag, 3 * n * 32, st));
+    BBG_CHECK(ntt_device(p->w_coef, n, 3, p->log_n, OP_IFFT, nullptr, st));
+    {
+    bbg_prof::Scope prof(bbg_prof::PLONK_ELEMENTWISE, st);
+    BBG_LAUNCH_NOSYNC(sigma_from_mapping_kernel, dim3(grid_for(3 * n, 256)), dim3(256), st, p->sigma, (const uint32_t*)p->map, p->pow_small, (unsigned)n,
+                      (unsigned)(3 * n));
+    ++g_plonk_launches;
+    }
+    for (int k = 0; k < 3; ++k) BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, out_xyz + 12 * k, st));
+    return bbg_rt::last_error();
+}
+
+// prover.cpp:137-225 compute_z_coefficients + :91-107 compute_z_commitment
+int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, uint64_t out_xyz[12], cudaStream_t st)
+{
+    const size_t n = p->n;
+    const fe beta = from_u64(beta_), gamma = from_u64(gamma_);
+    fe* num = p->tmp;
+    fe* den = p->tmp + n;
+    {
+        bbg_prof::Scope prof(bbg_prof::PLONK_ELEMENTWISE, st);
+        BBG_LAUNCH_NOSYNC(z_terms_kernel, dim3(grid_for(n, 128)), dim3(128), st, num, den, (const fe*)p->w_lag, (const fe*)p->sigma, p->pow_small, beta, gamma,
+                          (unsigned)n);
+    }
+    const unsigned runs = (unsigned)((n + ZRUN - 1) / ZRUN);
+    bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::PLONK_SCAN, st);
+    BBG_LAUNCH_NOSYNC(prod_reduce_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, (const fe*)p->tmp, p->aggs, (unsigned)n, (unsigned)ZRUN, n, p->aggs_stride);
+    BBG_LAUNCH(prod_spine_kernel, dim3(2), dim3(SCAN_THREADS), 0, st, p->aggs, runs, p->aggs_stride);
+    BBG_LAUNCH_NOSYNC(z_finish_kernel, dim3((runs + 63) / 64), dim3(64), st, p->z, (const fe*)num, (const fe*)den, (const fe*)p->aggs,
+                      (const fe*)(p->aggs + p->aggs_stride), (unsigned)n);
+    delete prof_scan;
+    g_plonk_launches += 4;
+    BBG_CHECK(ntt_device(p->z, n, 1, p->log_n, OP_IFFT, nullptr, st));
+    BBG_CHECK(commit(p, p->z, out_xyz, st));
+    return bbg_rt::last_error();
+}
+
+// prover.cpp:393-463 compute_quotient_polynomial (after the z commitment) + :109-124 compute_quotient_commitment
+int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* alpha_, const uint64_t* alpha_base_,
+                   uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
+{
+    const size_t n = p->n, n2 = 2 * n, n4 = 4 * n;
+    const fe beta = from_u64(beta_), gamma = from_u64(gamma_), alpha = from_u64(alpha_), alpha_base = from_u64(alpha_base_);
+    // wires on the 4n coset (prover.cpp:407-414)
+    BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->w4, (const fe*)p->w_coef, (unsigned)n, (unsigned)n4, n, n4);
+    BBG_CHECK(ntt_device(p->w4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
+    // sigma: Lagrange -> beta-scaled coefficients (:246-248), then beta sigma + w + gamma on the 4n coset (:252-273)
+    BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT_WITH_CONSTANT, beta_, st));
+    BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, gamma, (unsigned)n,
+                      (unsigned)n4);
+    BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
+    // alpha Z on the 4n coset (:275)
+    BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 1), dim3(256), st, p->z4, (const fe*)p->z, (unsigned)n, (unsigned)n4, n, n4);
+    BBG_CHECK(ntt_device(p->z4, n4, 1, p->log_n + 2, OP_COSET_FFT_WITH_CONSTANT, alpha_, st));
+    // L_1 on the 2n coset (:349-351)
+    BBG_CHECK(lagrange_fft_device(p->l1, p->log_n, p->log_n + 1, st));
+    // selectors: Lagrange -> coefficients -> alpha_base-scaled 2n coset evaluations (arithmetic_widget.cpp:62-78)
+    BBG_CHECK(ntt_device(p->q, n, 5, p->log_n, OP_IFFT, nullptr, st));
+    BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n2, 256), 5), dim3(256), st, p->q2, (const fe*)p->q, (unsigned)n, (unsigned)n2, n, n2);
+    BBG_CHECK(ntt_device(p->q2, n2, 5, p->log_n + 1, OP_COSET_FFT_WITH_CONSTANT, alpha_base_, st));
+    g_plonk_launches += 4;
+
+    QuotientConsts c;
+    c.g = gen_k1();
+    c.beta = beta;
+    c.gamma = gamma;
+    c.alpha = alpha;
+    c.alpha_sqr = Fr::reduce(Fr::sqr(alpha));
+    c.g_beta = Fr::reduce(Fr::mul(c.g, beta));
+    {
+        const fe w = host_root_of_unity(p->log_n);
+        c.neg_root_inv = Fr::reduce(Fr::neg(Fr::invert(w)));
+    }
+    // (g w_S^j)^n - 1 = g^n w_S^j - 1, S = target / source size (compute_multiplicative_subgroup, :104-127)
+    fe gn = c.g;
+    for (unsigned i = 0; i < p->log_n; ++i) gn = Fr::reduce(Fr::sqr(gn));
+    auto fill_vinv = [&](unsigned log_s) {
+        const fe ws = host_root_of_unity(log_s);
+        fe cur = gn;
+        for (unsigned j = 0; j < 4; ++j)
+        {
+            c.vinv[j] = j < (1u << log_s) ? Fr::invert(Fr::reduce(Fr::sub(cur, Fr::one()))) : Fr::zero();
+            cur = Fr::reduce(Fr::mul(cur, ws));
+        }
+    };
+    fill_vinv(2);
+    BBG_LAUNCH_NOSYNC(quotient_large_kernel, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->s4, (const fe*)p->w4, (const fe*)p->z4,
+                      p->pow_large, c, (unsigned)n4);
+    fill_vinv(1);
+    BBG_LAUNCH_NOSYNC(quotient_mid_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->z4, (const fe*)p->l1, (const fe*)p->w4,
+                      (const fe*)p->q2, p->pow_mid, c, (unsigned)n2);
+    BBG_CHECK(ntt_device(p->quot_mid, n2, 1, p->log_n + 1, OP_COSET_IFFT, nullptr, st));
+    BBG_CHECK(ntt_device(p->quot_large, n4, 1, p->log_n + 2, OP_COSET_IFFT, nullptr, st));
+    BBG_LAUNCH_NOSYNC(add_into_kernel, dim3(grid_for(n2, 256)), dim3(256), st, p->quot_large, (const fe*)p->quot_mid, (unsigned)n2);
+    g_plonk_launches += 3;
+    for (int k = 0; k < 3; ++k) BBG_CHECK(commit(p, p->quot_large + (size_t)k * n, out_xyz + 12 * k, st));
+    return bbg_rt::last_error();
+}
+
+static int run_evals(Prover* p, const EvalJobs& jobs, int count, uint64_t* out, cudaStream_t st)
+{
+    unsigned max_blocks = 1;
+    for (int j = 0; j < count; ++j)
+    {
+        const unsigned nb = (jobs.len[j] + EVAL_SPAN - 1) / EVAL_SPAN;
+        if (nb > max_blocks) max_blocks = nb;
+    }
+    BBG_LAUNCH(eval_partial_kernel, dim3(max_blocks, (unsigned)count), dim3(EVAL_THREADS), 0, st, jobs, p->eval_partial, p->partial_stride);
+    BBG_LAUNCH(eval_final_kernel, dim3((unsigned)count), dim3(SCAN_THREADS), 0, st, jobs, (const fe*)p->eval_partial, p->partial_stride, p->eval_out);
+    g_plonk_launches += 2;
+    BBG_CHECK(bbg_rt::d2h(out, p->eval_out, (size_t)count * 32, st));
+    return bbg_rt::sync(st);
+}
+
+// prover.cpp:465-477: w_l, w_r, w_o, beta sigma_1, beta sigma_2 at z; Z at z w; the quotient's 3n coefficients at z
+int round_evaluations(Prover* p, const uint64_t* zeta_, const uint64_t* zeta_omega_, uint64_t* out /* 7 x 4 */, cudaStream_t st)
+{
+    const size_t n = p->n;
+    EvalJobs jobs;
+    const fe zeta = from_u64(zeta_), zw = from_u64(zeta_omega_);
+    const fe* polys[7] = { p->w_coef, p->w_coef + n, p->w_coef + 2 * n, p->sigma, p->sigma + n, p->z, p->quot_large };
+    for (int j = 0; j < 7; ++j)
+    {
+        jobs.poly[j] = polys[j];
+        jobs.len[j] = (unsigned)(j == 6 ? 3 * n : n);
+        jobs.point[j] = j == 5 ? zw : zeta;
+    }
+    for (int j = 7; j < MAX_EVAL_JOBS; ++j)
+    {
+        jobs.poly[j] = nullptr;
+        jobs.len[j] = 0;
+        jobs.point[j] = Fr::zero();
+    }
+    return run_evals(p, jobs, 7, out, st);
+}
+
+// prover.cpp:479-503: the linearisation polynomial r(X) and its evaluation at z
+int round_linearise(Prover* p, const uint64_t* scalars /* 7 x 4: c_z, c_sigma3, w_lr, w_l, w_r, w_o, alpha_base */, const uint64_t* zeta_,
+                    uint64_t out_eval[4], cudaStream_t st)
+{
+    const size_t n = p->n;
+    LinearConsts c;
+    c.c_z = from_u64(scalars);
+    c.c_sigma3 = from_u64(scalars + 4);
+    c.w_lr = from_u64(scalars + 8);
+    c.w_l = from_u64(scalars + 12);
+    c.w_r = from_u64(scalars + 16);
+    c.w_o = from_u64(scalars + 20);
+    c.alpha_base = from_u64(scalars + 24);
+    BBG_LAUNCH_NOSYNC(linearise_kernel, dim3(grid_for(n, 128)), dim3(128), st, p->r, (const fe*)p->z, (const fe*)(p->sigma + 2 * n), (const fe*)p->q, c, (unsigned)n);
+    ++g_plonk_launches;
+    EvalJobs jobs;
+    for (int j = 0; j < MAX_EVAL_JOBS; ++j)
+    {
+        jobs.poly[j] = nullptr;
+        jobs.len[j] = 0;
+        jobs.point[j] = Fr::zero();
+    }
+    jobs.poly[0] = p->r;
+    jobs.len[0] = (unsigned)n;
+    jobs.point[0] = from_u64(zeta_);
+    return run_evals(p, jobs, 1, out_eval, st);
+}
+
+// prover.cpp:505-655 compute_opening_elements after the nu challenge
+int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint64_t* beta_inv_, const uint64_t* zeta_, const uint64_t* zeta_omega_,
+                   uint64_t* out_xyz /* 2 x 12 */, cudaStream_t st)
+{
+    const size_t n = p->n;
+    OpeningConsts c;
+    for (int i = 0; i < 7; ++i) c.nu[i] = from_u64(nu_powers + 4 * i);
+    c.beta_inv = from_u64(beta_inv_);
+    const fe zeta = from_u64(zeta_), zw = from_u64(zeta_omega_);
+    c.z_pow_n = host_pow(zeta, n);
+    c.z_pow_2n = host_pow(zeta, 2 * n);
+    fe* opening = p->tmp;
+    fe* shifted = p->tmp + n;
+    BBG_LAUNCH_NOSYNC(opening_combine_kernel, dim3(grid_for(n, 128)), dim3(128), st, opening, shifted, (const fe*)p->quot_large, (const fe*)p->r,
+                      (const fe*)p->w_coef, (const fe*)p->sigma, (const fe*)p->z, c, (unsigned)n);
+    const unsigned run = ZRUN;
+    const unsigned runs = (unsigned)((n + run - 1) / run);
+    const unsigned per = (runs + SCAN_THREADS - 1) / SCAN_THREADS;
+    KatePoints pts;
+    pts.z[0] = zeta;
+    pts.z[1] = zw;
+    for (int k = 0; k < 2; ++k)
+    {
+        pts.z_run[k] = host_pow(pts.z[k], run);
+        pts.z_span[k] = host_pow(pts.z_run[k], per);
+    }
+    BBG_LAUNCH_NOSYNC(kate_reduce_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, (const fe*)p->tmp, p->aggs, pts, (unsigned)n, run, p->aggs_stride);
+    BBG_LAUNCH(kate_spine_kernel, dim3(2), dim3(SCAN_THREADS), 0, st, p->aggs, pts, runs, p->aggs_stride);
+    BBG_LAUNCH_NOSYNC(kate_apply_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, p->tmp, (const fe*)p->aggs, pts, (unsigned)n, run, p->aggs_stride);
+    g_plonk_launches += 4;
+    BBG_CHECK(commit(p, opening, out_xyz, st));
+    BBG_CHECK(commit(p, shifted, out_xyz + 12, st));
+    return bbg_rt::last_error();
+}
+
+size_t launch_count() { return g_plonk_launches; }
+} // namespace plonk
+} // namespace bbg

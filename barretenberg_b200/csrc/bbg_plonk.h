@@ -1,0 +1,27 @@
+// Internal C++ interface of the HBM-resident PLONK prover rounds (bbg_plonk.cu); the C ABI wrappers live in
+// bbg_capi.cu (bbg_plonk_* in include/bbgpu.h).
+#pragma once
+#include "bbg_rt.h"
+
+namespace bbg
+{
+namespace plonk
+{
+struct Prover;
+int create(unsigned log_n, Prover** out);
+void destroy(Prover* p);
+int set_witness(Prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o, cudaStream_t st);
+int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uint32_t* m3, cudaStream_t st);
+int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t st);
+int set_srs(Prover* p, const void* d_table);
+int round_wires(Prover* p, uint64_t* out_xyz, cudaStream_t st);
+int round_grand_product(Prover* p, const uint64_t* beta, const uint64_t* gamma, uint64_t out_xyz[12], cudaStream_t st);
+int round_quotient(Prover* p, const uint64_t* beta, const uint64_t* gamma, const uint64_t* alpha, const uint64_t* alpha_base, uint64_t* out_xyz,
+                   cudaStream_t st);
+int round_evaluations(Prover* p, const uint64_t* zeta, const uint64_t* zeta_omega, uint64_t* out, cudaStream_t st);
+int round_linearise(Prover* p, const uint64_t* scalars, const uint64_t* zeta, uint64_t out_eval[4], cudaStream_t st);
+int round_openings(Prover* p, const uint64_t* nu_powers, const uint64_t* beta_inv, const uint64_t* zeta, const uint64_t* zeta_omega, uint64_t* out_xyz,
+                   cudaStream_t st);
+size_t launch_count();
+} // namespace plonk
+} // namespace bbg

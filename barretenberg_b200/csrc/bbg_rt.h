@@ -85,12 +85,16 @@ enum id
     MSM_REDUCE,
     MSM_HOST_FINISH,
     G1_GENERATE,
+    PLONK_ELEMENTWISE,
+    PLONK_SCAN,
+    PLONK_EVAL,
     NUM_IDS
 };
 inline const char* name(int i)
 {
     static const char* n[NUM_IDS] = { "ntt_pass_a", "ntt_pass_b", "ntt_small", "ntt_tables", "msm_digits", "msm_scan", "msm_scatter",
-                                      "msm_accumulate", "msm_fixup", "msm_chunk", "msm_reduce", "msm_host_finish", "g1_generate" };
+                                      "msm_accumulate", "msm_fixup", "msm_chunk", "msm_reduce", "msm_host_finish", "g1_generate",
+                                      "plonk_elementwise", "plonk_scan", "plonk_eval" };
     return (i >= 0 && i < NUM_IDS) ? n[i] : "?";
 }
 struct State

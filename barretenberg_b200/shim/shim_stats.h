@@ -12,7 +12,7 @@ namespace bbg_shim
 {
 struct Stats
 {
-    static constexpr int MAX = 16;
+    static constexpr int MAX = 40;
     const char* name[MAX];
     double ms[MAX];
     unsigned long calls[MAX];

@@ -1,6 +1,8 @@
 """BASELINE configs[4] at test size: the reference's unmodified waffle prover linked against the shims
 (barretenberg_b200/shim -> libbbgpu.so) must produce the SAME proof, field for field, as the all-CPU reference
-build, and the reference verifier must accept it.  Binaries are prebuilt by tests/cpp/Makefile (build/)."""
+build, and the reference verifier must accept it.  Binaries are prebuilt by tests/cpp/Makefile (build/):
+  prover_gpu          MSM / NTT shims + the HBM-resident Prover::construct_proof (shim/prover_gpu.cpp)
+  prover_gpu_classic  MSM / NTT shims only, the reference's own round structure"""
 import json
 import os
 import subprocess
@@ -29,8 +31,10 @@ def srs():
     return path
 
 
-def run(binary, log_gates):
-    out = subprocess.run([os.path.join(B, binary), str(log_gates)], cwd=H.ROOT, capture_output=True, text=True, timeout=600)
+def run(binary, log_gates, repeat=1, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run([os.path.join(B, binary), str(log_gates), str(repeat)], cwd=H.ROOT, capture_output=True, text=True, timeout=600, env=e)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return json.loads(out.stdout.strip().splitlines()[-1])
 
@@ -38,8 +42,21 @@ def run(binary, log_gates):
 @pytest.mark.parametrize("log_gates", [5, 8, 12, 14])  # 2^4 gives the recipe zero gates: the reference itself throws bad_alloc
 def test_prover_gpu_matches_cpu_reference(srs, log_gates):
     cpu = run("prover_cpu", log_gates)
-    gpu = run("prover_gpu", log_gates)
+    gpu = run("prover_gpu", log_gates, repeat=2)  # second proof after Prover::reset()
     assert cpu["verified"] and gpu["verified"]
     assert gpu["n"] == cpu["n"]
+    for k, v in cpu["proof"].items():
+        assert gpu["proof"][k] == v, k
+
+
+@pytest.mark.parametrize("binary,env", [("prover_gpu_classic", {}), ("prover_gpu", {"BBG_PLONK_RESIDENT": "0"})])
+@pytest.mark.parametrize("log_gates", [5, 12])
+def test_prover_classic_round_structure_matches_cpu_reference(srs, log_gates, binary, env):
+    """the ten-entry-point drop-in alone (reference round structure), also reachable from the resident build"""
+    if not os.path.exists(os.path.join(B, binary)):
+        pytest.skip(binary + " not built")
+    cpu = run("prover_cpu", log_gates)
+    gpu = run(binary, log_gates, repeat=2, env=env)
+    assert cpu["verified"] and gpu["verified"]
     for k, v in cpu["proof"].items():
         assert gpu["proof"][k] == v, k
