@@ -91,10 +91,10 @@ inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int thread
     for (auto& th : pool) th.join();
 }
 
-inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st)
+// `r`: the pinned staging ring to use (one per host thread that copies; the default ring belongs to the caller's thread)
+inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t st)
 {
     if (bytes < SMALL || is_pinned(h)) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
-    Ring& r = ring();
     BBG_CHECK(r.init());
     size_t off = 0;
     for (int k = 0; off < bytes; ++k)
@@ -109,6 +109,7 @@ inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st)
     }
     return 0;
 }
+inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st) { return h2d_ring(ring(), d, h, bytes, st); }
 
 // returns with the data in h (synchronous for pageable destinations, like cudaMemcpy)
 inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st)

@@ -26,6 +26,9 @@
 #include "bbg_plonk.h"
 
 #include <vector>
+#ifndef BBG_EMULATE
+#include <thread>
+#endif
 
 namespace bbg
 {
@@ -510,7 +513,30 @@ struct Prover
     unsigned aggs_stride = 0, partial_stride = 0;
     const void* d_srs = nullptr;
     bool have_witness = false, have_perm = false, have_selectors = false, tables_ready = false;
+    bool sigma_ready = false; // sigma[] holds this proof's Lagrange values
+#ifndef BBG_EMULATE
+    // circuit constants (mappings, selectors) are uploaded by a helper thread on its own stream and staging ring while
+    // round 1 already runs on the witness; the rounds that need them wait on the events
+    int device = 0;
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_perm = nullptr, ev_sel = nullptr, ev_fence = nullptr;
+    bbg_hostcopy::Ring upload_ring;
+    std::thread uploader;
+    int uploader_kind = 0; // 0 none, 1 mappings, 2 selectors
+    int upload_error = 0;
+#endif
 };
+
+#ifndef BBG_EMULATE
+static int join_uploader(Prover* p)
+{
+    if (p->uploader.joinable()) p->uploader.join();
+    p->uploader_kind = 0;
+    const int e = p->upload_error;
+    p->upload_error = 0;
+    return e;
+}
+#endif
 
 static int build_pow_table(Prover* p, unsigned log_size, fe*& cursor, PowTable* out, cudaStream_t st)
 {
@@ -579,6 +605,18 @@ int create(unsigned log_n, Prover** out)
     p->eval_out = take(counts[16]);
     p->pow_mem = take(counts[17]);
     p->map = (uint32_t*)cur;
+#ifndef BBG_EMULATE
+    cudaGetDevice(&p->device);
+    e = (int)cudaStreamCreateWithFlags(&p->upload_stream, cudaStreamNonBlocking);
+    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_perm, cudaEventDisableTiming);
+    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_sel, cudaEventDisableTiming);
+    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_fence, cudaEventDisableTiming);
+    if (e != 0)
+    {
+        destroy(p);
+        return e;
+    }
+#endif
     *out = p;
     return 0;
 }
@@ -586,6 +624,18 @@ int create(unsigned log_n, Prover** out)
 void destroy(Prover* p)
 {
     if (p == nullptr) return;
+#ifndef BBG_EMULATE
+    join_uploader(p);
+    if (p->upload_stream)
+    {
+        cudaStreamSynchronize(p->upload_stream);
+        cudaStreamDestroy(p->upload_stream);
+    }
+    if (p->ev_perm) cudaEventDestroy(p->ev_perm);
+    if (p->ev_sel) cudaEventDestroy(p->ev_sel);
+    if (p->ev_fence) cudaEventDestroy(p->ev_fence);
+    p->upload_ring.release();
+#endif
     if (p->arena) bbg_rt::dev_free(p->arena);
     delete p;
 }
@@ -613,25 +663,60 @@ int set_witness(Prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint6
     return 0;
 }
 
+// The host buffers of the next two calls must stay valid and unmodified until bbg_plonk_round_quotient has returned
+// (they are the Prover's own mapping vectors and the widget's selector polynomials).
 int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uint32_t* m3, cudaStream_t st)
 {
     const uint32_t* src[3] = { m1, m2, m3 };
     for (int k = 0; k < 3; ++k)
-    {
         if (src[k] == nullptr) return 1007;
-        BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * p->n, src[k], p->n * 4, st));
-    }
+    p->sigma_ready = false;
+#ifndef BBG_EMULATE
+    BBG_CHECK(join_uploader(p));
+    // the previous proof's kernels may still read map[]: the copies wait for the work stream
+    BBG_CHECK(cudaEventRecord(p->ev_fence, st));
+    BBG_CHECK(cudaStreamWaitEvent(p->upload_stream, p->ev_fence, 0));
+    p->uploader_kind = 1;
+    p->uploader = std::thread([p, m1, m2, m3]() {
+        cudaSetDevice(p->device);
+        const uint32_t* s3[3] = { m1, m2, m3 };
+        int e = 0;
+        for (int k = 0; k < 3 && e == 0; ++k) e = bbg_hostcopy::h2d_ring(p->upload_ring, p->map + (size_t)k * p->n, s3[k], p->n * 4, p->upload_stream);
+        if (e == 0) e = (int)cudaEventRecord(p->ev_perm, p->upload_stream);
+        p->upload_error = e;
+    });
+#else
+    for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * p->n, src[k], p->n * 4, st));
+#endif
     p->have_perm = true;
     return 0;
 }
 
 int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t st)
 {
+    const uint64_t* src[5];
     for (int k = 0; k < 5; ++k)
     {
         if (q_lagrange[k] == nullptr) return 1007;
-        BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * p->n, q_lagrange[k], p->n * 32, st));
+        src[k] = q_lagrange[k];
     }
+#ifndef BBG_EMULATE
+    BBG_CHECK(join_uploader(p));
+    BBG_CHECK(cudaEventRecord(p->ev_fence, st));
+    BBG_CHECK(cudaStreamWaitEvent(p->upload_stream, p->ev_fence, 0));
+    p->uploader_kind = 2;
+    const uint64_t *q0 = src[0], *q1 = src[1], *q2 = src[2], *q3 = src[3], *q4 = src[4];
+    p->uploader = std::thread([p, q0, q1, q2, q3, q4]() {
+        cudaSetDevice(p->device);
+        const uint64_t* s5[5] = { q0, q1, q2, q3, q4 };
+        int e = 0;
+        for (int k = 0; k < 5 && e == 0; ++k) e = bbg_hostcopy::h2d_ring(p->upload_ring, p->q + (size_t)k * p->n, s5[k], p->n * 32, p->upload_stream);
+        if (e == 0) e = (int)cudaEventRecord(p->ev_sel, p->upload_stream);
+        p->upload_error = e;
+    });
+#else
+    for (int k = 0; k < 5; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * p->n, src[k], p->n * 32, st));
+#endif
     p->have_selectors = true;
     return 0;
 }
@@ -659,12 +744,6 @@ int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
     const size_t n = p->n;
     BBG_CHECK(bbg_rt::d2d(p->w_coef, p->w_lag, 3 * n * 32, st));
     BBG_CHECK(ntt_device(p->w_coef, n, 3, p->log_n, OP_IFFT, nullptr, st));
-    {
-    bbg_prof::Scope prof(bbg_prof::PLONK_ELEMENTWISE, st);
-    BBG_LAUNCH_NOSYNC(sigma_from_mapping_kernel, dim3(grid_for(3 * n, 256)), dim3(256), st, p->sigma, (const uint32_t*)p->map, p->pow_small, (unsigned)n,
-                      (unsigned)(3 * n));
-    ++g_plonk_launches;
-    }
     for (int k = 0; k < 3; ++k) BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, out_xyz + 12 * k, st));
     return bbg_rt::last_error();
 }
@@ -676,8 +755,19 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
     const fe beta = from_u64(beta_), gamma = from_u64(gamma_);
     fe* num = p->tmp;
     fe* den = p->tmp + n;
+#ifndef BBG_EMULATE
+    // the mappings were uploaded behind round 1; ev_perm is recorded once their helper thread has finished (a selector
+    // upload that replaced it may still be running, which is fine)
+    if (p->uploader_kind == 1) BBG_CHECK(join_uploader(p));
+    BBG_CHECK(cudaStreamWaitEvent(st, p->ev_perm, 0));
+#endif
     {
         bbg_prof::Scope prof(bbg_prof::PLONK_ELEMENTWISE, st);
+        // permutation.hpp:13-88 (prover.cpp:659-661)
+        BBG_LAUNCH_NOSYNC(sigma_from_mapping_kernel, dim3(grid_for(3 * n, 256)), dim3(256), st, p->sigma, (const uint32_t*)p->map, p->pow_small, (unsigned)n,
+                          (unsigned)(3 * n));
+        ++g_plonk_launches;
+        p->sigma_ready = true;
         BBG_LAUNCH_NOSYNC(z_terms_kernel, dim3(grid_for(n, 128)), dim3(128), st, num, den, (const fe*)p->w_lag, (const fe*)p->sigma, p->pow_small, beta, gamma,
                           (unsigned)n);
     }
@@ -700,6 +790,11 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
 {
     const size_t n = p->n, n2 = 2 * n, n4 = 4 * n;
     const fe beta = from_u64(beta_), gamma = from_u64(gamma_), alpha = from_u64(alpha_), alpha_base = from_u64(alpha_base_);
+    if (!p->sigma_ready) return 1007;
+#ifndef BBG_EMULATE
+    BBG_CHECK(join_uploader(p)); // the selector copy has been queued completely
+    BBG_CHECK(cudaStreamWaitEvent(st, p->ev_sel, 0));
+#endif
     // wires on the 4n coset (prover.cpp:407-414)
     BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->w4, (const fe*)p->w_coef, (unsigned)n, (unsigned)n4, n, n4);
     BBG_CHECK(ntt_device(p->w4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));

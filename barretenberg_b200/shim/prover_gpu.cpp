@@ -196,7 +196,8 @@ plonk_proof Prover::construct_proof()
 void Prover::reset()
 {
     // The resident path never transforms the host polynomials (w_l, w_r, w_o and the selectors stay in Lagrange form),
-    // so there is nothing to undo; r is only sized by the reference's round structure (prover.cpp:467).
-    if (r.get_size() != 0) bbg_shim::reference_reset(*this);
+    // so there is nothing to undo.  The reference's round structure leaves a copy of the witness in
+    // circuit_state.w_l_fft (prover.cpp:128, :400) until its own reset() empties it (:678): that is the marker.
+    if (circuit_state.w_l_fft.get_size() != 0) bbg_shim::reference_reset(*this);
 }
 } // namespace waffle
