@@ -425,11 +425,39 @@ int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* po
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     BBG_CHECK(ensure_ready());
-    for (size_t i = 0; i < batches; ++i)
+    if (batches == 0) return 0;
+    if (scalars == nullptr || points_tables == nullptr || out_xyz == nullptr) return BBG_E_BAD_ARGUMENT;
+    // the prover's case (prover.cpp:65-124, :640-652): several polynomials against the same table -> one pipeline
+    constexpr size_t GROUP = 4;
+    size_t i = 0;
+    while (i < batches)
     {
-        hostg1::hxyzz r;
-        BBG_CHECK(msm_host(scalars[i], points_tables[i], n, &r));
-        hostg1::to_normalized_jacobian(r, out_xyz + 12 * i);
+        size_t same = 1;
+        while (n > 0 && i + same < batches && same < GROUP && points_tables[i + same] == points_tables[i]) ++same;
+        if (same == 1)
+        {
+            hostg1::hxyzz r;
+            BBG_CHECK(msm_host(scalars[i], points_tables[i], n, &r));
+            hostg1::to_normalized_jacobian(r, out_xyz + 12 * i);
+        }
+        else
+        {
+            const void* d_table = nullptr;
+            if (points_tables[i] == nullptr) return BBG_E_BAD_ARGUMENT;
+            BBG_CHECK(resolve_table(points_tables[i], n, &d_table));
+            BBG_CHECK(g_stage_scalars.ensure(same * n * 32));
+            const void* ptrs[GROUP];
+            for (size_t k = 0; k < same; ++k)
+            {
+                if (scalars[i + k] == nullptr) return BBG_E_BAD_ARGUMENT;
+                ptrs[k] = (char*)g_stage_scalars.p + k * n * 32;
+                BBG_CHECK(bbg_hostcopy::h2d((void*)ptrs[k], scalars[i + k], n * 32, g_stream));
+            }
+            hostg1::hxyzz r[GROUP];
+            BBG_CHECK(msm_device_batched(ptrs, same, d_table, n, r, g_stream));
+            for (size_t k = 0; k < same; ++k) hostg1::to_normalized_jacobian(r[k], out_xyz + 12 * (i + k));
+        }
+        i += same;
     }
     return 0;
 }

@@ -26,6 +26,7 @@ struct Ring
     cudaEvent_t ev[RING] = {};
     bool ready = false;
     int threads = 1;
+    unsigned next = 0; // slots rotate across calls, so a short copy never waits for the previous call's chunk
     int init()
     {
         if (ready) return 0;
@@ -97,9 +98,9 @@ inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t 
     if (bytes < SMALL || is_pinned(h)) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
     BBG_CHECK(r.init());
     size_t off = 0;
-    for (int k = 0; off < bytes; ++k)
+    while (off < bytes)
     {
-        const int i = k % RING;
+        const int i = (int)(r.next++ % RING);
         const size_t len = bytes - off < CHUNK ? bytes - off : CHUNK;
         BBG_CHECK(cudaEventSynchronize(r.ev[i])); // chunk i is off the wire (an unrecorded event is complete)
         parallel_memcpy(r.buf[i], (const char*)h + off, len, r.threads);

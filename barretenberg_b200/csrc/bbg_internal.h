@@ -35,6 +35,8 @@ size_t ntt_launch_count();
 // Writes the un-normalised sum as XYZZ (16 x uint64: X, Y, ZZ, ZZZ) to the HOST buffer out_xyzz_host;
 // synchronises the stream (the window fold is the host-side finish, bbg_host_g1.h).
 int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t stream);
+// `batch` same-size MSMs over one table in a single pipeline; out_xyzz_host: batch x 16 uint64
+int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t stream);
 int msm_release_workspace();
 size_t msm_launch_count();
 // d_points[i] = (start + i * step) * G (affine, canonical), i < n; start / step: Fr Montgomery limbs (host)

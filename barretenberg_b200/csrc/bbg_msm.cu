@@ -580,19 +580,30 @@ int msm_release_workspace()
     return 0;
 }
 
-// d_out_xyzz: HOST buffer of 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sum
-int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t st)
+// `batch` MSMs of the same size over the same point table in ONE pipeline: MSM b's windows become the virtual windows
+// b * W .. b * W + W - 1 of a single sort / accumulate / reduce pass, so the latency-bound tail kernels (scan, fix-up,
+// chunk, reduce) and the host round trip are paid once per batch (the prover commits 3 + 1 + 3 + 2 polynomials per
+// proof against the same SRS, prover.cpp:65-124, :640-652).
+// out_xyzz_host: HOST buffer of batch x 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sums
+int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t st)
 {
-    hostg1::hxyzz result = hostg1::infinity();
+    if (batch == 0) return 0;
     if (n == 0)
     {
-        memcpy(out_xyzz_host, &result, sizeof result);
+        const hostg1::hxyzz inf = hostg1::infinity();
+        for (size_t b = 0; b < batch; ++b) memcpy((char*)out_xyzz_host + b * sizeof inf, &inf, sizeof inf);
         return 0;
     }
     if (2 * n > ((size_t)1 << 28)) return 1008;
-    const Plan pl = make_plan(n);
-    if (pl.c < 2 || pl.c > 22 || pl.W < 1 || pl.W > 64 || (pl.W - 1) * pl.c >= 127 || pl.W * pl.c < 128) return 1009; // planner invariant
-    if (pl.max_entries >= ((size_t)1 << 32)) return 1008;
+    const Plan single = make_plan(n);
+    if (single.c < 2 || single.c > 22 || single.W < 1 || single.W > 64 || (single.W - 1) * single.c >= 127 || single.W * single.c < 128)
+        return 1009; // planner invariant
+    if (single.max_entries * batch >= ((size_t)1 << 32) || (size_t)single.total_buckets * batch >= ((size_t)1 << 31)) return 1008;
+    Plan pl = single; // the batch as one MSM with batch * W windows
+    pl.W = single.W * (int)batch;
+    pl.total_buckets = single.total_buckets * (uint32_t)batch;
+    pl.max_entries = single.max_entries * batch;
+    pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
 
     // carve the workspace
     size_t off = 0;
@@ -635,7 +646,9 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     BBG_CHECK(bbg_rt::dev_memset(counts, 0, (o_work_count - o_counts) + 256, st));
     {
         bbg_prof::Scope prof(bbg_prof::MSM_DIGITS, st);
-        BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars, n, pl.c, pl.W, pl.NB, digits, counts);
+        for (size_t b = 0; b < batch; ++b)
+            BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars[b], n, pl.c, single.W, pl.NB,
+                              digits + b * single.max_entries, counts + b * single.total_buckets);
     }
     bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::MSM_SCAN, st);
     BBG_LAUNCH(scan_block_sums_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, spine);
@@ -668,7 +681,7 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
         BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.W), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V,
                    pl.chunks_per_window, pl.reduce_outputs - 2, red);
     }
-    g_msm_launches += 10;
+    g_msm_launches += 9 + batch;
     BBG_CHECK(bbg_rt::last_error());
 
     // ---- 7. host finish -----------------------------------------------------------------------------
@@ -677,9 +690,12 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
     BBG_CHECK(bbg_rt::sync(st));
     const auto host_t0 = std::chrono::steady_clock::now();
     const int bits = pl.reduce_outputs - 2;
-    for (int w = pl.W - 1; w >= 0; --w)
+    for (size_t b = 0; b < batch; ++b)
     {
-        const hostg1::hxyzz* rw = r.data() + (size_t)w * pl.reduce_outputs;
+    hostg1::hxyzz result = hostg1::infinity();
+    for (int w = single.W - 1; w >= 0; --w)
+    {
+        const hostg1::hxyzz* rw = r.data() + (b * (size_t)single.W + (size_t)w) * pl.reduce_outputs;
         // sum_t t * A_t = sum_r 2^r T_r   (Horner from the top bit)
         hostg1::hxyzz tsum = hostg1::infinity();
         for (int b = bits - 1; b >= 0; --b)
@@ -694,9 +710,17 @@ int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_x
         for (int i = 0; i < pl.c; ++i) result = hostg1::dbl(result);
         result = hostg1::add(result, sw);
     }
-    memcpy(out_xyzz_host, &result, sizeof result);
+    memcpy((char*)out_xyzz_host + b * sizeof result, &result, sizeof result);
+    }
     bbg_prof::add_host_ms(bbg_prof::MSM_HOST_FINISH, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
     return 0;
+}
+
+// d_out_xyzz: HOST buffer of 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sum
+int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t st)
+{
+    const void* one[1] = { d_scalars };
+    return msm_device_batched(one, 1, d_table, n, out_xyzz_host, st);
 }
 
 // points[i] = (start + i * step) * G, i < n, affine with canonical coordinates.  One thread per run of GEN_RUN

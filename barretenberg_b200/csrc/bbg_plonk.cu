@@ -27,6 +27,7 @@
 
 #include <vector>
 #ifndef BBG_EMULATE
+#include <atomic>
 #include <thread>
 #endif
 
@@ -514,15 +515,20 @@ struct Prover
     const void* d_srs = nullptr;
     bool have_witness = false, have_perm = false, have_selectors = false, tables_ready = false;
     bool sigma_ready = false; // sigma[] holds this proof's Lagrange values
+    // this proof's inputs, in the order the rounds need them: w_l, w_r, w_o, the three mappings, the five selectors
+    enum { ITEM_WL = 0, ITEM_WR, ITEM_WO, ITEM_MAP, ITEM_SEL, NUM_ITEMS };
+    const void* host_src[11] = {};
+    bool uploads_started = false;
 #ifndef BBG_EMULATE
-    // circuit constants (mappings, selectors) are uploaded by a helper thread on its own stream and staging ring while
-    // round 1 already runs on the witness; the rounds that need them wait on the events
+    // One helper thread copies all of them through its own pinned ring and stream while the rounds already run on
+    // what has arrived: uploaded (host side) / ev_item (device side) say how far it is.
     int device = 0;
     cudaStream_t upload_stream = nullptr;
-    cudaEvent_t ev_perm = nullptr, ev_sel = nullptr, ev_fence = nullptr;
+    cudaEvent_t ev_item[NUM_ITEMS] = {};
+    cudaEvent_t ev_fence = nullptr;
     bbg_hostcopy::Ring upload_ring;
     std::thread uploader;
-    int uploader_kind = 0; // 0 none, 1 mappings, 2 selectors
+    std::atomic<int> uploaded{ 0 }; // items whose copies have all been queued (event recorded)
     int upload_error = 0;
 #endif
 };
@@ -531,7 +537,6 @@ struct Prover
 static int join_uploader(Prover* p)
 {
     if (p->uploader.joinable()) p->uploader.join();
-    p->uploader_kind = 0;
     const int e = p->upload_error;
     p->upload_error = 0;
     return e;
@@ -608,8 +613,7 @@ int create(unsigned log_n, Prover** out)
 #ifndef BBG_EMULATE
     cudaGetDevice(&p->device);
     e = (int)cudaStreamCreateWithFlags(&p->upload_stream, cudaStreamNonBlocking);
-    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_perm, cudaEventDisableTiming);
-    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_sel, cudaEventDisableTiming);
+    for (int i = 0; i < Prover::NUM_ITEMS && e == 0; ++i) e = (int)cudaEventCreateWithFlags(&p->ev_item[i], cudaEventDisableTiming);
     if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_fence, cudaEventDisableTiming);
     if (e != 0)
     {
@@ -631,8 +635,8 @@ void destroy(Prover* p)
         cudaStreamSynchronize(p->upload_stream);
         cudaStreamDestroy(p->upload_stream);
     }
-    if (p->ev_perm) cudaEventDestroy(p->ev_perm);
-    if (p->ev_sel) cudaEventDestroy(p->ev_sel);
+    for (int i = 0; i < Prover::NUM_ITEMS; ++i)
+        if (p->ev_item[i]) cudaEventDestroy(p->ev_item[i]);
     if (p->ev_fence) cudaEventDestroy(p->ev_fence);
     p->upload_ring.release();
 #endif
@@ -651,73 +655,93 @@ static int ensure_tables(Prover* p, cudaStream_t st)
     return 0;
 }
 
-int set_witness(Prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o, cudaStream_t st)
+// The host buffers handed to the three set_* calls must stay valid and unmodified until bbg_plonk_round_quotient has
+// returned (they are the Prover's own polynomials / mapping vectors and the widget's selector polynomials); the copies
+// start with bbg_plonk_round_wires.
+int set_witness(Prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o, cudaStream_t)
 {
-    const uint64_t* src[3] = { w_l, w_r, w_o };
-    for (int k = 0; k < 3; ++k)
-    {
-        if (src[k] == nullptr) return 1007;
-        BBG_CHECK(bbg_hostcopy::h2d(p->w_lag + (size_t)k * p->n, src[k], p->n * 32, st));
-    }
+    if (w_l == nullptr || w_r == nullptr || w_o == nullptr) return 1007;
+    if (p->uploads_started) return 1007; // a proof is in flight
+    p->host_src[0] = w_l;
+    p->host_src[1] = w_r;
+    p->host_src[2] = w_o;
     p->have_witness = true;
     return 0;
 }
 
-// The host buffers of the next two calls must stay valid and unmodified until bbg_plonk_round_quotient has returned
-// (they are the Prover's own mapping vectors and the widget's selector polynomials).
-int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uint32_t* m3, cudaStream_t st)
+int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uint32_t* m3, cudaStream_t)
 {
-    const uint32_t* src[3] = { m1, m2, m3 };
-    for (int k = 0; k < 3; ++k)
-        if (src[k] == nullptr) return 1007;
-    p->sigma_ready = false;
-#ifndef BBG_EMULATE
-    BBG_CHECK(join_uploader(p));
-    // the previous proof's kernels may still read map[]: the copies wait for the work stream
-    BBG_CHECK(cudaEventRecord(p->ev_fence, st));
-    BBG_CHECK(cudaStreamWaitEvent(p->upload_stream, p->ev_fence, 0));
-    p->uploader_kind = 1;
-    p->uploader = std::thread([p, m1, m2, m3]() {
-        cudaSetDevice(p->device);
-        const uint32_t* s3[3] = { m1, m2, m3 };
-        int e = 0;
-        for (int k = 0; k < 3 && e == 0; ++k) e = bbg_hostcopy::h2d_ring(p->upload_ring, p->map + (size_t)k * p->n, s3[k], p->n * 4, p->upload_stream);
-        if (e == 0) e = (int)cudaEventRecord(p->ev_perm, p->upload_stream);
-        p->upload_error = e;
-    });
-#else
-    for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * p->n, src[k], p->n * 4, st));
-#endif
+    if (m1 == nullptr || m2 == nullptr || m3 == nullptr) return 1007;
+    if (p->uploads_started) return 1007;
+    p->host_src[3] = m1;
+    p->host_src[4] = m2;
+    p->host_src[5] = m3;
     p->have_perm = true;
     return 0;
 }
 
-int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t st)
+int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t)
 {
-    const uint64_t* src[5];
     for (int k = 0; k < 5; ++k)
-    {
         if (q_lagrange[k] == nullptr) return 1007;
-        src[k] = q_lagrange[k];
-    }
+    if (p->uploads_started) return 1007;
+    for (int k = 0; k < 5; ++k) p->host_src[6 + k] = q_lagrange[k];
+    p->have_selectors = true;
+    return 0;
+}
+
+// queue every input copy (helper thread; synchronous in the emulation build)
+static int start_uploads(Prover* p, cudaStream_t st)
+{
+    const size_t n = p->n;
+    p->sigma_ready = false;
+    p->uploads_started = true;
 #ifndef BBG_EMULATE
     BBG_CHECK(join_uploader(p));
+    p->uploaded.store(0);
+    // kernels of an earlier proof may still read these buffers: the copies wait for the work stream
     BBG_CHECK(cudaEventRecord(p->ev_fence, st));
     BBG_CHECK(cudaStreamWaitEvent(p->upload_stream, p->ev_fence, 0));
-    p->uploader_kind = 2;
-    const uint64_t *q0 = src[0], *q1 = src[1], *q2 = src[2], *q3 = src[3], *q4 = src[4];
-    p->uploader = std::thread([p, q0, q1, q2, q3, q4]() {
+    p->uploader = std::thread([p, n]() {
         cudaSetDevice(p->device);
-        const uint64_t* s5[5] = { q0, q1, q2, q3, q4 };
         int e = 0;
-        for (int k = 0; k < 5 && e == 0; ++k) e = bbg_hostcopy::h2d_ring(p->upload_ring, p->q + (size_t)k * p->n, s5[k], p->n * 32, p->upload_stream);
-        if (e == 0) e = (int)cudaEventRecord(p->ev_sel, p->upload_stream);
+        auto copy = [&](void* dst, const void* src, size_t bytes) {
+            if (e == 0) e = bbg_hostcopy::h2d_ring(p->upload_ring, dst, src, bytes, p->upload_stream);
+        };
+        auto done = [&](int item) {
+            if (e == 0) e = (int)cudaEventRecord(p->ev_item[item], p->upload_stream);
+            p->uploaded.store(item + 1);
+        };
+        for (int k = 0; k < 3; ++k)
+        {
+            copy(p->w_lag + (size_t)k * n, p->host_src[k], n * 32);
+            done(Prover::ITEM_WL + k);
+        }
+        for (int k = 0; k < 3; ++k) copy(p->map + (size_t)k * n, p->host_src[3 + k], n * 4);
+        done(Prover::ITEM_MAP);
+        for (int k = 0; k < 5; ++k) copy(p->q + (size_t)k * n, p->host_src[6 + k], n * 32);
+        done(Prover::ITEM_SEL);
         p->upload_error = e;
     });
 #else
-    for (int k = 0; k < 5; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * p->n, src[k], p->n * 32, st));
+    for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->w_lag + (size_t)k * n, p->host_src[k], n * 32, st));
+    for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * n, p->host_src[3 + k], n * 4, st));
+    for (int k = 0; k < 5; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * n, p->host_src[6 + k], n * 32, st));
 #endif
-    p->have_selectors = true;
+    return 0;
+}
+// make the work stream wait for input `item`
+static int wait_item(Prover* p, int item, cudaStream_t st)
+{
+#ifndef BBG_EMULATE
+    while (p->uploaded.load() <= item) std::this_thread::yield();
+    if (item == Prover::NUM_ITEMS - 1) BBG_CHECK(join_uploader(p));
+    BBG_CHECK(cudaStreamWaitEvent(st, p->ev_item[item], 0));
+#else
+    (void)p;
+    (void)item;
+    (void)st;
+#endif
     return 0;
 }
 
@@ -727,11 +751,15 @@ int set_srs(Prover* p, const void* d_table)
     return 0;
 }
 
-static int commit(Prover* p, const fe* d_scalars, uint64_t out_xyz[12], cudaStream_t st)
+// commitments to `count` polynomials of n coefficients, `stride` elements apart, in one batched MSM pipeline
+static int commit(Prover* p, const fe* d_scalars, size_t stride, int count, uint64_t* out_xyz, cudaStream_t st)
 {
-    hostg1::hxyzz r;
-    BBG_CHECK(msm_device(d_scalars, p->d_srs, p->n, &r, st));
-    hostg1::to_normalized_jacobian(r, out_xyz);
+    hostg1::hxyzz r[4];
+    const void* ptrs[4];
+    if (count < 1 || count > 4) return 1007;
+    for (int k = 0; k < count; ++k) ptrs[k] = d_scalars + (size_t)k * stride;
+    BBG_CHECK(msm_device_batched(ptrs, (size_t)count, p->d_srs, p->n, r, st));
+    for (int k = 0; k < count; ++k) hostg1::to_normalized_jacobian(r[k], out_xyz + 12 * k);
     return 0;
 }
 
@@ -742,9 +770,15 @@ int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
     if (!p->have_witness || !p->have_perm || !p->have_selectors || p->d_srs == nullptr) return 1007;
     BBG_CHECK(ensure_tables(p, st));
     const size_t n = p->n;
-    BBG_CHECK(bbg_rt::d2d(p->w_coef, p->w_lag, 3 * n * 32, st));
-    BBG_CHECK(ntt_device(p->w_coef, n, 3, p->log_n, OP_IFFT, nullptr, st));
-    for (int k = 0; k < 3; ++k) BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, out_xyz + 12 * k, st));
+    BBG_CHECK(start_uploads(p, st));
+    // wire by wire: the commitment to w_l is computed while w_r and w_o are still on the PCIe bus
+    for (int k = 0; k < 3; ++k)
+    {
+        BBG_CHECK(wait_item(p, Prover::ITEM_WL + k, st));
+        BBG_CHECK(bbg_rt::d2d(p->w_coef + (size_t)k * n, p->w_lag + (size_t)k * n, n * 32, st));
+        BBG_CHECK(ntt_device(p->w_coef + (size_t)k * n, n, 1, p->log_n, OP_IFFT, nullptr, st));
+        BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, n, 1, out_xyz + 12 * k, st));
+    }
     return bbg_rt::last_error();
 }
 
@@ -755,12 +789,8 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
     const fe beta = from_u64(beta_), gamma = from_u64(gamma_);
     fe* num = p->tmp;
     fe* den = p->tmp + n;
-#ifndef BBG_EMULATE
-    // the mappings were uploaded behind round 1; ev_perm is recorded once their helper thread has finished (a selector
-    // upload that replaced it may still be running, which is fine)
-    if (p->uploader_kind == 1) BBG_CHECK(join_uploader(p));
-    BBG_CHECK(cudaStreamWaitEvent(st, p->ev_perm, 0));
-#endif
+    if (!p->uploads_started) return 1007;
+    BBG_CHECK(wait_item(p, Prover::ITEM_MAP, st)); // the mappings arrived behind round 1
     {
         bbg_prof::Scope prof(bbg_prof::PLONK_ELEMENTWISE, st);
         // permutation.hpp:13-88 (prover.cpp:659-661)
@@ -780,7 +810,7 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
     delete prof_scan;
     g_plonk_launches += 4;
     BBG_CHECK(ntt_device(p->z, n, 1, p->log_n, OP_IFFT, nullptr, st));
-    BBG_CHECK(commit(p, p->z, out_xyz, st));
+    BBG_CHECK(commit(p, p->z, n, 1, out_xyz, st));
     return bbg_rt::last_error();
 }
 
@@ -790,11 +820,9 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
 {
     const size_t n = p->n, n2 = 2 * n, n4 = 4 * n;
     const fe beta = from_u64(beta_), gamma = from_u64(gamma_), alpha = from_u64(alpha_), alpha_base = from_u64(alpha_base_);
-    if (!p->sigma_ready) return 1007;
-#ifndef BBG_EMULATE
-    BBG_CHECK(join_uploader(p)); // the selector copy has been queued completely
-    BBG_CHECK(cudaStreamWaitEvent(st, p->ev_sel, 0));
-#endif
+    if (!p->sigma_ready || !p->uploads_started) return 1007;
+    BBG_CHECK(wait_item(p, Prover::ITEM_SEL, st)); // the selectors arrived behind rounds 1 and 2
+    p->uploads_started = false;                    // every input of this proof is on the device
     // wires on the 4n coset (prover.cpp:407-414)
     BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->w4, (const fe*)p->w_coef, (unsigned)n, (unsigned)n4, n, n4);
     BBG_CHECK(ntt_device(p->w4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
@@ -847,7 +875,7 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     BBG_CHECK(ntt_device(p->quot_large, n4, 1, p->log_n + 2, OP_COSET_IFFT, nullptr, st));
     BBG_LAUNCH_NOSYNC(add_into_kernel, dim3(grid_for(n2, 256)), dim3(256), st, p->quot_large, (const fe*)p->quot_mid, (unsigned)n2);
     g_plonk_launches += 3;
-    for (int k = 0; k < 3; ++k) BBG_CHECK(commit(p, p->quot_large + (size_t)k * n, out_xyz + 12 * k, st));
+    BBG_CHECK(commit(p, p->quot_large, n, 3, out_xyz, st));
     return bbg_rt::last_error();
 }
 
@@ -946,8 +974,7 @@ int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint6
     BBG_LAUNCH(kate_spine_kernel, dim3(2), dim3(SCAN_THREADS), 0, st, p->aggs, pts, runs, p->aggs_stride);
     BBG_LAUNCH_NOSYNC(kate_apply_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, p->tmp, (const fe*)p->aggs, pts, (unsigned)n, run, p->aggs_stride);
     g_plonk_launches += 4;
-    BBG_CHECK(commit(p, opening, out_xyz, st));
-    BBG_CHECK(commit(p, shifted, out_xyz + 12, st));
+    BBG_CHECK(commit(p, opening, n, 2, out_xyz, st)); // shifted = opening + n
     return bbg_rt::last_error();
 }
 
