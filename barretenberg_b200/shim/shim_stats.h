@@ -15,6 +15,7 @@ struct Stats
     static constexpr int MAX = 40;
     const char* name[MAX];
     double ms[MAX];
+    double min_ms[MAX];
     unsigned long calls[MAX];
     unsigned long units[MAX];
     int count = 0;
@@ -32,7 +33,8 @@ struct Stats
         double total = 0;
         for (int i = 0; i < count; ++i) total += ms[i];
         fprintf(stderr, "bbgpu shim stats: %.1f ms behind the boundary\n", total);
-        for (int i = 0; i < count; ++i) fprintf(stderr, "  %-32s calls %5lu  units %5lu  %10.2f ms\n", name[i], calls[i], units[i], ms[i]);
+        for (int i = 0; i < count; ++i)
+            fprintf(stderr, "  %-36s calls %5lu  units %5lu  total %10.2f ms  best call %9.3f ms\n", name[i], calls[i], units[i], ms[i], min_ms[i]);
         fprintf(stderr, "bbgpu kernel profile (CUDA events):\n");
         for (int i = 0; i < bbg_profile_count(); ++i)
         {
@@ -53,6 +55,7 @@ struct Stats
             if (strcmp(name[i], n) == 0)
             {
                 ms[i] += t;
+                if (t < min_ms[i]) min_ms[i] = t;
                 calls[i] += 1;
                 units[i] += u;
                 return;
@@ -62,6 +65,7 @@ struct Stats
         {
             name[count] = n;
             ms[count] = t;
+            min_ms[count] = t;
             calls[count] = 1;
             units[count] = u;
             ++count;
