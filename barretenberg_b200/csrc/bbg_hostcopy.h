@@ -11,6 +11,9 @@
 #include <string.h>
 
 #ifndef BBG_EMULATE
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -20,6 +23,82 @@ constexpr size_t CHUNK = (size_t)8 << 20;
 constexpr int RING = 4;
 constexpr size_t SMALL = (size_t)1 << 20; // below this the plain path is as good
 
+// memcpy split over a few threads (a single core does not saturate even one PCIe direction).  The workers are
+// persistent: creating and joining threads per 8 MiB chunk cost about as much as the copy itself.
+class CopyPool
+{
+  public:
+    explicit CopyPool(int workers) : stop_(false), generation_(0), pending_(0)
+    {
+        for (int i = 0; i < workers; ++i) threads_.emplace_back([this, i]() { run(i); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int workers() const { return (int)threads_.size(); }
+    // copies [0, bytes) with the calling thread taking one slice; returns when every slice is done
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        const int parts = workers() + 1;
+        const size_t part = (((bytes + parts - 1) / parts) + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            dst_ = (char*)dst;
+            src_ = (const char*)src;
+            bytes_ = bytes;
+            part_ = part;
+            pending_ = workers();
+            ++generation_;
+        }
+        cv_.notify_all();
+        slice(workers()); // the caller's share: the last slice
+        std::unique_lock<std::mutex> lock(m_);
+        done_.wait(lock, [this]() { return pending_ == 0; });
+    }
+
+  private:
+    void slice(int idx)
+    {
+        const size_t off = (size_t)idx * part_;
+        if (off >= bytes_) return;
+        const size_t len = bytes_ - off < part_ ? bytes_ - off : part_;
+        memcpy(dst_ + off, src_ + off, len);
+    }
+    void run(int idx)
+    {
+        unsigned long seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&]() { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            slice(idx);
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    bool stop_;
+    unsigned long generation_;
+    int pending_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0, part_ = 0;
+};
+
 struct Ring
 {
     void* buf[RING] = {};
@@ -27,6 +106,7 @@ struct Ring
     bool ready = false;
     int threads = 1;
     unsigned next = 0; // slots rotate across calls, so a short copy never waits for the previous call's chunk
+    std::unique_ptr<CopyPool> pool; // one pool per ring: each ring belongs to one copying thread
     int init()
     {
         if (ready) return 0;
@@ -39,8 +119,14 @@ struct Ring
         }
         unsigned hc = std::thread::hardware_concurrency();
         threads = hc >= 16 ? 8 : (hc >= 8 ? 4 : (hc >= 4 ? 2 : 1));
+        if (threads > 1) pool.reset(new CopyPool(threads - 1));
         ready = true;
         return 0;
+    }
+    void parallel_memcpy(void* dst, const void* src, size_t bytes)
+    {
+        if (!pool || bytes < ((size_t)1 << 20)) memcpy(dst, src, bytes);
+        else pool->copy(dst, src, bytes);
     }
     void release()
     {
@@ -51,6 +137,7 @@ struct Ring
             buf[i] = nullptr;
             ev[i] = nullptr;
         }
+        pool.reset();
         ready = false;
     }
 };
@@ -71,27 +158,6 @@ inline bool is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// memcpy split over a few threads (a single core does not saturate even one PCIe direction)
-inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads)
-{
-    if (threads <= 1 || bytes < ((size_t)1 << 20))
-    {
-        memcpy(dst, src, bytes);
-        return;
-    }
-    std::vector<std::thread> pool;
-    const size_t part = ((bytes / threads) + 4095) & ~(size_t)4095;
-    for (int t = 1; t < threads; ++t)
-    {
-        const size_t off = (size_t)t * part;
-        if (off >= bytes) break;
-        const size_t len = bytes - off < part ? bytes - off : part;
-        pool.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, len); });
-    }
-    memcpy(dst, src, part < bytes ? part : bytes);
-    for (auto& th : pool) th.join();
-}
-
 // `r`: the pinned staging ring to use (one per host thread that copies; the default ring belongs to the caller's thread)
 inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t st)
 {
@@ -103,7 +169,7 @@ inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t 
         const int i = (int)(r.next++ % RING);
         const size_t len = bytes - off < CHUNK ? bytes - off : CHUNK;
         BBG_CHECK(cudaEventSynchronize(r.ev[i])); // chunk i is off the wire (an unrecorded event is complete)
-        parallel_memcpy(r.buf[i], (const char*)h + off, len, r.threads);
+        r.parallel_memcpy(r.buf[i], (const char*)h + off, len);
         BBG_CHECK(cudaMemcpyAsync((char*)d + off, r.buf[i], len, cudaMemcpyHostToDevice, st));
         BBG_CHECK(cudaEventRecord(r.ev[i], st));
         off += len;
@@ -134,7 +200,7 @@ inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st)
             const int i = (int)(j % RING);
             const size_t off = j * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
             BBG_CHECK(cudaEventSynchronize(r.ev[i]));
-            parallel_memcpy((char*)h + off, r.buf[i], len, r.threads);
+            r.parallel_memcpy((char*)h + off, r.buf[i], len);
         }
     }
     return 0;

@@ -47,6 +47,17 @@ __device__ __noinline__ fe fr_mul_shared(const fe a, const fe b) { return Fr::mu
 #else
 #define NTT_MUL(a, b) Fr::mul((a), (b))
 #endif
+// BBG_NTT_ABLATE (development only, never set in the product build; results are WRONG): time the pass kernels with one
+// ingredient removed to see what the multiply pipe is waiting for.  1: no CTA barriers  2: no shared-memory exchange
+// 3: additions / subtractions without the modular correction  4: twiddles not loaded (constant)  5: no global traffic
+#ifndef BBG_NTT_ABLATE
+#define BBG_NTT_ABLATE 0
+#endif
+#if BBG_NTT_ABLATE == 1 || BBG_NTT_ABLATE == 2
+#define NTT_SYNC() ((void)0)
+#else
+#define NTT_SYNC() __syncthreads()
+#endif
 BBG_HD int pad(int q) { return q + (q >> 5); }          // twiddle planes: power-of-two strides
 // data planes: XOR swizzle of the bank bits with tile-slot bits 3..7.  A bijection on [0, TILE) that makes every
 // access pattern of every radix step conflict-free (checked exhaustively for all sub-transform lengths and both
@@ -69,12 +80,30 @@ BBG_D fe sm_load(const uint32_t* data, int q)
 }
 BBG_D fe tw_load(const uint32_t* tw, int e)
 {
+#if BBG_NTT_ABLATE == 4
+    fe r;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) r.v[l] = 0x1234567u * (l + 1) + (e & 1);
+    return r;
+#else
     const int p = pad(e);
     fe r;
 #pragma unroll
     for (int l = 0; l < 8; ++l) r.v[l] = tw[l * TWP + p];
     return r;
+#endif
 }
+#if BBG_NTT_ABLATE == 3
+BBG_D fe abl_add(const fe& a, const fe& b) { fe r; cc::add8(r.v, a.v, b.v); return r; }
+BBG_D fe abl_sub(const fe& a, const fe& b) { fe r; cc::sub8(r.v, a.v, b.v); return r; }
+#define NTT_ADD(a, b) abl_add((a), (b))
+#define NTT_SUB(a, b) abl_sub((a), (b))
+#define NTT_SUB_LAZY(a, b) abl_sub((a), (b))
+#else
+#define NTT_ADD(a, b) Fr::add((a), (b))
+#define NTT_SUB(a, b) Fr::sub((a), (b))
+#define NTT_SUB_LAZY(a, b) Fr::sub_lazy((a), (b))
+#endif
 
 struct PassParams
 {
@@ -107,16 +136,16 @@ template <int L, int B, int R> BBG_D void radix_step(fe (&x)[8], int base_low, c
             const int jm = m & (half - 1);
             const fe u = x[m];
             const fe v = x[m | half];
-            x[m] = Fr::add(u, v);
+            x[m] = NTT_ADD(u, v);
             if (B == 0 && jm == 0)
             {
-                x[m | half] = Fr::sub(u, v); // twiddle w^0
+                x[m | half] = NTT_SUB(u, v); // twiddle w^0
             }
             else
             {
                 // the sub-transform twiddles are canonical (< p), so the difference may stay in (0, 4p)
                 const int e = (base_low | (jm << B)) << (L - 1 - s);
-                x[m | half] = NTT_MUL(Fr::sub_lazy(u, v), tw_load(tw, e));
+                x[m | half] = NTT_MUL(NTT_SUB_LAZY(u, v), tw_load(tw, e));
             }
         }
     }
@@ -152,14 +181,21 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             size_t g;
             if (COLS_LOW) g = ((size_t)k << rest) + ((size_t)tile << TM::CLOG) + c;
             else g = ((((size_t)tile << TM::CLOG) + c) << L) + k;
+#if BBG_NTT_ABLATE == 5
+            x[m] = Fr::zero();
+            x[m].v[0] = (uint32_t)g;
+#else
             x[m] = load_fe(src + g);
+#endif
             if (COLS_LOW && p.vec != nullptr) x[m] = NTT_MUL(x[m], load_fe(p.vec + k));
         }
     }
     else
     {
+#if BBG_NTT_ABLATE != 2
 #pragma unroll
         for (int m = 0; m < 8; ++m) x[m] = sm_load(data, TM::template slot<B>(t, m));
+#endif
     }
     {
         const int q0 = TM::template slot<B>(t, 0);
@@ -177,7 +213,12 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             if (COLS_LOW)
             {
                 const size_t o = ((size_t)isub << rest) + ((size_t)tile << TM::CLOG) + c;
+#if BBG_NTT_ABLATE == 5
+                const fe y5 = NTT_MUL(x[m], x[(m + 1) & 7]);
+                if (y5.v[0] == 0x12345u && y5.v[7] == 0x777u) store_fe(dst + o, y5);
+#else
                 store_fe(dst + o, NTT_MUL(x[m], load_fe(p.mat + o)));
+#endif
             }
             else
             {
@@ -186,16 +227,21 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
                 fe y = x[m];
                 if (p.vec != nullptr) y = NTT_MUL(y, load_fe(p.vec + isub));
                 if (p.has_post_const) y = NTT_MUL(y, p.post_const);
+#if BBG_NTT_ABLATE == 5
+                if (y.v[0] == 0x12345u && y.v[7] == 0x777u)
+#endif
                 store_fe(dst + o, Fr::reduce(y));
             }
         }
     }
     else
     {
-        if (!FIRST) __syncthreads(); // everyone has read its inputs of this step
+        if (!FIRST) NTT_SYNC(); // everyone has read its inputs of this step
+#if BBG_NTT_ABLATE != 2
 #pragma unroll
         for (int m = 0; m < 8; ++m) sm_store(data, TM::template slot<B>(t, m), x[m]);
-        __syncthreads();
+#endif
+        NTT_SYNC();
     }
 }
 
@@ -227,7 +273,7 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT, 2) ntt_pas
         const size_t b = (size_t)(work / p.num_tiles);
         fe x[8];
         run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.dst + b * p.batch_stride, tile, data, tw);
-        __syncthreads(); // the last step's shared-memory reads finish before the next tile overwrites
+        NTT_SYNC(); // the last step's shared-memory reads finish before the next tile overwrites
     }
 }
 

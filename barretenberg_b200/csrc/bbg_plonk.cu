@@ -25,6 +25,9 @@
 #include "bbg_hostcopy.h"
 #include "bbg_plonk.h"
 
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 #ifndef BBG_EMULATE
 #include <atomic>
@@ -445,19 +448,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) kate_spine_kernel(fe* aggs_all, 
         carry = Fr::add(c, Fr::mul(carry, M));
     }
 }
-__global__ void kate_apply_kernel(fe* data, const fe* aggs, KatePoints pts, unsigned n, unsigned run, unsigned aggs_stride)
+// out of place (in place the loads cannot be hoisted above the stores and every thread walks its run at memory latency)
+__global__ void kate_apply_kernel(fe* __restrict__ out, const fe* __restrict__ in, const fe* __restrict__ aggs, KatePoints pts, unsigned n, unsigned run,
+                                  unsigned aggs_stride)
 {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned first = k * run;
     if (first >= n) return;
-    fe* f = data + (size_t)blockIdx.y * n;
+    const fe* f = in + (size_t)blockIdx.y * n;
+    fe* w = out + (size_t)blockIdx.y * n;
     const fe z = pts.z[blockIdx.y];
     fe carry = load_fe(aggs + (size_t)blockIdx.y * aggs_stride + k);
     const unsigned last = (first + run < n) ? first + run : n;
-    for (unsigned j = last; j > first; --j)
+    unsigned j = last;
+    for (; j >= first + 4; j -= 4)
+    {
+        const fe c0 = load_fe(f + j - 1), c1 = load_fe(f + j - 2), c2 = load_fe(f + j - 3), c3 = load_fe(f + j - 4);
+        store_fe(w + j - 1, carry);
+        carry = Fr::add(c0, Fr::mul(carry, z));
+        store_fe(w + j - 2, carry);
+        carry = Fr::add(c1, Fr::mul(carry, z));
+        store_fe(w + j - 3, carry);
+        carry = Fr::add(c2, Fr::mul(carry, z));
+        store_fe(w + j - 4, carry);
+        carry = Fr::add(c3, Fr::mul(carry, z));
+    }
+    for (; j > first; --j)
     {
         const fe c = load_fe(f + j - 1);
-        store_fe(f + j - 1, carry);
+        store_fe(w + j - 1, carry);
         carry = Fr::add(c, Fr::mul(carry, z));
     }
 }
@@ -515,6 +534,7 @@ struct Prover
     const void* d_srs = nullptr;
     bool have_witness = false, have_perm = false, have_selectors = false, tables_ready = false;
     bool sigma_ready = false; // sigma[] holds this proof's Lagrange values
+    bool l1_ready = false;    // l1[] depends on the circuit size only: computed once
     // this proof's inputs, in the order the rounds need them: w_l, w_r, w_o, the three mappings, the five selectors
     enum { ITEM_WL = 0, ITEM_WR, ITEM_WO, ITEM_MAP, ITEM_SEL, NUM_ITEMS };
     const void* host_src[11] = {};
@@ -765,8 +785,23 @@ static int commit(Prover* p, const fe* d_scalars, size_t stride, int count, uint
 
 // prover.cpp:126-135 compute_wire_coefficients + :65-89 compute_wire_commitments (and, off the critical path of the
 // transcript, permutation.hpp's sigma polynomials)
+// BBG_PLONK_TRACE=1: host-side timeline of the rounds on stderr (development aid)
+struct Trace
+{
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("BBG_PLONK_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, cudaStream_t st)
+    {
+        if (!on) return;
+        bbg_rt::sync(st);
+        fprintf(stderr, "  [plonk trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
 {
+    Trace tr;
     if (!p->have_witness || !p->have_perm || !p->have_selectors || p->d_srs == nullptr) return 1007;
     BBG_CHECK(ensure_tables(p, st));
     const size_t n = p->n;
@@ -775,9 +810,12 @@ int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
     for (int k = 0; k < 3; ++k)
     {
         BBG_CHECK(wait_item(p, Prover::ITEM_WL + k, st));
+        tr.mark("wire uploaded", st);
         BBG_CHECK(bbg_rt::d2d(p->w_coef + (size_t)k * n, p->w_lag + (size_t)k * n, n * 32, st));
         BBG_CHECK(ntt_device(p->w_coef + (size_t)k * n, n, 1, p->log_n, OP_IFFT, nullptr, st));
+        tr.mark("wire ifft", st);
         BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, n, 1, out_xyz + 12 * k, st));
+        tr.mark("wire commitment", st);
     }
     return bbg_rt::last_error();
 }
@@ -820,28 +858,34 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
 {
     const size_t n = p->n, n2 = 2 * n, n4 = 4 * n;
     const fe beta = from_u64(beta_), gamma = from_u64(gamma_), alpha = from_u64(alpha_), alpha_base = from_u64(alpha_base_);
+    Trace tr;
     if (!p->sigma_ready || !p->uploads_started) return 1007;
     BBG_CHECK(wait_item(p, Prover::ITEM_SEL, st)); // the selectors arrived behind rounds 1 and 2
     p->uploads_started = false;                    // every input of this proof is on the device
     // wires on the 4n coset (prover.cpp:407-414)
     BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->w4, (const fe*)p->w_coef, (unsigned)n, (unsigned)n4, n, n4);
     BBG_CHECK(ntt_device(p->w4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
+    tr.mark("w4 coset_fft", st);
     // sigma: Lagrange -> beta-scaled coefficients (:246-248), then beta sigma + w + gamma on the 4n coset (:252-273)
     BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT_WITH_CONSTANT, beta_, st));
     BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, gamma, (unsigned)n,
                       (unsigned)n4);
     BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
+    tr.mark("sigma ifft + s4 coset_fft", st);
     // alpha Z on the 4n coset (:275)
     BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 1), dim3(256), st, p->z4, (const fe*)p->z, (unsigned)n, (unsigned)n4, n, n4);
     BBG_CHECK(ntt_device(p->z4, n4, 1, p->log_n + 2, OP_COSET_FFT_WITH_CONSTANT, alpha_, st));
     // L_1 on the 2n coset (:349-351)
-    BBG_CHECK(lagrange_fft_device(p->l1, p->log_n, p->log_n + 1, st));
+    if (!p->l1_ready) BBG_CHECK(lagrange_fft_device(p->l1, p->log_n, p->log_n + 1, st));
+    p->l1_ready = true;
+    tr.mark("z4 + l1", st);
     // selectors: Lagrange -> coefficients -> alpha_base-scaled 2n coset evaluations (arithmetic_widget.cpp:62-78)
     BBG_CHECK(ntt_device(p->q, n, 5, p->log_n, OP_IFFT, nullptr, st));
     BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n2, 256), 5), dim3(256), st, p->q2, (const fe*)p->q, (unsigned)n, (unsigned)n2, n, n2);
     BBG_CHECK(ntt_device(p->q2, n2, 5, p->log_n + 1, OP_COSET_FFT_WITH_CONSTANT, alpha_base_, st));
     g_plonk_launches += 4;
 
+    tr.mark("selectors ifft + coset_fft", st);
     QuotientConsts c;
     c.g = gen_k1();
     c.beta = beta;
@@ -871,11 +915,14 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     fill_vinv(1);
     BBG_LAUNCH_NOSYNC(quotient_mid_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->z4, (const fe*)p->l1, (const fe*)p->w4,
                       (const fe*)p->q2, p->pow_mid, c, (unsigned)n2);
+    tr.mark("quotient kernels", st);
     BBG_CHECK(ntt_device(p->quot_mid, n2, 1, p->log_n + 1, OP_COSET_IFFT, nullptr, st));
     BBG_CHECK(ntt_device(p->quot_large, n4, 1, p->log_n + 2, OP_COSET_IFFT, nullptr, st));
     BBG_LAUNCH_NOSYNC(add_into_kernel, dim3(grid_for(n2, 256)), dim3(256), st, p->quot_large, (const fe*)p->quot_mid, (unsigned)n2);
     g_plonk_launches += 3;
+    tr.mark("coset_ifft x2 + add", st);
     BBG_CHECK(commit(p, p->quot_large, n, 3, out_xyz, st));
+    tr.mark("3 commitments", st);
     return bbg_rt::last_error();
 }
 
@@ -972,9 +1019,11 @@ int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint6
     }
     BBG_LAUNCH_NOSYNC(kate_reduce_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, (const fe*)p->tmp, p->aggs, pts, (unsigned)n, run, p->aggs_stride);
     BBG_LAUNCH(kate_spine_kernel, dim3(2), dim3(SCAN_THREADS), 0, st, p->aggs, pts, runs, p->aggs_stride);
-    BBG_LAUNCH_NOSYNC(kate_apply_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, p->tmp, (const fe*)p->aggs, pts, (unsigned)n, run, p->aggs_stride);
+    fe* quotients = p->s4; // free since the quotient round; 2 x n
+    BBG_LAUNCH_NOSYNC(kate_apply_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, quotients, (const fe*)p->tmp, (const fe*)p->aggs, pts, (unsigned)n, run,
+                      p->aggs_stride);
     g_plonk_launches += 4;
-    BBG_CHECK(commit(p, opening, n, 2, out_xyz, st)); // shifted = opening + n
+    BBG_CHECK(commit(p, quotients, n, 2, out_xyz, st));
     return bbg_rt::last_error();
 }
 

@@ -72,6 +72,24 @@ int main(int argc, char** argv)
     const size_t log_gates = argc > 1 ? strtoull(argv[1], nullptr, 10) : 12;
     const int repeat = argc > 2 ? atoi(argv[2]) : 1;
     const size_t num_gates = (size_t)1 << log_gates;
+    {
+        // the reference's transcript reader does not check the file size (io.hpp:157-182): refuse to run into a short SRS
+        FILE* f = fopen(BARRETENBERG_SRS_PATH, "rb");
+        long have = 0;
+        if (f != nullptr)
+        {
+            fseek(f, 0, SEEK_END);
+            have = ftell(f);
+            fclose(f);
+        }
+        const long need = 28 + 64 * (long)(num_gates - 1) + 256;
+        if (have < need)
+        {
+            fprintf(stderr, "prover_harness: %s holds %ld bytes, %ld needed for 2^%zu gates (run build/make_srs %zu %s)\n", BARRETENBERG_SRS_PATH, have, need,
+                    log_gates, num_gates, BARRETENBERG_SRS_PATH);
+            return 2;
+        }
+    }
 
     auto t0 = std::chrono::steady_clock::now();
     waffle::StandardComposer composer = waffle::StandardComposer(num_gates);
