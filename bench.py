@@ -199,6 +199,44 @@ class ReferenceCpu:
                 "scaled x%d; OMP threads = %d" % (self.log_n, BATCH, self.log_n, self.log_n + 2, BATCH, self.threads))
 
 
+def prove_leg(log_gates, with_cpu):
+    """BASELINE configs[4] next to the step metric: the reference's waffle StandardComposer prover, prebuilt by
+    tests/cpp/Makefile (build/ travels to the GPU box), once with Prover::construct_proof on the GPU (HBM-resident rounds)
+    and once all-CPU; proofs compared field for field.  Returns None when the binaries are not there."""
+    import subprocess
+
+    b = os.path.join(ROOT, "build")
+    need = [os.path.join(b, f) for f in ("make_srs", "prover_gpu") + (("prover_cpu",) if with_cpu else ())]
+    if not all(os.path.exists(f) for f in need):
+        return None
+    srs = os.path.join(b, "srs", "transcript.dat")
+    os.makedirs(os.path.dirname(srs), exist_ok=True)
+    n = 1 << log_gates
+    if not os.path.exists(srs) or os.path.getsize(srs) < 28 + 64 * (n - 1) + 256 + 64:
+        subprocess.run([need[0], str(n), srs], cwd=ROOT, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    env = dict(os.environ)
+    threads = 1
+    while threads * 2 <= (os.cpu_count() or 1):
+        threads *= 2
+    env["OMP_NUM_THREADS"] = str(threads)
+
+    def run(binary, repeat):
+        out = subprocess.run([os.path.join(b, binary), str(log_gates), str(repeat)], cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+        if out.returncode != 0:
+            raise RuntimeError("%s failed: %s" % (binary, (out.stderr or out.stdout)[-300:]))
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    gpu = run("prover_gpu", 5)
+    res = {"workload": "configs[4]: waffle StandardComposer prove, n = 2^%d (bench_plonk.cpp:25-37 circuit, seeded witnesses, synthetic SRS)" % log_gates,
+           "gpu_prove_ms": gpu["prove_ms_best"], "gpu_prove_ms_first": gpu["prove_ms_first"], "gpu_verified": gpu["verified"],
+           "path": "Prover::construct_proof -> shim/prover_gpu.cpp -> bbg_plonk_* (witness, mappings and selectors uploaded from pageable host memory every proof)"}
+    if with_cpu:
+        cpu = run("prover_cpu", 1)
+        res.update({"cpu_reference_prove_ms": cpu["prove_ms_best"], "cpu_threads": threads, "cpu_verified": cpu["verified"],
+                    "proofs_identical": all(cpu["proof"][k] == gpu["proof"][k] for k in cpu["proof"])})
+    return res
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -487,6 +525,13 @@ def run_b200(args, rank, local_rank, world):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if world == 1 and not args.no_prove:
+            try:
+                prove = prove_leg(log_n, with_cpu=not args.no_cpu_baseline)
+            except Exception as e:  # noqa: BLE001
+                prove = {"unavailable": str(e).splitlines()[0][:200]}
+            if prove is not None:
+                line["prove"] = prove
         print(json.dumps(line))
     barrier()
     if world > 1:
@@ -501,6 +546,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="log2 of the MSM / NTT size (BASELINE: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prove", action="store_true", help="skip the full-prover leg (BASELINE configs[4])")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e, microbench and CPU-baseline legs (short runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
