@@ -543,14 +543,19 @@ int bbg_plonk_set_permutation(bbg_plonk_prover* p, const uint32_t* sigma_1_mappi
     if (p == nullptr) return BBG_E_BAD_ARGUMENT;
     return plonk::set_permutation((plonk::Prover*)p, sigma_1_mapping, sigma_2_mapping, sigma_3_mapping, g_stream);
 }
-int bbg_plonk_set_arithmetic_selectors(bbg_plonk_prover* p, const uint64_t* q_m, const uint64_t* q_l, const uint64_t* q_r, const uint64_t* q_o,
-                                       const uint64_t* q_c)
+int bbg_plonk_set_widgets(bbg_plonk_prover* p, const int* kinds, int count, const uint64_t* const* selectors)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     BBG_CHECK(ensure_ready());
     if (p == nullptr) return BBG_E_BAD_ARGUMENT;
+    return plonk::set_widgets((plonk::Prover*)p, kinds, count, selectors, g_stream);
+}
+int bbg_plonk_set_arithmetic_selectors(bbg_plonk_prover* p, const uint64_t* q_m, const uint64_t* q_l, const uint64_t* q_r, const uint64_t* q_o,
+                                       const uint64_t* q_c)
+{
+    const int kind = BBG_WIDGET_ARITHMETIC;
     const uint64_t* q[5] = { q_m, q_l, q_r, q_o, q_c };
-    return plonk::set_arithmetic_selectors((plonk::Prover*)p, q, g_stream);
+    return bbg_plonk_set_widgets(p, &kind, 1, q);
 }
 int bbg_plonk_set_srs(bbg_plonk_prover* p, const uint64_t* points_table, size_t n)
 {
@@ -598,13 +603,14 @@ int bbg_plonk_round_linearise(bbg_plonk_prover* p, const uint64_t* scalars, cons
     return plonk::round_linearise((plonk::Prover*)p, scalars, zeta, out_linear_eval, g_stream);
 }
 int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, const uint64_t beta_inv[4], const uint64_t zeta[4],
-                             const uint64_t zeta_omega[4], uint64_t* out_xyz)
+                             const uint64_t zeta_omega[4], const uint64_t* wire_shift_terms, const uint64_t* selector_terms, uint64_t* out_xyz)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     BBG_CHECK(ensure_ready());
-    if (p == nullptr || nu_powers == nullptr || beta_inv == nullptr || zeta == nullptr || zeta_omega == nullptr || out_xyz == nullptr)
+    if (p == nullptr || nu_powers == nullptr || beta_inv == nullptr || zeta == nullptr || zeta_omega == nullptr || wire_shift_terms == nullptr ||
+        selector_terms == nullptr || out_xyz == nullptr)
         return BBG_E_BAD_ARGUMENT;
-    return plonk::round_openings((plonk::Prover*)p, nu_powers, beta_inv, zeta, zeta_omega, out_xyz, g_stream);
+    return plonk::round_openings((plonk::Prover*)p, nu_powers, beta_inv, zeta, zeta_omega, wire_shift_terms, selector_terms, out_xyz, g_stream);
 }
 
 // ---- device memory helpers ------------------------------------------------------------------------

@@ -18,7 +18,7 @@
 // Layout in HBM for a circuit of n = 2^k gates (field element = 32 B; n = 2^20 -> 2.3 GB in total):
 //   w_lag[3][n]  witness, Lagrange form          w_coef[3][n]   coefficient form       w4[3][4n]  coset evaluations
 //   sigma[3][n]  permutation polys (Lagrange -> beta-scaled coefficients in place)     s4[3][4n]
-//   z[n], z4[4n] grand product                   q[5][n], q2[5][2n]  selectors         l1[2n]
+//   z[n], z4[4n] grand product                   q[11][n], q2[9][2n], q4[2][4n]  selectors (all four widget kinds)   l1[2n]
 //   quot_large[4n], quot_mid[2n], r[n], tmp[2][n] (scan inputs / opening polynomials)
 #include "bbg_internal.h"
 #include "bbg_host_g1.h"
@@ -229,7 +229,7 @@ struct QuotientConsts
 // Z_H*(X) on the large domain), one pass:
 //   q[i] = ( (w_l + b x + c)(w_r + b k1 x + c)(w_o + b k2 x + c) aZ(x)  -  s1 s2 s3 aZ(x w) ) (x - w^(n-1)) / (x^n - 1),
 //   x = g w_4n^i
-__global__ void quotient_large_kernel(fe* q, const fe* s4, const fe* w4, const fe* z4, PowTable large, QuotientConsts c, unsigned n4)
+template <bool DIVIDE> __global__ void quotient_large_kernel(fe* q, const fe* s4, const fe* w4, const fe* z4, PowTable large, QuotientConsts c, unsigned n4)
 {
     const unsigned mask = n4 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
@@ -243,8 +243,12 @@ __global__ void quotient_large_kernel(fe* q, const fe* s4, const fe* w4, const f
         fe pm = Fr::mul(load_fe(s4 + i), load_fe(s4 + (size_t)n4 + i));
         pm = Fr::mul(pm, load_fe(s4 + 2 * (size_t)n4 + i));
         pm = Fr::mul(pm, load_fe(z4 + ((i + 4) & mask)));
-        fe v = Fr::mul(Fr::sub(id, pm), c.vinv[i & 3]);
-        v = Fr::mul(v, Fr::add(Fr::mul(root, c.g), c.neg_root_inv));
+        fe v = Fr::sub(id, pm);
+        if (DIVIDE)
+        {
+            v = Fr::mul(v, c.vinv[i & 3]);
+            v = Fr::mul(v, Fr::add(Fr::mul(root, c.g), c.neg_root_inv));
+        }
         store_fe(q + i, v);
     }
 }
@@ -275,6 +279,100 @@ __global__ void quotient_mid_kernel(fe* q, const fe* z4, const fe* l1, const fe*
     }
 }
 
+// ---- widget mixes other than the standard composer's: the same sums, one widget at a time -------------------------
+// the two L_1 boundary terms only (prover.cpp:325-391), undivided
+__global__ void quotient_mid_base_kernel(fe* q, const fe* z4, const fe* l1, QuotientConsts c, unsigned n2)
+{
+    const unsigned n4 = 2 * n2, mask2 = n2 - 1, mask4 = n4 - 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+    {
+        fe t6 = Fr::sub(load_fe(z4 + ((2 * i + 4) & mask4)), c.alpha);
+        t6 = Fr::mul(Fr::mul(t6, c.alpha), load_fe(l1 + ((i + 4) & mask2)));
+        fe t4 = Fr::sub(load_fe(z4 + 2 * i), c.alpha);
+        t4 = Fr::mul(Fr::mul(t4, c.alpha_sqr), load_fe(l1 + i));
+        store_fe(q + i, Fr::add(t4, t6));
+    }
+}
+// arithmetic_widget.cpp:80-97
+__global__ void arith_mid_add_kernel(fe* q, const fe* w4, const fe* q2, unsigned n2)
+{
+    const unsigned n4 = 2 * n2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+    {
+        const fe wl = load_fe(w4 + 2 * i), wr = load_fe(w4 + (size_t)n4 + 2 * i), wo = load_fe(w4 + 2 * (size_t)n4 + 2 * i);
+        fe a = Fr::mul(Fr::mul(wl, load_fe(q2 + i)), wr);
+        a = Fr::add(a, Fr::mul(wl, load_fe(q2 + (size_t)n2 + i)));
+        fe b = Fr::mul(wr, load_fe(q2 + 2 * (size_t)n2 + i));
+        b = Fr::add(b, Fr::mul(wo, load_fe(q2 + 3 * (size_t)n2 + i)));
+        a = Fr::add(Fr::add(a, b), load_fe(q2 + 4 * (size_t)n2 + i));
+        store_fe(q + i, Fr::add(load_fe(q + i), a));
+    }
+}
+// bool_widget.cpp:76-97: (w^2 - w) q_b for the three wires (the alpha powers ride on the selector transforms)
+__global__ void bool_mid_add_kernel(fe* q, const fe* w4, const fe* q2, unsigned n2)
+{
+    const unsigned n4 = 2 * n2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+    {
+        fe acc = load_fe(q + i);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const fe w = load_fe(w4 + (size_t)k * n4 + 2 * i);
+            acc = Fr::add(acc, Fr::mul(Fr::sub(Fr::sqr(w), w), load_fe(q2 + (size_t)k * n2 + i)));
+        }
+        store_fe(q + i, acc);
+    }
+}
+// sequential_widget.cpp:56-59: w_o(X w) q_o_next
+__global__ void seq_mid_add_kernel(fe* q, const fe* wo4, const fe* q2, unsigned n2)
+{
+    const unsigned mask4 = 2 * n2 - 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(load_fe(wo4 + ((2 * i + 4) & mask4)), load_fe(q2 + i))));
+}
+// mimc_widget.cpp:68-86 on the large domain: T0 = w_o + w_l + q_c;  ((T0^3 - w_r) + (w_r^2 T0 - w_o(X w)) alpha) q_mimc
+__global__ void mimc_large_add_kernel(fe* q, const fe* w4, const fe* q4, fe alpha, unsigned n4)
+{
+    const unsigned mask = n4 - 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    {
+        const fe wl = load_fe(w4 + i), wr = load_fe(w4 + (size_t)n4 + i), wo = load_fe(w4 + 2 * (size_t)n4 + i);
+        const fe t0 = Fr::add(Fr::add(wo, wl), load_fe(q4 + (size_t)n4 + i));
+        fe t1 = Fr::sub(Fr::mul(Fr::sqr(t0), t0), wr);
+        fe t2 = Fr::sub(Fr::mul(Fr::sqr(wr), t0), load_fe(w4 + 2 * (size_t)n4 + ((i + 4) & mask)));
+        t1 = Fr::add(t1, Fr::mul(t2, alpha));
+        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(t1, load_fe(q4 + i))));
+    }
+}
+// polynomial_arithmetic.cpp:478-560 on its own: v[i] *= (g w^i - w_n^(n-1)) / ((g w^i)^n - 1)
+__global__ void divide_vanishing_kernel(fe* v, PowTable table, QuotientConsts c, unsigned s_mask, unsigned count)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        fe x = Fr::mul(load_fe(v + i), c.vinv[i & s_mask]);
+        x = Fr::mul(x, Fr::add(Fr::mul(root_pow(table, i), c.g), c.neg_root_inv));
+        store_fe(v + i, x);
+    }
+}
+// dst[i] (+)= sum_j c_j src_j[i]
+constexpr int MAX_TERMS = 12;
+struct LinTerms
+{
+    const fe* src[MAX_TERMS];
+    fe c[MAX_TERMS];
+    int count;
+};
+template <bool ACCUMULATE> __global__ void axpy_terms_kernel(fe* dst, LinTerms t, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        fe acc = ACCUMULATE ? load_fe(dst + i) : Fr::zero();
+        for (int j = 0; j < t.count; ++j) acc = Fr::add(acc, Fr::mul(load_fe(t.src[j] + i), t.c[j]));
+        store_fe(dst + i, acc);
+    }
+}
+
 // a[i] += b[i]
 __global__ void add_into_kernel(fe* a, const fe* b, unsigned count)
 {
@@ -286,7 +384,7 @@ __global__ void add_into_kernel(fe* a, const fe* b, unsigned count)
 constexpr int EVAL_THREADS = 256;
 constexpr int EVAL_RUN = 16;
 constexpr int EVAL_SPAN = EVAL_THREADS * EVAL_RUN;
-constexpr int MAX_EVAL_JOBS = 8;
+constexpr int MAX_EVAL_JOBS = 12;
 struct EvalJobs
 {
     const fe* poly[MAX_EVAL_JOBS];
@@ -346,24 +444,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) eval_final_kernel(EvalJobs jobs,
     }
     const fe r = block_horner_reduce(acc, Fr::pow_u64(step, per), sh);
     if (t == 0) store_fe(out + job, Fr::reduce(r));
-}
-
-// prover.cpp:479-493 + arithmetic_widget.cpp:99-122: r[i] = c_z z[i] + c_s3 sigma_3[i] + (wlr qm + wl ql + wr qr + wo qo + qc) a
-struct LinearConsts
-{
-    fe c_z, c_sigma3; // linear_terms.z_1 ; linear_terms.sigma_3 * beta^-1
-    fe w_lr, w_l, w_r, w_o, alpha_base;
-};
-__global__ void linearise_kernel(fe* r, const fe* z, const fe* sigma3, const fe* q, LinearConsts c, unsigned n)
-{
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        fe v = Fr::add(Fr::mul(load_fe(z + i), c.c_z), Fr::mul(load_fe(sigma3 + i), c.c_sigma3));
-        fe a = Fr::add(Fr::mul(load_fe(q + i), c.w_lr), Fr::mul(load_fe(q + (size_t)n + i), c.w_l));
-        fe b = Fr::add(Fr::mul(load_fe(q + 2 * (size_t)n + i), c.w_r), Fr::mul(load_fe(q + 3 * (size_t)n + i), c.w_o));
-        a = Fr::add(Fr::add(a, b), load_fe(q + 4 * (size_t)n + i));
-        store_fe(r + i, Fr::add(v, Fr::mul(a, c.alpha_base)));
-    }
 }
 
 // prover.cpp:552-590: the two batched opening polynomials before the division
@@ -516,6 +596,20 @@ unsigned grid_for(size_t count, unsigned block)
 }
 } // namespace
 
+constexpr int MAX_WIDGETS = 4;
+constexpr int MAX_SELECTORS = 11; // 5 arithmetic + 3 bool + 2 MiMC + 1 sequential
+inline int selectors_of(int kind)
+{
+    switch (kind)
+    {
+    case WIDGET_ARITHMETIC: return 5; // q_m, q_l, q_r, q_o, q_c          (arithmetic_widget.hpp:45-49)
+    case WIDGET_BOOL: return 3;       // q_bl, q_br, q_bo                 (bool_widget.hpp:45-47)
+    case WIDGET_MIMC: return 2;       // q_mimc_selector, q_mimc_coefficient (mimc_widget.hpp:43-44)
+    case WIDGET_SEQUENTIAL: return 1; // q_o_next                         (sequential_widget.hpp:46)
+    }
+    return -1;
+}
+
 struct Prover
 {
     unsigned log_n = 0;
@@ -524,7 +618,11 @@ struct Prover
     fe *w_lag = nullptr, *w_coef = nullptr, *w4 = nullptr;
     fe *sigma = nullptr, *s4 = nullptr;
     fe *z = nullptr, *z4 = nullptr;
-    fe *q = nullptr, *q2 = nullptr, *l1 = nullptr;
+    fe *q = nullptr, *q2 = nullptr, *q4 = nullptr, *l1 = nullptr;
+    // widget list of the circuit (prover.hpp:60), in the prover's order; selectors are stored back to back in q[]
+    int num_widgets = 0, num_selectors = 0;
+    int widget_kind[MAX_WIDGETS] = {};
+    int widget_first_selector[MAX_WIDGETS] = {};
     fe *quot_large = nullptr, *quot_mid = nullptr, *r = nullptr, *tmp = nullptr;
     fe *aggs = nullptr, *eval_partial = nullptr, *eval_out = nullptr;
     uint32_t* map = nullptr;
@@ -537,7 +635,7 @@ struct Prover
     bool l1_ready = false;    // l1[] depends on the circuit size only: computed once
     // this proof's inputs, in the order the rounds need them: w_l, w_r, w_o, the three mappings, the five selectors
     enum { ITEM_WL = 0, ITEM_WR, ITEM_WO, ITEM_MAP, ITEM_SEL, NUM_ITEMS };
-    const void* host_src[11] = {};
+    const void* host_src[6 + MAX_SELECTORS] = {};
     bool uploads_started = false;
 #ifndef BBG_EMULATE
     // One helper thread copies all of them through its own pinned ring and stream while the rounds already run on
@@ -598,11 +696,11 @@ int create(unsigned log_n, Prover** out)
     p->partial_stride = (unsigned)((4 * n + EVAL_SPAN - 1) / EVAL_SPAN + 8);
     const size_t pow_elems = 3 * ((size_t)2 << 11) + 64;
     // element counts, in the order of the header comment
-    const size_t counts[] = { 3 * n, 3 * n, 12 * n, 3 * n, 12 * n, n, 4 * n, 5 * n, 10 * n, 2 * n, 4 * n, 2 * n, n, 2 * n,
-                              2 * (size_t)p->aggs_stride, (size_t)MAX_EVAL_JOBS * p->partial_stride, MAX_EVAL_JOBS, pow_elems };
+    const size_t counts[] = { 3 * n, 3 * n, 12 * n, 3 * n, 12 * n, n, 4 * n, MAX_SELECTORS * n, 18 * n, 2 * n, 4 * n, 2 * n, n, 2 * n,
+                              2 * (size_t)p->aggs_stride, (size_t)MAX_EVAL_JOBS * p->partial_stride, MAX_EVAL_JOBS, pow_elems, 8 * n };
     size_t total = 0;
     for (size_t c : counts) total += (c + 7) & ~(size_t)7;
-    const size_t bytes = total * 32 + 3 * n * 4 + 256;
+    const size_t bytes = total * 32 + 3 * n * 4 + 256; // (2.9 GB at n = 2^20)
     int e = bbg_rt::dev_alloc(&p->arena, bytes);
     if (e != 0)
     {
@@ -629,6 +727,7 @@ int create(unsigned log_n, Prover** out)
     p->eval_partial = take(counts[15]);
     p->eval_out = take(counts[16]);
     p->pow_mem = take(counts[17]);
+    p->q4 = take(counts[18]);
     p->map = (uint32_t*)cur;
 #ifndef BBG_EMULATE
     cudaGetDevice(&p->device);
@@ -700,12 +799,28 @@ int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uin
     return 0;
 }
 
-int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t)
+int set_widgets(Prover* p, const int* kinds, int count, const uint64_t* const* selectors_lagrange, cudaStream_t)
 {
-    for (int k = 0; k < 5; ++k)
-        if (q_lagrange[k] == nullptr) return 1007;
+    if (kinds == nullptr || selectors_lagrange == nullptr || count < 1 || count > MAX_WIDGETS) return 1007;
     if (p->uploads_started) return 1007;
-    for (int k = 0; k < 5; ++k) p->host_src[6 + k] = q_lagrange[k];
+    int total = 0;
+    for (int w = 0; w < count; ++w)
+    {
+        const int k = selectors_of(kinds[w]);
+        if (k < 0 || total + k > MAX_SELECTORS) return 1007;
+        for (int prev = 0; prev < w; ++prev)
+            if (kinds[prev] == kinds[w]) return 1007; // each widget kind at most once (what the reference's composers build)
+        p->widget_kind[w] = kinds[w];
+        p->widget_first_selector[w] = total;
+        total += k;
+    }
+    for (int k = 0; k < total; ++k)
+    {
+        if (selectors_lagrange[k] == nullptr) return 1007;
+        p->host_src[6 + k] = selectors_lagrange[k];
+    }
+    p->num_widgets = count;
+    p->num_selectors = total;
     p->have_selectors = true;
     return 0;
 }
@@ -739,14 +854,14 @@ static int start_uploads(Prover* p, cudaStream_t st)
         }
         for (int k = 0; k < 3; ++k) copy(p->map + (size_t)k * n, p->host_src[3 + k], n * 4);
         done(Prover::ITEM_MAP);
-        for (int k = 0; k < 5; ++k) copy(p->q + (size_t)k * n, p->host_src[6 + k], n * 32);
+        for (int k = 0; k < p->num_selectors; ++k) copy(p->q + (size_t)k * n, p->host_src[6 + k], n * 32);
         done(Prover::ITEM_SEL);
         p->upload_error = e;
     });
 #else
     for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->w_lag + (size_t)k * n, p->host_src[k], n * 32, st));
     for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * n, p->host_src[3 + k], n * 4, st));
-    for (int k = 0; k < 5; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * n, p->host_src[6 + k], n * 32, st));
+    for (int k = 0; k < p->num_selectors; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * n, p->host_src[6 + k], n * 32, st));
 #endif
     return 0;
 }
@@ -879,13 +994,11 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     if (!p->l1_ready) BBG_CHECK(lagrange_fft_device(p->l1, p->log_n, p->log_n + 1, st));
     p->l1_ready = true;
     tr.mark("z4 + l1", st);
-    // selectors: Lagrange -> coefficients -> alpha_base-scaled 2n coset evaluations (arithmetic_widget.cpp:62-78)
-    BBG_CHECK(ntt_device(p->q, n, 5, p->log_n, OP_IFFT, nullptr, st));
-    BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n2, 256), 5), dim3(256), st, p->q2, (const fe*)p->q, (unsigned)n, (unsigned)n2, n, n2);
-    BBG_CHECK(ntt_device(p->q2, n2, 5, p->log_n + 1, OP_COSET_FFT_WITH_CONSTANT, alpha_base_, st));
-    g_plonk_launches += 4;
+    // selectors: Lagrange -> coefficients (arithmetic_widget.cpp:62-66 and the other widgets' first lines)
+    const int S = p->num_selectors;
+    BBG_CHECK(ntt_device(p->q, n, (size_t)S, p->log_n, OP_IFFT, nullptr, st));
+    ++g_plonk_launches;
 
-    tr.mark("selectors ifft + coset_fft", st);
     QuotientConsts c;
     c.g = gen_k1();
     c.beta = beta;
@@ -909,12 +1022,88 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
             cur = Fr::reduce(Fr::mul(cur, ws));
         }
     };
-    fill_vinv(2);
-    BBG_LAUNCH_NOSYNC(quotient_large_kernel, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->s4, (const fe*)p->w4, (const fe*)p->z4,
-                      p->pow_large, c, (unsigned)n4);
-    fill_vinv(1);
-    BBG_LAUNCH_NOSYNC(quotient_mid_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->z4, (const fe*)p->l1, (const fe*)p->w4,
-                      (const fe*)p->q2, p->pow_mid, c, (unsigned)n2);
+    // selector polynomial `sel` -> its coset evaluations on the 2n / 4n domain, scaled by `k` (null: unscaled)
+    auto to_coset = [&](fe* dst, int sel, int count, size_t size, unsigned log_size, const fe* k) -> int {
+        BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(size, 256), (unsigned)count), dim3(256), st, dst, (const fe*)(p->q + (size_t)sel * n), (unsigned)n,
+                          (unsigned)size, n, size);
+        ++g_plonk_launches;
+        return ntt_device(dst, size, (size_t)count, log_size, k != nullptr ? OP_COSET_FFT_WITH_CONSTANT : OP_COSET_FFT, k != nullptr ? (const uint64_t*)k->v : nullptr,
+                          st);
+    };
+    const bool standard = p->num_widgets == 1 && p->widget_kind[0] == WIDGET_ARITHMETIC;
+    if (standard)
+    {
+        // StandardComposer circuits: the gate identity is fused into the mid-domain pass (arithmetic_widget.cpp:68-97)
+        BBG_CHECK(to_coset(p->q2, 0, 5, n2, p->log_n + 1, &alpha_base));
+        tr.mark("selectors ifft + coset_fft", st);
+        fill_vinv(2);
+        BBG_LAUNCH_NOSYNC(quotient_large_kernel<true>, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->s4, (const fe*)p->w4,
+                          (const fe*)p->z4, p->pow_large, c, (unsigned)n4);
+        fill_vinv(1);
+        BBG_LAUNCH_NOSYNC(quotient_mid_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->z4, (const fe*)p->l1, (const fe*)p->w4,
+                          (const fe*)p->q2, p->pow_mid, c, (unsigned)n2);
+        g_plonk_launches += 2;
+    }
+    else
+    {
+        // any other widget mix: permutation / boundary terms first, then every widget adds its term in the prover's order
+        // with the reference's alpha_base chain (prover.cpp:436-441), then the two divisions by Z_H*
+        BBG_LAUNCH_NOSYNC(quotient_large_kernel<false>, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->s4, (const fe*)p->w4,
+                          (const fe*)p->z4, p->pow_large, c, (unsigned)n4);
+        BBG_LAUNCH_NOSYNC(quotient_mid_base_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->z4, (const fe*)p->l1, c, (unsigned)n2);
+        g_plonk_launches += 2;
+        fe ab = alpha_base;
+        fe* q2_cursor = p->q2;
+        for (int w = 0; w < p->num_widgets; ++w)
+        {
+            const int sel = p->widget_first_selector[w];
+            switch (p->widget_kind[w])
+            {
+            case WIDGET_ARITHMETIC: // arithmetic_widget.cpp:60-99
+                BBG_CHECK(to_coset(q2_cursor, sel, 5, n2, p->log_n + 1, &ab));
+                BBG_LAUNCH_NOSYNC(arith_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->w4, (const fe*)q2_cursor, (unsigned)n2);
+                q2_cursor += 5 * n2;
+                ab = Fr::reduce(Fr::mul(ab, alpha));
+                break;
+            case WIDGET_BOOL: // bool_widget.cpp:62-100
+            {
+                fe k = ab;
+                for (int j = 0; j < 3; ++j)
+                {
+                    BBG_CHECK(to_coset(q2_cursor + (size_t)j * n2, sel + j, 1, n2, p->log_n + 1, &k));
+                    k = Fr::reduce(Fr::mul(k, alpha));
+                }
+                BBG_LAUNCH_NOSYNC(bool_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->w4, (const fe*)q2_cursor, (unsigned)n2);
+                q2_cursor += 3 * n2;
+                ab = k; // alpha_base * alpha^3
+                break;
+            }
+            case WIDGET_MIMC: // mimc_widget.cpp:57-89
+                BBG_CHECK(to_coset(p->q4, sel, 1, n4, p->log_n + 2, &ab));
+                BBG_CHECK(to_coset(p->q4 + n4, sel + 1, 1, n4, p->log_n + 2, nullptr));
+                BBG_LAUNCH_NOSYNC(mimc_large_add_kernel, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->w4, (const fe*)p->q4, alpha,
+                                  (unsigned)n4);
+                ab = Fr::reduce(Fr::mul(ab, c.alpha_sqr));
+                break;
+            case WIDGET_SEQUENTIAL: // sequential_widget.cpp:47-62
+            {
+                const fe old_alpha = Fr::reduce(Fr::mul(ab, Fr::invert(alpha)));
+                BBG_CHECK(to_coset(q2_cursor, sel, 1, n2, p->log_n + 1, &old_alpha));
+                BBG_LAUNCH_NOSYNC(seq_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)(p->w4 + 2 * n4), (const fe*)q2_cursor,
+                                  (unsigned)n2);
+                q2_cursor += n2;
+                break;
+            }
+            }
+            ++g_plonk_launches;
+        }
+        tr.mark("selectors ifft + coset_fft + widget terms", st);
+        fill_vinv(2);
+        BBG_LAUNCH_NOSYNC(divide_vanishing_kernel, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, p->pow_large, c, 3u, (unsigned)n4);
+        fill_vinv(1);
+        BBG_LAUNCH_NOSYNC(divide_vanishing_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, p->pow_mid, c, 1u, (unsigned)n2);
+        g_plonk_launches += 2;
+    }
     tr.mark("quotient kernels", st);
     BBG_CHECK(ntt_device(p->quot_mid, n2, 1, p->log_n + 1, OP_COSET_IFFT, nullptr, st));
     BBG_CHECK(ntt_device(p->quot_large, n4, 1, p->log_n + 2, OP_COSET_IFFT, nullptr, st));
@@ -941,42 +1130,82 @@ static int run_evals(Prover* p, const EvalJobs& jobs, int count, uint64_t* out, 
     return bbg_rt::sync(st);
 }
 
-// prover.cpp:465-477: w_l, w_r, w_o, beta sigma_1, beta sigma_2 at z; Z at z w; the quotient's 3n coefficients at z
-int round_evaluations(Prover* p, const uint64_t* zeta_, const uint64_t* zeta_omega_, uint64_t* out /* 7 x 4 */, cudaStream_t st)
+// prover.cpp:465-477 (+ :455-463 shifted wire, mimc_widget.cpp:91-94): w_l, w_r, w_o, beta sigma_1, beta sigma_2 at z; Z at z w;
+// the quotient's 3n coefficients at z; then w_o at z w when a widget needs it and q_mimc_coefficient at z (zero otherwise)
+int round_evaluations(Prover* p, const uint64_t* zeta_, const uint64_t* zeta_omega_, uint64_t* out /* 9 x 4 */, cudaStream_t st)
 {
     const size_t n = p->n;
     EvalJobs jobs;
     const fe zeta = from_u64(zeta_), zw = from_u64(zeta_omega_);
     const fe* polys[7] = { p->w_coef, p->w_coef + n, p->w_coef + 2 * n, p->sigma, p->sigma + n, p->z, p->quot_large };
+    for (int j = 0; j < MAX_EVAL_JOBS; ++j)
+    {
+        jobs.poly[j] = nullptr;
+        jobs.len[j] = 0;
+        jobs.point[j] = Fr::zero();
+    }
     for (int j = 0; j < 7; ++j)
     {
         jobs.poly[j] = polys[j];
         jobs.len[j] = (unsigned)(j == 6 ? 3 * n : n);
         jobs.point[j] = j == 5 ? zw : zeta;
     }
-    for (int j = 7; j < MAX_EVAL_JOBS; ++j)
+    int count = 7, shifted_at = -1, mimc_at = -1;
+    for (int w = 0; w < p->num_widgets; ++w)
     {
-        jobs.poly[j] = nullptr;
-        jobs.len[j] = 0;
-        jobs.point[j] = Fr::zero();
+        const int kind = p->widget_kind[w];
+        if ((kind == WIDGET_MIMC || kind == WIDGET_SEQUENTIAL) && shifted_at < 0)
+        {
+            shifted_at = count;
+            jobs.poly[count] = p->w_coef + 2 * n;
+            jobs.len[count] = (unsigned)n;
+            jobs.point[count++] = zw;
+        }
+        if (kind == WIDGET_MIMC)
+        {
+            mimc_at = count;
+            jobs.poly[count] = p->q + (size_t)(p->widget_first_selector[w] + 1) * n;
+            jobs.len[count] = (unsigned)n;
+            jobs.point[count++] = zeta;
+        }
     }
-    return run_evals(p, jobs, 7, out, st);
+    uint64_t tmp[MAX_EVAL_JOBS * 4];
+    BBG_CHECK(run_evals(p, jobs, count, tmp, st));
+    memset(out, 0, 9 * 32);
+    memcpy(out, tmp, 7 * 32);
+    if (shifted_at >= 0) memcpy(out + 28, tmp + 4 * shifted_at, 32);
+    if (mimc_at >= 0) memcpy(out + 32, tmp + 4 * mimc_at, 32);
+    return 0;
 }
 
-// prover.cpp:479-503: the linearisation polynomial r(X) and its evaluation at z
-int round_linearise(Prover* p, const uint64_t* scalars /* 7 x 4: c_z, c_sigma3, w_lr, w_l, w_r, w_o, alpha_base */, const uint64_t* zeta_,
-                    uint64_t out_eval[4], cudaStream_t st)
+// prover.cpp:479-503 and the widgets' compute_linear_contribution: r[i] = s_0 z[i] + s_1 [beta sigma_3][i] + sum_k s_(2+k) q_k[i]
+// over the circuit's selectors in coefficient form (the host has folded wire evaluations and the alpha chain into s_k)
+int round_linearise(Prover* p, const uint64_t* scalars /* (2 + selectors) x 4 */, const uint64_t* zeta_, uint64_t out_eval[4], cudaStream_t st)
 {
     const size_t n = p->n;
-    LinearConsts c;
-    c.c_z = from_u64(scalars);
-    c.c_sigma3 = from_u64(scalars + 4);
-    c.w_lr = from_u64(scalars + 8);
-    c.w_l = from_u64(scalars + 12);
-    c.w_r = from_u64(scalars + 16);
-    c.w_o = from_u64(scalars + 20);
-    c.alpha_base = from_u64(scalars + 24);
-    BBG_LAUNCH_NOSYNC(linearise_kernel, dim3(grid_for(n, 128)), dim3(128), st, p->r, (const fe*)p->z, (const fe*)(p->sigma + 2 * n), (const fe*)p->q, c, (unsigned)n);
+    LinTerms t;
+    t.count = 0;
+    auto term = [&](const fe* src, const uint64_t* c) {
+        t.src[t.count] = src;
+        t.c[t.count++] = from_u64(c);
+    };
+    term(p->z, scalars);
+    term(p->sigma + 2 * n, scalars + 4);
+    bool first = true;
+    for (int k = 0; k < p->num_selectors; ++k)
+    {
+        if (t.count == MAX_TERMS)
+        {
+            if (first) BBG_LAUNCH_NOSYNC(axpy_terms_kernel<false>, dim3(grid_for(n, 128)), dim3(128), st, p->r, t, (unsigned)n);
+            else BBG_LAUNCH_NOSYNC(axpy_terms_kernel<true>, dim3(grid_for(n, 128)), dim3(128), st, p->r, t, (unsigned)n);
+            first = false;
+            t.count = 0;
+            ++g_plonk_launches;
+        }
+        term(p->q + (size_t)k * n, scalars + 8 + 4 * k);
+    }
+    if (first) BBG_LAUNCH_NOSYNC(axpy_terms_kernel<false>, dim3(grid_for(n, 128)), dim3(128), st, p->r, t, (unsigned)n);
+    else BBG_LAUNCH_NOSYNC(axpy_terms_kernel<true>, dim3(grid_for(n, 128)), dim3(128), st, p->r, t, (unsigned)n);
     ++g_plonk_launches;
     EvalJobs jobs;
     for (int j = 0; j < MAX_EVAL_JOBS; ++j)
@@ -992,8 +1221,11 @@ int round_linearise(Prover* p, const uint64_t* scalars /* 7 x 4: c_z, c_sigma3, 
 }
 
 // prover.cpp:505-655 compute_opening_elements after the nu challenge
+// wire_shift: nu-power coefficients of w_l, w_r, w_o in the shifted opening polynomial (:597-631; zero = not needed);
+// selector_terms: coefficients of the selectors in the opening polynomial (the widgets' compute_opening_poly_contribution)
 int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint64_t* beta_inv_, const uint64_t* zeta_, const uint64_t* zeta_omega_,
-                   uint64_t* out_xyz /* 2 x 12 */, cudaStream_t st)
+                   const uint64_t* wire_shift /* 3 x 4 */, const uint64_t* selector_terms /* selectors x 4 */, uint64_t* out_xyz /* 2 x 12 */,
+                   cudaStream_t st)
 {
     const size_t n = p->n;
     OpeningConsts c;
@@ -1006,6 +1238,35 @@ int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint6
     fe* shifted = p->tmp + n;
     BBG_LAUNCH_NOSYNC(opening_combine_kernel, dim3(grid_for(n, 128)), dim3(128), st, opening, shifted, (const fe*)p->quot_large, (const fe*)p->r,
                       (const fe*)p->w_coef, (const fe*)p->sigma, (const fe*)p->z, c, (unsigned)n);
+    {
+        LinTerms t;
+        t.count = 0;
+        for (int k = 0; k < 3; ++k)
+        {
+            const fe ck = from_u64(wire_shift + 4 * k);
+            if (Fr::is_zero_raw(ck)) continue;
+            t.src[t.count] = p->w_coef + (size_t)k * n;
+            t.c[t.count++] = ck;
+        }
+        if (t.count > 0)
+        {
+            BBG_LAUNCH_NOSYNC(axpy_terms_kernel<true>, dim3(grid_for(n, 128)), dim3(128), st, shifted, t, (unsigned)n);
+            ++g_plonk_launches;
+        }
+        t.count = 0;
+        for (int k = 0; k < p->num_selectors; ++k)
+        {
+            const fe ck = from_u64(selector_terms + 4 * k);
+            if (Fr::is_zero_raw(ck)) continue;
+            t.src[t.count] = p->q + (size_t)k * n;
+            t.c[t.count++] = ck;
+        }
+        if (t.count > 0)
+        {
+            BBG_LAUNCH_NOSYNC(axpy_terms_kernel<true>, dim3(grid_for(n, 128)), dim3(128), st, opening, t, (unsigned)n);
+            ++g_plonk_launches;
+        }
+    }
     const unsigned run = ZRUN;
     const unsigned runs = (unsigned)((n + run - 1) / run);
     const unsigned per = (runs + SCAN_THREADS - 1) / SCAN_THREADS;

@@ -7,12 +7,19 @@ namespace bbg
 {
 namespace plonk
 {
+enum widget_kind // == bbg_plonk_widget in include/bbgpu.h
+{
+    WIDGET_ARITHMETIC = 0,
+    WIDGET_BOOL = 1,
+    WIDGET_MIMC = 2,
+    WIDGET_SEQUENTIAL = 3,
+};
 struct Prover;
 int create(unsigned log_n, Prover** out);
 void destroy(Prover* p);
 int set_witness(Prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o, cudaStream_t st);
 int set_permutation(Prover* p, const uint32_t* m1, const uint32_t* m2, const uint32_t* m3, cudaStream_t st);
-int set_arithmetic_selectors(Prover* p, const uint64_t* const* q_lagrange, cudaStream_t st);
+int set_widgets(Prover* p, const int* kinds, int count, const uint64_t* const* selectors_lagrange, cudaStream_t st);
 int set_srs(Prover* p, const void* d_table);
 int round_wires(Prover* p, uint64_t* out_xyz, cudaStream_t st);
 int round_grand_product(Prover* p, const uint64_t* beta, const uint64_t* gamma, uint64_t out_xyz[12], cudaStream_t st);
@@ -20,8 +27,8 @@ int round_quotient(Prover* p, const uint64_t* beta, const uint64_t* gamma, const
                    cudaStream_t st);
 int round_evaluations(Prover* p, const uint64_t* zeta, const uint64_t* zeta_omega, uint64_t* out, cudaStream_t st);
 int round_linearise(Prover* p, const uint64_t* scalars, const uint64_t* zeta, uint64_t out_eval[4], cudaStream_t st);
-int round_openings(Prover* p, const uint64_t* nu_powers, const uint64_t* beta_inv, const uint64_t* zeta, const uint64_t* zeta_omega, uint64_t* out_xyz,
-                   cudaStream_t st);
+int round_openings(Prover* p, const uint64_t* nu_powers, const uint64_t* beta_inv, const uint64_t* zeta, const uint64_t* zeta_omega,
+                   const uint64_t* wire_shift, const uint64_t* selector_terms, uint64_t* out_xyz, cudaStream_t st);
 size_t launch_count();
 } // namespace plonk
 } // namespace bbg

@@ -112,8 +112,8 @@ int bbg_generate_pippenger_point_table_dev(const void* d_points, void* d_table, 
 int bbg_g1_generate_multiples_dev(const uint64_t start[4], const uint64_t step[4], void* d_points, size_t n);
 
 /* ---- HBM-resident PLONK prover rounds -------------------------------------
- * Stand behind waffle::Prover::construct_proof (waffle/proof_system/prover/prover.cpp:657-666) for circuits whose only
- * widget is the arithmetic widget (StandardComposer): the witness, the permutation mappings and the selectors are
+ * Stand behind waffle::Prover::construct_proof (waffle/proof_system/prover/prover.cpp:657-666) for circuits built from
+ * the arithmetic, bool, MiMC and sequential widgets (Standard / Bool / MiMC / Extended composers): the witness, the permutation mappings and the selectors are
  * uploaded once per proof, every polynomial of the proof stays in HBM, and only commitments (12 limbs, the same
  * normalised form as bbg_msm_g1) and evaluations (4 limbs, canonical) come back.  The Fiat-Shamir transcript stays
  * with the caller (challenge.hpp), which feeds the challenges back in between rounds.
@@ -125,7 +125,22 @@ int bbg_plonk_destroy(bbg_plonk_prover* p);
 int bbg_plonk_set_witness(bbg_plonk_prover* p, const uint64_t* w_l, const uint64_t* w_r, const uint64_t* w_o);
 /* prover.hpp:56-58 sigma_k_mapping: n entries, wire column << 30 | row (permutation.hpp:13-88) */
 int bbg_plonk_set_permutation(bbg_plonk_prover* p, const uint32_t* sigma_1_mapping, const uint32_t* sigma_2_mapping, const uint32_t* sigma_3_mapping);
-/* arithmetic_widget.hpp:45-49 q_m, q_l, q_r, q_o, q_c in Lagrange form (host, not modified) */
+/* The circuit's widgets in the prover's order (prover.hpp:60 `widgets`), each kind at most once, and their selector
+ * polynomials in Lagrange form (host, not modified), back to back in this order:
+ *   arithmetic  q_m, q_l, q_r, q_o, q_c                 (arithmetic_widget.hpp:45-49)
+ *   bool        q_bl, q_br, q_bo                        (bool_widget.hpp:45-47)
+ *   MiMC        q_mimc_selector, q_mimc_coefficient     (mimc_widget.hpp:43-44)
+ *   sequential  q_o_next                                (sequential_widget.hpp:46)
+ * "selectors" below = the total number of these polynomials (5 for a StandardComposer circuit). */
+enum bbg_plonk_widget
+{
+    BBG_WIDGET_ARITHMETIC = 0,
+    BBG_WIDGET_BOOL = 1,
+    BBG_WIDGET_MIMC = 2,
+    BBG_WIDGET_SEQUENTIAL = 3,
+};
+int bbg_plonk_set_widgets(bbg_plonk_prover* p, const int* kinds, int count, const uint64_t* const* selectors);
+/* shorthand for the StandardComposer's single arithmetic widget */
 int bbg_plonk_set_arithmetic_selectors(bbg_plonk_prover* p, const uint64_t* q_m, const uint64_t* q_l, const uint64_t* q_r, const uint64_t* q_o,
                                        const uint64_t* q_c);
 /* ReferenceString::monomials, the 2n-entry point table (goes through the SRS cache of bbg_srs_register) */
@@ -134,20 +149,27 @@ int bbg_plonk_set_srs(bbg_plonk_prover* p, const uint64_t* points_table, size_t 
 int bbg_plonk_round_wires(bbg_plonk_prover* p, uint64_t* out_xyz);
 /* compute_z_coefficients + compute_z_commitment (:137-225, :91-107): out = Z_1 */
 int bbg_plonk_round_grand_product(bbg_plonk_prover* p, const uint64_t beta[4], const uint64_t gamma[4], uint64_t out_xyz[12]);
-/* rest of compute_quotient_polynomial + compute_quotient_commitment (:227-463, :109-124, arithmetic_widget.cpp:60-97);
- * alpha_base = the widget's quotient scaling (alpha^4 in prover.cpp:436-441): out = T_LO, T_MID, T_HI (3 x 12) */
+/* rest of compute_quotient_polynomial + compute_quotient_commitment (:227-463, :109-124) and every widget's
+ * compute_quotient_contribution (arithmetic_widget.cpp:60-99, bool_widget.cpp:62-100, mimc_widget.cpp:57-89,
+ * sequential_widget.cpp:47-62); alpha_base = the first widget's scaling (alpha^4 in prover.cpp:436-441), chained through
+ * the widgets as the reference does: out = T_LO, T_MID, T_HI (3 x 12) */
 int bbg_plonk_round_quotient(bbg_plonk_prover* p, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4], const uint64_t alpha_base[4],
                              uint64_t* out_xyz);
-/* compute_linearisation_coefficients, first half (:465-477): out (7 x 4) = w_l(z), w_r(z), w_o(z), [beta sigma_1](z),
- * [beta sigma_2](z), Z(z w), t(z) over the quotient's first 3n coefficients */
+/* compute_linearisation_coefficients, first half (:465-477): out (9 x 4) = w_l(z), w_r(z), w_o(z), [beta sigma_1](z),
+ * [beta sigma_2](z), Z(z w), t(z) over the quotient's first 3n coefficients, w_o(z w) when a MiMC / sequential widget is
+ * present (:455-463), q_mimc_coefficient(z) (mimc_widget.cpp:91-94); zero where not applicable */
 int bbg_plonk_round_evaluations(bbg_plonk_prover* p, const uint64_t zeta[4], const uint64_t zeta_omega[4], uint64_t* out_evals);
-/* second half (:479-503, arithmetic_widget.cpp:99-122): r[i] = s0 z[i] + s1 [beta sigma_3][i] + (s2 q_m + s3 q_l + s4 q_r +
- * s5 q_o + q_c)[i] s6, scalars = s0..s6 (7 x 4); out = r(zeta) */
+/* second half (:479-503 and the widgets' compute_linear_contribution): r[i] = s_0 z[i] + s_1 [beta sigma_3][i] +
+ * sum_k s_(2+k) selector_k[i] (coefficient forms); scalars = (2 + selectors) x 4, the caller folds wire evaluations and
+ * the alpha chain into them; out = r(zeta) */
 int bbg_plonk_round_linearise(bbg_plonk_prover* p, const uint64_t* scalars, const uint64_t zeta[4], uint64_t out_linear_eval[4]);
 /* compute_opening_elements after the nu challenge (:505-655; compute_kate_opening_coefficients,
- * polynomial_arithmetic.cpp:562-591): nu_powers = nu^1..nu^7 (7 x 4); out = PI_Z, PI_Z_OMEGA (2 x 12) */
+ * polynomial_arithmetic.cpp:562-591): nu_powers = nu^1..nu^7 (7 x 4); wire_shift_terms (3 x 4) = coefficients of w_l, w_r,
+ * w_o in the shifted opening polynomial (:597-631, zero = wire not needed); selector_terms (selectors x 4) = coefficients
+ * of the selectors in the opening polynomial (compute_opening_poly_contribution, zero for most);
+ * out = PI_Z, PI_Z_OMEGA (2 x 12) */
 int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, const uint64_t beta_inv[4], const uint64_t zeta[4],
-                             const uint64_t zeta_omega[4], uint64_t* out_xyz);
+                             const uint64_t zeta_omega[4], const uint64_t* wire_shift_terms, const uint64_t* selector_terms, uint64_t* out_xyz);
 
 /* ---- device memory helpers (tests, bench, device-resident callers) ---------------------------- */
 int bbg_dev_alloc(void** d_ptr, size_t bytes);

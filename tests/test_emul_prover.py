@@ -30,20 +30,22 @@ def srs():
     return path
 
 
-def run(binary, log_gates, env=None):
+def run(binary, log_gates, composer="standard", env=None):
     e = dict(os.environ)
     e["OMP_NUM_THREADS"] = "4"
     e.update(env or {})
-    out = subprocess.run([os.path.join(B, binary), str(log_gates)], cwd=H.ROOT, capture_output=True, text=True, timeout=900, env=e)
+    out = subprocess.run([os.path.join(B, binary), str(log_gates), "1", composer], cwd=H.ROOT, capture_output=True, text=True, timeout=900, env=e)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("log_gates", [5, 9])
-def test_resident_prover_emulated_matches_cpu_reference(srs, log_gates):
-    cpu = run("prover_cpu", log_gates)
-    emu = run("prover_gpu_emul", log_gates)
+@pytest.mark.parametrize("composer,log_gates", [("standard", 5), ("standard", 9), ("bool", 6), ("mimc", 6), ("extended", 7)])
+def test_resident_prover_emulated_matches_cpu_reference(srs, composer, log_gates):
+    """standard = arithmetic widget; bool = bool + arithmetic; mimc = MiMC + arithmetic (shifted output wire, selector in
+    the opening polynomial); extended = bool + arithmetic + sequential (test/composer/test_*_composer.cpp circuits)"""
+    cpu = run("prover_cpu", log_gates, composer)
+    emu = run("prover_gpu_emul", log_gates, composer)
     assert cpu["verified"] and emu["verified"]
-    assert emu["n"] == cpu["n"]
+    assert emu["n"] == cpu["n"] and emu["widgets"] == cpu["widgets"]
     for k, v in cpu["proof"].items():
         assert emu["proof"][k] == v, k

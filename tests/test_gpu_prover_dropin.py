@@ -31,10 +31,11 @@ def srs():
     return path
 
 
-def run(binary, log_gates, repeat=1, env=None):
+def run(binary, log_gates, repeat=1, env=None, composer="standard"):
     e = dict(os.environ)
     e.update(env or {})
-    out = subprocess.run([os.path.join(B, binary), str(log_gates), str(repeat)], cwd=H.ROOT, capture_output=True, text=True, timeout=600, env=e)
+    out = subprocess.run([os.path.join(B, binary), str(log_gates), str(repeat), composer], cwd=H.ROOT, capture_output=True, text=True, timeout=600,
+                         env=e)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return json.loads(out.stdout.strip().splitlines()[-1])
 
@@ -45,6 +46,18 @@ def test_prover_gpu_matches_cpu_reference(srs, log_gates):
     gpu = run("prover_gpu", log_gates, repeat=2)  # second proof after Prover::reset()
     assert cpu["verified"] and gpu["verified"]
     assert gpu["n"] == cpu["n"]
+    for k, v in cpu["proof"].items():
+        assert gpu["proof"][k] == v, k
+
+
+@pytest.mark.parametrize("composer", ["bool", "mimc", "extended"])
+@pytest.mark.parametrize("log_gates", [7, 11, 13])
+def test_resident_prover_other_widget_mixes(srs, log_gates, composer):
+    """bool / MiMC / sequential widgets inside the resident rounds (test/composer/test_*_composer.cpp circuits, scaled)"""
+    cpu = run("prover_cpu", log_gates, composer=composer)
+    gpu = run("prover_gpu", log_gates, repeat=2, composer=composer)
+    assert cpu["verified"] and gpu["verified"]
+    assert gpu["n"] == cpu["n"] and gpu["widgets"] == cpu["widgets"] >= 2
     for k, v in cpu["proof"].items():
         assert gpu["proof"][k] == v, k
 
