@@ -188,9 +188,12 @@ template <typename Composer> static int run(Composer& composer, size_t log_gates
     print_fe("sigma_1_eval", proof.sigma_1_eval.data);
     print_fe("sigma_2_eval", proof.sigma_2_eval.data);
     print_fe("z_1_shifted_eval", proof.z_1_shifted_eval.data);
-    // (only written by provers whose widgets need them; zero-initialised here so both builds print the same)
-    print_fe("w_o_shifted_eval", proof.w_o_shifted_eval.data);
-    print_fe("q_mimc_coefficient_eval", proof.q_mimc_coefficient_eval.data);
+    // plonk_proof fields the prover only writes when a widget asks for them (uninitialised memory otherwise)
+    bool has_shifted = false;
+    for (size_t i = 0; i < prover.widgets.size(); ++i)
+        has_shifted |= prover.widgets[i]->version.has_dependency(waffle::WidgetVersionControl::Dependencies::REQUIRES_W_O_SHIFTED);
+    if (has_shifted) print_fe("w_o_shifted_eval", proof.w_o_shifted_eval.data);
+    if (strcmp(kind, "mimc") == 0) print_fe("q_mimc_coefficient_eval", proof.q_mimc_coefficient_eval.data);
     print_fe("linear_eval", proof.linear_eval.data, true);
     printf("}}\n");
     if (bbg_shim_report) bbg_shim_report();
