@@ -252,7 +252,7 @@ const char* bbg_error_string(int code)
     switch (code)
     {
     case 0: return "success";
-    case BBG_E_BAD_SIZE: return "bbgpu: NTT size must be 2^1 .. 2^22";
+    case BBG_E_BAD_SIZE: return "bbgpu: NTT size must be 2^1 .. 2^28";
     case BBG_E_BAD_OP: return "bbgpu: unknown NTT operation";
     case BBG_E_NULL_CONSTANT: return "bbgpu: this NTT operation needs a constant";
     case BBG_E_NOT_INITIALISED: return "bbgpu: bbg_init() has not been called";
@@ -288,7 +288,7 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
     BBG_CHECK(ensure_ready());
     if (batch == 0) return 0;
     if (coeffs == nullptr) return BBG_E_BAD_ARGUMENT;
-    if (log2_n < 1 || log2_n > 22) return BBG_E_BAD_SIZE;
+    if (log2_n < 1 || log2_n > 28) return BBG_E_BAD_SIZE;
     const size_t n = (size_t)1 << log2_n, bytes = n * 32;
     BBG_CHECK(g_stage_coeffs.ensure(batch * bytes));
     for (size_t i = 0; i < batch; ++i)

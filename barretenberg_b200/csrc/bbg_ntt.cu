@@ -20,6 +20,10 @@
 //     2 CTAs/SM (2 x 99 KiB smem, <=128 regs).  Work per element: (log2 n)/2 products + 1 for the
 //     inter-pass twiddle (+1 per fused coset / constant scaling), i.e. IMAD-bound, ~2 x 64 B of HBM
 //     traffic per element per pass.
+//   n >= 2^23 (up to the field's 2^28 two-adicity): one more outer split n = N0 * M, M <= 2^22: an outer pass A over
+//       columns of length N0 (same kernel, matrix w_n^(i0 j)), then the two passes above on the N0 contiguous blocks of
+//       M elements, whose last pass scatters block i0's output u to natural position i0 + N0 u.  THREE HBM passes;
+//       coset / constant scalings run as one extra element-wise pass here (3% of the products, not worth more tables).
 //   All twiddles, the inter-pass matrices and the coset power tables are generated ON THE DEVICE the
 //   first time a domain size is used and cached (the reference's host round_roots tables are never
 //   uploaded).
@@ -118,6 +122,7 @@ struct PassParams
     const fe* vec;          // pass A: pre-scale P[j1] or null;  pass B: post-scale Q[i2] or null
     fe post_const;          // pass B: extra constant (fft/ifft_with_constant)
     int has_post_const;
+    int scatter_shift;      // pass B as the last of three passes: block b's output o goes to dst[(o << scatter_shift) + b]
 };
 
 // DIF butterflies on the 3-bit owned field x[m] <-> k = base | m << B of a 2^L-point transform:
@@ -223,7 +228,8 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             else
             {
                 const size_t row = ((size_t)tile << TM::CLOG) + c;
-                const size_t o = row + ((size_t)isub << rest);
+                size_t o = row + ((size_t)isub << rest);
+                if (p.scatter_shift) o <<= p.scatter_shift; // (dst already points at this block's column)
                 fe y = x[m];
                 if (p.vec != nullptr) y = NTT_MUL(y, load_fe(p.vec + isub));
                 if (p.has_post_const) y = NTT_MUL(y, p.post_const);
@@ -272,7 +278,7 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT, 2) ntt_pas
         const int tile = work % p.num_tiles;
         const size_t b = (size_t)(work / p.num_tiles);
         fe x[8];
-        run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.dst + b * p.batch_stride, tile, data, tw);
+        run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.scatter_shift ? p.dst + b : p.dst + b * p.batch_stride, tile, data, tw);
         NTT_SYNC(); // the last step's shared-memory reads finish before the next tile overwrites
     }
 }
@@ -395,6 +401,16 @@ __global__ void __launch_bounds__(64) lagrange_fft_kernel(fe* out, fe root_T, fe
     }
 }
 
+// x[i] = canonical(x[i] * k * lo[i & mask] * hi[i >> lo_log]): the coset scalings of the three-pass sizes
+__global__ void scale_powers_kernel(fe* x, const fe* lo, const fe* hi, int lo_log, fe k, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        fe w = Fr::mul(load_fe(lo + (i & (((size_t)1 << lo_log) - 1))), load_fe(hi + (i >> lo_log)));
+        store_fe(x + i, Fr::mul_full(Fr::mul(load_fe(x + i), w), k));
+    }
+}
+
 // out[i] = in[i] * k
 __global__ void scale_vector_kernel(fe* out, const fe* in, fe k, unsigned count)
 {
@@ -497,11 +513,22 @@ enum vec_kind
 {
     VEC_PRE_COSET = 0,   // big: g^(N2 j1), j1 < N1        small: g^j, j < n
     VEC_POST_ICOSET = 1, // big: g^(-N1 i2), i2 < N2       small: g^(-i) / n, i < n
+    VEC_G_LO = 2,        // three-pass sizes: g^j, j < 2^11           VEC_G_HI = 3: g^(2^11 j), j < n / 2^11
+    VEC_G_HI = 3,
+    VEC_GINV_LO = 4,     // the same for g^-1
+    VEC_GINV_HI = 5,
 };
 
 // split used for n >= 2^12: N1 = 2^L1 rows (pass A transform length), N2 = 2^L2 columns (pass B length)
 void split(unsigned log_n, int& L1, int& L2)
 {
+    if (log_n > 2 * (unsigned)TILE_LOG)
+    {
+        // three passes: outer length 2^L1, then the two-pass transform of size 2^L2 <= 2^22 on every block
+        L1 = (int)(log_n + 2) / 3;
+        L2 = (int)log_n - L1;
+        return;
+    }
     L1 = (int)(log_n + 1) / 2;
     L2 = (int)log_n - L1;
 }
@@ -515,7 +542,14 @@ int get_vec(unsigned log_n, int kind, cudaStream_t st, const fe** out)
         fe* v = nullptr;
         unsigned count;
         fe base, scale = Fr::one();
-        if (log_n <= (unsigned)TILE_LOG)
+        if (kind >= VEC_G_LO)
+        {
+            const fe g = (kind == VEC_G_LO || kind == VEC_G_HI) ? COSET_GEN : COSET_GEN_INV;
+            const bool hi = (kind == VEC_G_HI || kind == VEC_GINV_HI);
+            count = hi ? 1u << (log_n - LO_TABLE_LOG) : 1u << LO_TABLE_LOG;
+            base = hi ? host_pow(g, (uint64_t)1 << LO_TABLE_LOG) : g;
+        }
+        else if (log_n <= (unsigned)TILE_LOG)
         {
             count = 1u << log_n;
             if (kind == VEC_PRE_COSET) base = COSET_GEN;
@@ -549,7 +583,8 @@ int get_vec(unsigned log_n, int kind, cudaStream_t st, const fe** out)
     return 0;
 }
 
-// variant: 0 forward, 1 inverse (x 1/n), 2 coset forward (x g^j2), 3 coset inverse (x g^-i1 / n)
+// variant: 0 forward, 1 inverse (x 1/n), 2 coset forward (x g^j2), 3 coset inverse (x g^-i1 / n),
+//          4 inverse roots without the 1/n (the inner transform of the three-pass sizes)
 int get_matrix(unsigned log_n, int variant, cudaStream_t st, const fe** out)
 {
     const int key = (int)log_n * 8 + variant;
@@ -559,10 +594,10 @@ int get_matrix(unsigned log_n, int variant, cudaStream_t st, const fe** out)
         int L1, L2;
         split(log_n, L1, L2);
         const size_t n = (size_t)1 << log_n;
-        const bool inverse = (variant & 1) != 0;
+        const bool inverse = (variant & 1) != 0 || variant == 4;
         fe w = host_root_of_unity(log_n);
         if (inverse) w = Fr::invert(w);
-        const fe scale = inverse ? host_domain_inverse(log_n) : Fr::one();
+        const fe scale = (variant & 1) != 0 ? host_domain_inverse(log_n) : Fr::one();
         const unsigned lo_count = 1u << LO_TABLE_LOG, hi_count = (unsigned)(n >> LO_TABLE_LOG);
         fe *lo = nullptr, *hi = nullptr, *rf = nullptr, *cf = nullptr, *M = nullptr;
         BBG_CHECK(bbg_rt::dev_alloc((void**)&lo, (size_t)lo_count * 32));
@@ -668,9 +703,88 @@ int ntt_release_tables()
     return 0;
 }
 
+namespace
+{
+// n = 2^23 .. 2^28: outer pass over columns of length N0 = 2^L0, then the two-pass transform of size M = n / N0 on each of
+// the N0 contiguous blocks, the last pass writing block i0's output u to i0 + N0 u.  coeffs -> scratch -> scratch2 -> coeffs.
+int ntt_three_pass(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, bool inverse, bool coset, bool with_constant, const fe& k,
+                   cudaStream_t st)
+{
+    const size_t n = (size_t)1 << log_n;
+    int L0, LM;
+    split(log_n, L0, LM); // outer length 2^L0, inner size 2^LM (12 .. 22)
+    int L1, L2;
+    split((unsigned)LM, L1, L2);
+    const size_t M = (size_t)1 << LM;
+    BBG_CHECK(g_tables.scratch.ensure(2 * n * 32));
+    fe* s1 = (fe*)g_tables.scratch.p;
+    fe* s2 = s1 + n;
+    const fe *g_lo = nullptr, *g_hi = nullptr;
+    if (coset)
+    {
+        BBG_CHECK(get_vec(log_n, inverse ? VEC_GINV_LO : VEC_G_LO, st, &g_lo));
+        BBG_CHECK(get_vec(log_n, inverse ? VEC_GINV_HI : VEC_G_HI, st, &g_hi));
+    }
+    const int scale_grid = 8 * bbg_rt::num_sms();
+    for (size_t poly = 0; poly < batch; ++poly)
+    {
+        fe* x = (fe*)d_coeffs + poly * stride;
+        if (coset && !inverse)
+        {
+            // scale_by_generator (polynomial_arithmetic.cpp:81-102): x[j] *= k g^j before the transform
+            BBG_LAUNCH_NOSYNC(scale_powers_kernel, dim3((unsigned)scale_grid), dim3(256), st, x, g_lo, g_hi, LO_TABLE_LOG, with_constant ? k : Fr::one(), n);
+            ++g_ntt_launches;
+        }
+        PassParams o;
+        o.src = x;
+        o.dst = s1;
+        o.batch_stride = n;
+        o.log_n = (int)log_n;
+        o.num_tiles = (int)(n >> TILE_LOG);
+        o.total_work = o.num_tiles;
+        o.vec = nullptr;
+        o.has_post_const = 0;
+        o.post_const = Fr::one();
+        o.scatter_shift = 0;
+        BBG_CHECK(get_sub_tw(L0, inverse, st, &o.sub_tw));
+        BBG_CHECK(get_matrix(log_n, inverse ? 1 : 0, st, &o.mat)); // w_n^(+-i0 j) (x 1/n for the inverse)
+        BBG_CHECK(launch_pass<true>(L0, o, st));
+        PassParams a = o;
+        a.src = s1;
+        a.dst = s2;
+        a.batch_stride = M;
+        a.log_n = LM;
+        a.num_tiles = (int)(M >> TILE_LOG);
+        a.total_work = a.num_tiles << L0;
+        BBG_CHECK(get_sub_tw(L1, inverse, st, &a.sub_tw));
+        BBG_CHECK(get_matrix((unsigned)LM, inverse ? 4 : 0, st, &a.mat));
+        BBG_CHECK(launch_pass<true>(L1, a, st));
+        PassParams b = a;
+        b.src = s2;
+        b.dst = x;
+        b.mat = nullptr;
+        b.scatter_shift = L0;
+        BBG_CHECK(get_sub_tw(L2, inverse, st, &b.sub_tw));
+        if (with_constant && !coset)
+        {
+            b.has_post_const = 1; // fft / ifft_with_constant (:279-285, :301-309)
+            b.post_const = k;
+        }
+        BBG_CHECK(launch_pass<false>(L2, b, st));
+        if (coset && inverse)
+        {
+            // coset_ifft (:311-315): x[i] *= g^-i after the inverse transform
+            BBG_LAUNCH_NOSYNC(scale_powers_kernel, dim3((unsigned)scale_grid), dim3(256), st, x, g_lo, g_hi, LO_TABLE_LOG, Fr::one(), n);
+            ++g_ntt_launches;
+        }
+    }
+    return bbg_rt::last_error();
+}
+} // namespace
+
 int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int op, const uint64_t* constant, cudaStream_t st)
 {
-    if (log_n < 1 || log_n > 2 * (unsigned)TILE_LOG) return 1002; // n = 2 .. 2^22
+    if (log_n < 1 || log_n > 28) return 1002; // n = 2 .. 2^28 (the two-adicity of the field, fr.hpp:59-63)
     if (op < OP_FFT || op > OP_COSET_FFT_WITH_CONSTANT) return 1003;
     if (batch == 0) return 0;
     const bool inverse = (op == OP_IFFT || op == OP_COSET_IFFT || op == OP_IFFT_WITH_CONSTANT);
@@ -732,6 +846,8 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
         return bbg_rt::last_error();
     }
 
+    if (log_n > 2 * (unsigned)TILE_LOG) return ntt_three_pass(d_coeffs, stride, batch, log_n, inverse, coset, with_constant, k, st);
+
     int L1, L2;
     split(log_n, L1, L2);
     BBG_CHECK(g_tables.scratch.ensure(batch * n * 32));
@@ -745,6 +861,7 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
     a.vec = nullptr;
     a.has_post_const = 0;
     a.post_const = Fr::one();
+    a.scatter_shift = 0;
     b = a;
     // pass A writes polynomial i at scratch + i * n; pass B reads it back from there
     b.src = (const fe*)g_tables.scratch.p;

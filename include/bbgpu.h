@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BBG_E_BAD_SIZE 1002      /* NTT: log2_n outside [1, 22] */
+#define BBG_E_BAD_SIZE 1002      /* NTT: log2_n outside [1, 28] */
 #define BBG_E_BAD_OP 1003
 #define BBG_E_NULL_CONSTANT 1004
 #define BBG_E_NOT_INITIALISED 1005

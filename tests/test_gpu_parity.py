@@ -79,6 +79,30 @@ def test_ntt_large_vs_compiled_reference(lib, log_n):
         assert (got == ref_ntt(H.NTT_OPS[name], x, k)).all(), (log_n, name)
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("log_n,ops", [(23, list(H.NTT_OPS)), (24, ["fft", "ifft", "coset_fft", "coset_ifft"]), (25, ["coset_fft", "ifft"])])
+def test_ntt_three_pass_sizes_vs_compiled_reference(lib, log_n, ops):
+    """n > 2^22 (up to the field's 2^28 two-adicity): outer split + two-pass blocks, three HBM passes.  A circuit of
+    2^21 .. 2^23 gates needs these for its 4n domain."""
+    ref_threads_pow2()
+    n = 1 << log_n
+    x = H.random_scalars_mont(log_n, n)
+    x[1] = H.to_limbs(H.from_limbs(x[1]) + H.FR_MODULUS)  # lazily reduced input
+    k = H.random_scalars_mont(9, 1)[0]
+    for name in ops:
+        got = lib.ntt(name, x.copy(), k)
+        assert (got == ref_ntt(H.NTT_OPS[name], x, k)).all(), (log_n, name)
+
+
+def test_ntt_three_pass_round_trip_2p26(lib):
+    """2^26 elements (2 GiB): round trips only (the CPU reference would take minutes)."""
+    n = 1 << 26
+    x = H.random_scalars_mont(26, n)
+    fx = lib.ntt("coset_fft", x.copy())
+    assert not (fx[:64] == x[:64]).all()
+    assert (lib.ntt("coset_ifft", fx) == x).all()
+
+
 @pytest.mark.parametrize("log_n", [20, 22])
 def test_ntt_properties_full_size(lib, log_n):
     """Round trips, linearity and canonical outputs at the BASELINE sizes (no reference needed)."""
