@@ -685,8 +685,9 @@ static int build_pow_table(Prover* p, unsigned log_size, fe*& cursor, PowTable* 
 
 int create(unsigned log_n, Prover** out)
 {
-    // the 4n domain has to fit the NTT (<= 2^22) and every domain needs at least 4 points for the Z(X w) index shifts
-    if (log_n < 2 || log_n > 20) return 1002;
+    // every domain needs at least 4 points for the Z(X w) index shifts; above 2^23 gates the arena (86 n field elements)
+    // and the 32-bit element indices of the 4n passes would need another look
+    if (log_n < 2 || log_n > 23) return 1002;
     Prover* p = new Prover();
     p->log_n = log_n;
     p->n = (size_t)1 << log_n;
@@ -694,7 +695,8 @@ int create(unsigned log_n, Prover** out)
     const unsigned run_aggs = (unsigned)((n + ZRUN - 1) / ZRUN);
     p->aggs_stride = (run_aggs + 7) & ~7u;
     p->partial_stride = (unsigned)((4 * n + EVAL_SPAN - 1) / EVAL_SPAN + 8);
-    const size_t pow_elems = 3 * ((size_t)2 << 11) + 64;
+    size_t pow_elems = 64;
+    for (unsigned lg = log_n; lg <= log_n + 2; ++lg) pow_elems += ((size_t)1 << (lg < 11 ? lg : 11)) + (lg > 11 ? (size_t)1 << (lg - 11) : 0);
     // element counts, in the order of the header comment
     const size_t counts[] = { 3 * n, 3 * n, 12 * n, 3 * n, 12 * n, n, 4 * n, MAX_SELECTORS * n, 18 * n, 2 * n, 4 * n, 2 * n, n, 2 * n,
                               2 * (size_t)p->aggs_stride, (size_t)MAX_EVAL_JOBS * p->partial_stride, MAX_EVAL_JOBS, pow_elems, 8 * n };

@@ -68,7 +68,7 @@ void init_library()
     ready = true;
 }
 
-// one device-side prover per circuit size, kept for the life of the process (2.1 GB of HBM at n = 2^20)
+// one device-side prover per circuit size, kept for the life of the process (2.9 GB of HBM at n = 2^20)
 bbg_plonk_prover* device_prover(size_t log2_n)
 {
     static bbg_plonk_prover* cached = nullptr;
@@ -163,7 +163,7 @@ plonk_proof Prover::construct_proof()
         needs_w_o_shifted |= widgets[i]->version.has_dependency(WidgetVersionControl::Dependencies::REQUIRES_W_O_SHIFTED);
     }
     const char* mode = getenv("BBG_PLONK_RESIDENT");
-    const bool resident = known && !needs_w_l_shifted && !needs_w_r_shifted && n >= 4 && n <= ((size_t)1 << 20) && (n & (n - 1)) == 0 &&
+    const bool resident = known && !needs_w_l_shifted && !needs_w_r_shifted && n >= 4 && n <= ((size_t)1 << 23) && (n & (n - 1)) == 0 &&
                           !(mode != nullptr && mode[0] == '0') && w_l.get_size() >= n && w_r.get_size() >= n && w_o.get_size() >= n &&
                           sigma_1_mapping.size() >= n && sigma_2_mapping.size() >= n && sigma_3_mapping.size() >= n;
     if (!resident) return bbg_shim::reference_construct_proof(*this);

@@ -117,7 +117,7 @@ int bbg_g1_generate_multiples_dev(const uint64_t start[4], const uint64_t step[4
  * uploaded once per proof, every polynomial of the proof stays in HBM, and only commitments (12 limbs, the same
  * normalised form as bbg_msm_g1) and evaluations (4 limbs, canonical) come back.  The Fiat-Shamir transcript stays
  * with the caller (challenge.hpp), which feeds the challenges back in between rounds.
- * Host shim: barretenberg_b200/shim/prover_gpu.cpp.  n = 2^log2_n gates, 2 <= log2_n <= 20. */
+ * Host shim: barretenberg_b200/shim/prover_gpu.cpp.  n = 2^log2_n gates, 2 <= log2_n <= 23. */
 typedef struct bbg_plonk_prover bbg_plonk_prover;
 int bbg_plonk_create(unsigned log2_n, bbg_plonk_prover** out);
 int bbg_plonk_destroy(bbg_plonk_prover* p);
