@@ -198,8 +198,9 @@ __global__ void pad_copy_kernel(fe* dst, const fe* src, unsigned n_src, unsigned
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += gridDim.x * blockDim.x)
         store_fe(d + i, i < n_src ? load_fe(s + i) : Fr::zero());
 }
-// prover.cpp:246-262: s4[b] = beta sigma_b(X) + w_b(X) + gamma in coefficient form, zero padded to 4n
-__global__ void sigma_combine_pad_kernel(fe* s4, const fe* sigma_coef, const fe* w_coef, fe gamma, unsigned n, unsigned n4)
+// prover.cpp:246-262: s4[b] = beta sigma_b(X) + w_b(X) + gamma in coefficient form, zero padded to 4n (the reference scales
+// sigma by beta inside its ifft; here the coefficient form is a cached circuit constant and beta is applied in this pass)
+__global__ void sigma_combine_pad_kernel(fe* s4, const fe* sigma_coef, const fe* w_coef, fe beta, fe gamma, unsigned n, unsigned n4)
 {
     const fe* s = sigma_coef + (size_t)blockIdx.y * n;
     const fe* w = w_coef + (size_t)blockIdx.y * n;
@@ -209,7 +210,7 @@ __global__ void sigma_combine_pad_kernel(fe* s4, const fe* sigma_coef, const fe*
         fe v = Fr::zero();
         if (i < n)
         {
-            v = Fr::add(load_fe(s + i), load_fe(w + i));
+            v = Fr::add(Fr::mul(load_fe(s + i), beta), load_fe(w + i)); // sigma_coef is kept unscaled (proving-key cache)
             if (i == 0) v = Fr::add(v, gamma);
         }
         store_fe(d + i, v);
@@ -256,7 +257,8 @@ template <bool DIVIDE> __global__ void quotient_large_kernel(fe* q, const fe* s4
 // prover.cpp:325-391 (the two L_1 boundary terms), arithmetic_widget.cpp:60-97 (gate identity) and the division by
 // Z_H*(X) on the mid domain, one pass over i < 2n (aZ = alpha Z: z4 was transformed with the constant alpha):
 //   q[i] = ( (aZ(x w) - a) a L1[i+4] + (aZ(x) - a) a^2 L1[i] + qm wl wr + ql wl + qr wr + qo wo + qc ) (x - w^(n-1)) / (x^n - 1)
-__global__ void quotient_mid_kernel(fe* q, const fe* z4, const fe* l1, const fe* w4, const fe* q2, PowTable mid, QuotientConsts c, unsigned n2)
+__global__ void quotient_mid_kernel(fe* q, const fe* z4, const fe* l1, const fe* w4, const fe* q2, PowTable mid, QuotientConsts c, fe alpha_base,
+                                    unsigned n2)
 {
     const unsigned n4 = 2 * n2, mask2 = n2 - 1, mask4 = n4 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
@@ -271,6 +273,7 @@ __global__ void quotient_mid_kernel(fe* q, const fe* z4, const fe* l1, const fe*
         fe b = Fr::mul(wr, load_fe(q2 + 2 * (size_t)n2 + i));
         b = Fr::add(b, Fr::mul(wo, load_fe(q2 + 3 * (size_t)n2 + i)));
         a = Fr::add(Fr::add(a, b), load_fe(q2 + 4 * (size_t)n2 + i));
+        a = Fr::mul(a, alpha_base); // the selectors' coset evaluations are cached unscaled
         fe v = Fr::add(Fr::add(t4, t6), a);
         v = Fr::mul(v, c.vinv[i & 1]);
         const fe x = Fr::mul(root_pow(mid, i), c.g);
@@ -294,7 +297,7 @@ __global__ void quotient_mid_base_kernel(fe* q, const fe* z4, const fe* l1, Quot
     }
 }
 // arithmetic_widget.cpp:80-97
-__global__ void arith_mid_add_kernel(fe* q, const fe* w4, const fe* q2, unsigned n2)
+__global__ void arith_mid_add_kernel(fe* q, const fe* w4, const fe* q2, fe scale, unsigned n2)
 {
     const unsigned n4 = 2 * n2;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
@@ -305,11 +308,15 @@ __global__ void arith_mid_add_kernel(fe* q, const fe* w4, const fe* q2, unsigned
         fe b = Fr::mul(wr, load_fe(q2 + 2 * (size_t)n2 + i));
         b = Fr::add(b, Fr::mul(wo, load_fe(q2 + 3 * (size_t)n2 + i)));
         a = Fr::add(Fr::add(a, b), load_fe(q2 + 4 * (size_t)n2 + i));
-        store_fe(q + i, Fr::add(load_fe(q + i), a));
+        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(a, scale)));
     }
 }
-// bool_widget.cpp:76-97: (w^2 - w) q_b for the three wires (the alpha powers ride on the selector transforms)
-__global__ void bool_mid_add_kernel(fe* q, const fe* w4, const fe* q2, unsigned n2)
+// bool_widget.cpp:76-97: (w^2 - w) q_b alpha_base alpha^k for the three wires
+struct Scale3
+{
+    fe s[3];
+};
+__global__ void bool_mid_add_kernel(fe* q, const fe* w4, const fe* q2, Scale3 scale, unsigned n2)
 {
     const unsigned n4 = 2 * n2;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
@@ -319,20 +326,20 @@ __global__ void bool_mid_add_kernel(fe* q, const fe* w4, const fe* q2, unsigned 
         for (int k = 0; k < 3; ++k)
         {
             const fe w = load_fe(w4 + (size_t)k * n4 + 2 * i);
-            acc = Fr::add(acc, Fr::mul(Fr::sub(Fr::sqr(w), w), load_fe(q2 + (size_t)k * n2 + i)));
+            acc = Fr::add(acc, Fr::mul(Fr::mul(Fr::sub(Fr::sqr(w), w), load_fe(q2 + (size_t)k * n2 + i)), scale.s[k]));
         }
         store_fe(q + i, acc);
     }
 }
 // sequential_widget.cpp:56-59: w_o(X w) q_o_next
-__global__ void seq_mid_add_kernel(fe* q, const fe* wo4, const fe* q2, unsigned n2)
+__global__ void seq_mid_add_kernel(fe* q, const fe* wo4, const fe* q2, fe scale, unsigned n2)
 {
     const unsigned mask4 = 2 * n2 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
-        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(load_fe(wo4 + ((2 * i + 4) & mask4)), load_fe(q2 + i))));
+        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(Fr::mul(load_fe(wo4 + ((2 * i + 4) & mask4)), load_fe(q2 + i)), scale)));
 }
 // mimc_widget.cpp:68-86 on the large domain: T0 = w_o + w_l + q_c;  ((T0^3 - w_r) + (w_r^2 T0 - w_o(X w)) alpha) q_mimc
-__global__ void mimc_large_add_kernel(fe* q, const fe* w4, const fe* q4, fe alpha, unsigned n4)
+__global__ void mimc_large_add_kernel(fe* q, const fe* w4, const fe* q4, fe alpha, fe scale, unsigned n4)
 {
     const unsigned mask = n4 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
@@ -342,7 +349,7 @@ __global__ void mimc_large_add_kernel(fe* q, const fe* w4, const fe* q4, fe alph
         fe t1 = Fr::sub(Fr::mul(Fr::sqr(t0), t0), wr);
         fe t2 = Fr::sub(Fr::mul(Fr::sqr(wr), t0), load_fe(w4 + 2 * (size_t)n4 + ((i + 4) & mask)));
         t1 = Fr::add(t1, Fr::mul(t2, alpha));
-        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(t1, load_fe(q4 + i))));
+        store_fe(q + i, Fr::add(load_fe(q + i), Fr::mul(Fr::mul(t1, load_fe(q4 + i)), scale)));
     }
 }
 // polynomial_arithmetic.cpp:478-560 on its own: v[i] *= (g w^i - w_n^(n-1)) / ((g w^i)^n - 1)
@@ -461,8 +468,8 @@ __global__ void opening_combine_kernel(fe* opening, fe* shifted, const fe* quot,
         fe t8 = Fr::add(Fr::mul(load_fe(quot + (size_t)n + i), c.z_pow_n), Fr::mul(load_fe(quot + 2 * (size_t)n + i), c.z_pow_2n));
         fe t1 = Fr::add(Fr::mul(load_fe(r + i), c.nu[0]), Fr::mul(load_fe(w_coef + i), c.nu[1]));
         fe t3 = Fr::add(Fr::mul(load_fe(w_coef + (size_t)n + i), c.nu[2]), Fr::mul(load_fe(w_coef + 2 * (size_t)n + i), c.nu[3]));
+        // (the reference holds beta sigma and multiplies by beta^-1 here, :586; sigma is kept unscaled)
         fe t4 = Fr::add(Fr::mul(load_fe(sigma + i), c.nu[4]), Fr::mul(load_fe(sigma + (size_t)n + i), c.nu[5]));
-        t4 = Fr::mul(t4, c.beta_inv);
         fe v = Fr::add(Fr::add(t3, t1), Fr::add(t4, t8));
         store_fe(opening + i, Fr::add(v, load_fe(quot + i)));
         store_fe(shifted + i, Fr::mul(load_fe(z + i), c.nu[6]));
@@ -616,7 +623,7 @@ struct Prover
     size_t n = 0;
     void* arena = nullptr;
     fe *w_lag = nullptr, *w_coef = nullptr, *w4 = nullptr;
-    fe *sigma = nullptr, *s4 = nullptr;
+    fe *sigma = nullptr, *sigma_lag = nullptr, *s4 = nullptr;
     fe *z = nullptr, *z4 = nullptr;
     fe *q = nullptr, *q2 = nullptr, *q4 = nullptr, *l1 = nullptr;
     // widget list of the circuit (prover.hpp:60), in the prover's order; selectors are stored back to back in q[]
@@ -631,7 +638,17 @@ struct Prover
     unsigned aggs_stride = 0, partial_stride = 0;
     const void* d_srs = nullptr;
     bool have_witness = false, have_perm = false, have_selectors = false, tables_ready = false;
-    bool sigma_ready = false; // sigma[] holds this proof's Lagrange values
+    bool sigma_ready = false; // sigma_lag[] holds this proof's Lagrange values
+    // Proving-key cache: the permutation polynomials (Lagrange + coefficient form) and the selectors (coefficient form +
+    // coset evaluations, all unscaled) are circuit constants.  Every proof the helper thread hashes the host buffers it
+    // was handed; when the hash equals the one the device copies were built from, the copies and the 13 transforms of
+    // rounds 2-3 that only depend on them are skipped.  BBG_PLONK_KEY_CACHE=0 switches this off.
+    bool key_cache_enabled = true;
+    bool key_valid = false;          // device constants are complete and belong to key_hash
+    uint64_t key_hash[2] = { 0, 0 };
+    uint64_t pending_hash[2] = { 0, 0 };
+    bool constants_cached = false;   // this proof: the helper thread found the constants unchanged
+    fe beta{};                       // this proof's beta (sigma is stored unscaled)
     bool l1_ready = false;    // l1[] depends on the circuit size only: computed once
     // this proof's inputs, in the order the rounds need them: w_l, w_r, w_o, the three mappings, the five selectors
     enum { ITEM_WL = 0, ITEM_WR, ITEM_WO, ITEM_MAP, ITEM_SEL, NUM_ITEMS };
@@ -699,7 +716,7 @@ int create(unsigned log_n, Prover** out)
     for (unsigned lg = log_n; lg <= log_n + 2; ++lg) pow_elems += ((size_t)1 << (lg < 11 ? lg : 11)) + (lg > 11 ? (size_t)1 << (lg - 11) : 0);
     // element counts, in the order of the header comment
     const size_t counts[] = { 3 * n, 3 * n, 12 * n, 3 * n, 12 * n, n, 4 * n, MAX_SELECTORS * n, 18 * n, 2 * n, 4 * n, 2 * n, n, 2 * n,
-                              2 * (size_t)p->aggs_stride, (size_t)MAX_EVAL_JOBS * p->partial_stride, MAX_EVAL_JOBS, pow_elems, 8 * n };
+                              2 * (size_t)p->aggs_stride, (size_t)MAX_EVAL_JOBS * p->partial_stride, MAX_EVAL_JOBS, pow_elems, 8 * n, 3 * n };
     size_t total = 0;
     for (size_t c : counts) total += (c + 7) & ~(size_t)7;
     const size_t bytes = total * 32 + 3 * n * 4 + 256; // (2.9 GB at n = 2^20)
@@ -730,6 +747,11 @@ int create(unsigned log_n, Prover** out)
     p->eval_out = take(counts[16]);
     p->pow_mem = take(counts[17]);
     p->q4 = take(counts[18]);
+    p->sigma_lag = take(counts[19]);
+    {
+        const char* e = getenv("BBG_PLONK_KEY_CACHE");
+        p->key_cache_enabled = !(e != nullptr && e[0] == '0');
+    }
     p->map = (uint32_t*)cur;
 #ifndef BBG_EMULATE
     cudaGetDevice(&p->device);
@@ -827,6 +849,90 @@ int set_widgets(Prover* p, const int* kinds, int count, const uint64_t* const* s
     return 0;
 }
 
+// 128-bit fingerprint of the circuit constants (mappings, widget kinds, selectors): four multiply-xorshift lanes per slice,
+// slices hashed by a few threads and folded in order.  Memory-bound (~170 MB at n = 2^20, a few ms behind round 1).
+static void hash_slice(const uint64_t* w, size_t words, uint64_t out[2])
+{
+    uint64_t h0 = 0x9E3779B97F4A7C15ULL, h1 = 0xC2B2AE3D27D4EB4FULL, h2 = 0x165667B19E3779F9ULL, h3 = 0x27D4EB2F165667C5ULL;
+    size_t i = 0;
+    for (; i + 4 <= words; i += 4)
+    {
+        h0 = (h0 ^ w[i]) * 0xFF51AFD7ED558CCDULL;
+        h0 ^= h0 >> 29;
+        h1 = (h1 ^ w[i + 1]) * 0xC4CEB9FE1A85EC53ULL;
+        h1 ^= h1 >> 31;
+        h2 = (h2 ^ w[i + 2]) * 0x9FB21C651E98DF25ULL;
+        h2 ^= h2 >> 30;
+        h3 = (h3 ^ w[i + 3]) * 0xD6E8FEB86659FD93ULL;
+        h3 ^= h3 >> 32;
+    }
+    for (; i < words; ++i)
+    {
+        h0 = (h0 ^ w[i]) * 0xFF51AFD7ED558CCDULL;
+        h0 ^= h0 >> 29;
+    }
+    out[0] = (h0 ^ (h1 << 1 | h1 >> 63)) * 0x9E3779B97F4A7C15ULL ^ h2;
+    out[1] = (h2 ^ (h3 << 7 | h3 >> 57)) * 0xC2B2AE3D27D4EB4FULL ^ h0 ^ h1;
+}
+static void fold_hash(uint64_t acc[2], const uint64_t h[2])
+{
+    acc[0] = (acc[0] ^ h[0]) * 0xFF51AFD7ED558CCDULL;
+    acc[0] ^= acc[0] >> 32;
+    acc[1] = (acc[1] ^ h[1] ^ acc[0]) * 0xC4CEB9FE1A85EC53ULL;
+    acc[1] ^= acc[1] >> 29;
+}
+static void hash_constants(const Prover* p, uint64_t out[2])
+{
+    struct Part
+    {
+        const uint64_t* w;
+        size_t words;
+    };
+    std::vector<Part> parts;
+    const size_t slice_words = (size_t)1 << 20; // 8 MiB
+    auto add = [&](const void* ptr, size_t bytes) {
+        const uint64_t* w = (const uint64_t*)ptr;
+        size_t words = bytes / 8;
+        while (words > 0)
+        {
+            const size_t take = words < slice_words ? words : slice_words;
+            parts.push_back({ w, take });
+            w += take;
+            words -= take;
+        }
+    };
+    for (int k = 0; k < 3; ++k) add(p->host_src[3 + k], p->n * 4);
+    for (int k = 0; k < p->num_selectors; ++k) add(p->host_src[6 + k], p->n * 32);
+    std::vector<uint64_t> h(2 * parts.size());
+#ifndef BBG_EMULATE
+    const unsigned hc = std::thread::hardware_concurrency();
+    const int threads = hc >= 16 ? 8 : (hc >= 4 ? 4 : 1);
+    std::atomic<size_t> next{ 0 };
+    auto work = [&]() {
+        for (;;)
+        {
+            const size_t i = next.fetch_add(1);
+            if (i >= parts.size()) break;
+            hash_slice(parts[i].w, parts[i].words, &h[2 * i]);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+#else
+    for (size_t i = 0; i < parts.size(); ++i) hash_slice(parts[i].w, parts[i].words, &h[2 * i]);
+#endif
+    out[0] = 0x243F6A8885A308D3ULL ^ (uint64_t)p->n;
+    out[1] = 0x13198A2E03707344ULL ^ (uint64_t)p->num_selectors;
+    for (int w = 0; w < p->num_widgets; ++w)
+    {
+        const uint64_t kind[2] = { (uint64_t)p->widget_kind[w] + 1, (uint64_t)w };
+        fold_hash(out, kind);
+    }
+    for (size_t i = 0; i < parts.size(); ++i) fold_hash(out, &h[2 * i]);
+}
+
 // queue every input copy (helper thread; synchronous in the emulation build)
 static int start_uploads(Prover* p, cudaStream_t st)
 {
@@ -854,16 +960,38 @@ static int start_uploads(Prover* p, cudaStream_t st)
             copy(p->w_lag + (size_t)k * n, p->host_src[k], n * 32);
             done(Prover::ITEM_WL + k);
         }
-        for (int k = 0; k < 3; ++k) copy(p->map + (size_t)k * n, p->host_src[3 + k], n * 4);
+        // circuit constants: unchanged since the device copies were built?
+        bool cached = false;
+        if (p->key_cache_enabled)
+        {
+            hash_constants(p, p->pending_hash);
+            cached = p->key_valid && p->pending_hash[0] == p->key_hash[0] && p->pending_hash[1] == p->key_hash[1];
+        }
+        p->constants_cached = cached;
+        if (!cached) p->key_valid = false; // the device constants are about to be overwritten
+        if (!cached)
+            for (int k = 0; k < 3; ++k) copy(p->map + (size_t)k * n, p->host_src[3 + k], n * 4);
         done(Prover::ITEM_MAP);
-        for (int k = 0; k < p->num_selectors; ++k) copy(p->q + (size_t)k * n, p->host_src[6 + k], n * 32);
+        if (!cached)
+            for (int k = 0; k < p->num_selectors; ++k) copy(p->q + (size_t)k * n, p->host_src[6 + k], n * 32);
         done(Prover::ITEM_SEL);
         p->upload_error = e;
     });
 #else
     for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->w_lag + (size_t)k * n, p->host_src[k], n * 32, st));
-    for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * n, p->host_src[3 + k], n * 4, st));
-    for (int k = 0; k < p->num_selectors; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * n, p->host_src[6 + k], n * 32, st));
+    bool cached = false;
+    if (p->key_cache_enabled)
+    {
+        hash_constants(p, p->pending_hash);
+        cached = p->key_valid && p->pending_hash[0] == p->key_hash[0] && p->pending_hash[1] == p->key_hash[1];
+    }
+    p->constants_cached = cached;
+    if (!cached)
+    {
+        p->key_valid = false;
+        for (int k = 0; k < 3; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->map + (size_t)k * n, p->host_src[3 + k], n * 4, st));
+        for (int k = 0; k < p->num_selectors; ++k) BBG_CHECK(bbg_hostcopy::h2d(p->q + (size_t)k * n, p->host_src[6 + k], n * 32, st));
+    }
 #endif
     return 0;
 }
@@ -949,12 +1077,16 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
     {
         bbg_prof::Scope prof(bbg_prof::PLONK_ELEMENTWISE, st);
         // permutation.hpp:13-88 (prover.cpp:659-661)
-        BBG_LAUNCH_NOSYNC(sigma_from_mapping_kernel, dim3(grid_for(3 * n, 256)), dim3(256), st, p->sigma, (const uint32_t*)p->map, p->pow_small, (unsigned)n,
-                          (unsigned)(3 * n));
-        ++g_plonk_launches;
+        if (!p->constants_cached)
+        {
+            BBG_LAUNCH_NOSYNC(sigma_from_mapping_kernel, dim3(grid_for(3 * n, 256)), dim3(256), st, p->sigma_lag, (const uint32_t*)p->map, p->pow_small,
+                              (unsigned)n, (unsigned)(3 * n));
+            ++g_plonk_launches;
+        }
         p->sigma_ready = true;
-        BBG_LAUNCH_NOSYNC(z_terms_kernel, dim3(grid_for(n, 128)), dim3(128), st, num, den, (const fe*)p->w_lag, (const fe*)p->sigma, p->pow_small, beta, gamma,
-                          (unsigned)n);
+        p->beta = beta;
+        BBG_LAUNCH_NOSYNC(z_terms_kernel, dim3(grid_for(n, 128)), dim3(128), st, num, den, (const fe*)p->w_lag, (const fe*)p->sigma_lag, p->pow_small, beta,
+                          gamma, (unsigned)n);
     }
     const unsigned runs = (unsigned)((n + ZRUN - 1) / ZRUN);
     bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::PLONK_SCAN, st);
@@ -983,10 +1115,16 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->w4, (const fe*)p->w_coef, (unsigned)n, (unsigned)n4, n, n4);
     BBG_CHECK(ntt_device(p->w4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
     tr.mark("w4 coset_fft", st);
-    // sigma: Lagrange -> beta-scaled coefficients (:246-248), then beta sigma + w + gamma on the 4n coset (:252-273)
-    BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT_WITH_CONSTANT, beta_, st));
-    BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, gamma, (unsigned)n,
-                      (unsigned)n4);
+    // sigma: Lagrange -> coefficients (:246-248; a circuit constant, kept unscaled), then beta sigma + w + gamma on the
+    // 4n coset (:252-273)
+    const bool cached = p->constants_cached;
+    if (!cached)
+    {
+        BBG_CHECK(bbg_rt::d2d(p->sigma, p->sigma_lag, 3 * n * 32, st));
+        BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT, nullptr, st));
+    }
+    BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, beta, gamma,
+                      (unsigned)n, (unsigned)n4);
     BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
     tr.mark("sigma ifft + s4 coset_fft", st);
     // alpha Z on the 4n coset (:275)
@@ -998,8 +1136,7 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     tr.mark("z4 + l1", st);
     // selectors: Lagrange -> coefficients (arithmetic_widget.cpp:62-66 and the other widgets' first lines)
     const int S = p->num_selectors;
-    BBG_CHECK(ntt_device(p->q, n, (size_t)S, p->log_n, OP_IFFT, nullptr, st));
-    ++g_plonk_launches;
+    if (!cached) BBG_CHECK(ntt_device(p->q, n, (size_t)S, p->log_n, OP_IFFT, nullptr, st));
 
     QuotientConsts c;
     c.g = gen_k1();
@@ -1024,26 +1161,27 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
             cur = Fr::reduce(Fr::mul(cur, ws));
         }
     };
-    // selector polynomial `sel` -> its coset evaluations on the 2n / 4n domain, scaled by `k` (null: unscaled)
-    auto to_coset = [&](fe* dst, int sel, int count, size_t size, unsigned log_size, const fe* k) -> int {
+    // selector polynomials sel .. sel + count - 1 -> their (unscaled) coset evaluations on the 2n / 4n domain: circuit
+    // constants, computed once per proving key; the widgets' alpha powers are applied in the passes that consume them
+    auto to_coset = [&](fe* dst, int sel, int count, size_t size, unsigned log_size) -> int {
+        if (cached) return 0;
         BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(size, 256), (unsigned)count), dim3(256), st, dst, (const fe*)(p->q + (size_t)sel * n), (unsigned)n,
                           (unsigned)size, n, size);
         ++g_plonk_launches;
-        return ntt_device(dst, size, (size_t)count, log_size, k != nullptr ? OP_COSET_FFT_WITH_CONSTANT : OP_COSET_FFT, k != nullptr ? (const uint64_t*)k->v : nullptr,
-                          st);
+        return ntt_device(dst, size, (size_t)count, log_size, OP_COSET_FFT, nullptr, st);
     };
     const bool standard = p->num_widgets == 1 && p->widget_kind[0] == WIDGET_ARITHMETIC;
     if (standard)
     {
         // StandardComposer circuits: the gate identity is fused into the mid-domain pass (arithmetic_widget.cpp:68-97)
-        BBG_CHECK(to_coset(p->q2, 0, 5, n2, p->log_n + 1, &alpha_base));
+        BBG_CHECK(to_coset(p->q2, 0, 5, n2, p->log_n + 1));
         tr.mark("selectors ifft + coset_fft", st);
         fill_vinv(2);
         BBG_LAUNCH_NOSYNC(quotient_large_kernel<true>, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->s4, (const fe*)p->w4,
                           (const fe*)p->z4, p->pow_large, c, (unsigned)n4);
         fill_vinv(1);
         BBG_LAUNCH_NOSYNC(quotient_mid_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->z4, (const fe*)p->l1, (const fe*)p->w4,
-                          (const fe*)p->q2, p->pow_mid, c, (unsigned)n2);
+                          (const fe*)p->q2, p->pow_mid, c, alpha_base, (unsigned)n2);
         g_plonk_launches += 2;
     }
     else
@@ -1062,37 +1200,40 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
             switch (p->widget_kind[w])
             {
             case WIDGET_ARITHMETIC: // arithmetic_widget.cpp:60-99
-                BBG_CHECK(to_coset(q2_cursor, sel, 5, n2, p->log_n + 1, &ab));
-                BBG_LAUNCH_NOSYNC(arith_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->w4, (const fe*)q2_cursor, (unsigned)n2);
+                BBG_CHECK(to_coset(q2_cursor, sel, 5, n2, p->log_n + 1));
+                BBG_LAUNCH_NOSYNC(arith_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->w4, (const fe*)q2_cursor, ab,
+                                  (unsigned)n2);
                 q2_cursor += 5 * n2;
                 ab = Fr::reduce(Fr::mul(ab, alpha));
                 break;
             case WIDGET_BOOL: // bool_widget.cpp:62-100
             {
+                Scale3 sc;
                 fe k = ab;
                 for (int j = 0; j < 3; ++j)
                 {
-                    BBG_CHECK(to_coset(q2_cursor + (size_t)j * n2, sel + j, 1, n2, p->log_n + 1, &k));
+                    sc.s[j] = k; // alpha_base, alpha_base alpha, alpha_base alpha^2 (bool_widget.cpp:72-74)
                     k = Fr::reduce(Fr::mul(k, alpha));
                 }
-                BBG_LAUNCH_NOSYNC(bool_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->w4, (const fe*)q2_cursor, (unsigned)n2);
+                BBG_CHECK(to_coset(q2_cursor, sel, 3, n2, p->log_n + 1));
+                BBG_LAUNCH_NOSYNC(bool_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)p->w4, (const fe*)q2_cursor, sc,
+                                  (unsigned)n2);
                 q2_cursor += 3 * n2;
                 ab = k; // alpha_base * alpha^3
                 break;
             }
             case WIDGET_MIMC: // mimc_widget.cpp:57-89
-                BBG_CHECK(to_coset(p->q4, sel, 1, n4, p->log_n + 2, &ab));
-                BBG_CHECK(to_coset(p->q4 + n4, sel + 1, 1, n4, p->log_n + 2, nullptr));
-                BBG_LAUNCH_NOSYNC(mimc_large_add_kernel, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->w4, (const fe*)p->q4, alpha,
+                BBG_CHECK(to_coset(p->q4, sel, 2, n4, p->log_n + 2));
+                BBG_LAUNCH_NOSYNC(mimc_large_add_kernel, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->w4, (const fe*)p->q4, alpha, ab,
                                   (unsigned)n4);
                 ab = Fr::reduce(Fr::mul(ab, c.alpha_sqr));
                 break;
             case WIDGET_SEQUENTIAL: // sequential_widget.cpp:47-62
             {
                 const fe old_alpha = Fr::reduce(Fr::mul(ab, Fr::invert(alpha)));
-                BBG_CHECK(to_coset(q2_cursor, sel, 1, n2, p->log_n + 1, &old_alpha));
+                BBG_CHECK(to_coset(q2_cursor, sel, 1, n2, p->log_n + 1));
                 BBG_LAUNCH_NOSYNC(seq_mid_add_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, (const fe*)(p->w4 + 2 * n4), (const fe*)q2_cursor,
-                                  (unsigned)n2);
+                                  old_alpha, (unsigned)n2);
                 q2_cursor += n2;
                 break;
             }
@@ -1105,6 +1246,13 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
         fill_vinv(1);
         BBG_LAUNCH_NOSYNC(divide_vanishing_kernel, dim3(grid_for(n2, 128)), dim3(128), st, p->quot_mid, p->pow_mid, c, 1u, (unsigned)n2);
         g_plonk_launches += 2;
+    }
+    if (!cached && p->key_cache_enabled)
+    {
+        // every device-side constant now belongs to the hash the helper thread computed for this proof
+        p->key_hash[0] = p->pending_hash[0];
+        p->key_hash[1] = p->pending_hash[1];
+        p->key_valid = true;
     }
     tr.mark("quotient kernels", st);
     BBG_CHECK(ntt_device(p->quot_mid, n2, 1, p->log_n + 1, OP_COSET_IFFT, nullptr, st));
@@ -1173,6 +1321,12 @@ int round_evaluations(Prover* p, const uint64_t* zeta_, const uint64_t* zeta_ome
     }
     uint64_t tmp[MAX_EVAL_JOBS * 4];
     BBG_CHECK(run_evals(p, jobs, count, tmp, st));
+    // sigma is stored unscaled: hand back [beta sigma_k](z) as the reference's prover holds it (:473-477 divide it out again)
+    for (int j = 3; j <= 4; ++j)
+    {
+        const fe v = Fr::mul_full(from_u64(tmp + 4 * j), p->beta);
+        memcpy(tmp + 4 * j, v.v, 32);
+    }
     memset(out, 0, 9 * 32);
     memcpy(out, tmp, 7 * 32);
     if (shifted_at >= 0) memcpy(out + 28, tmp + 4 * shifted_at, 32);
@@ -1193,6 +1347,7 @@ int round_linearise(Prover* p, const uint64_t* scalars /* (2 + selectors) x 4 */
     };
     term(p->z, scalars);
     term(p->sigma + 2 * n, scalars + 4);
+    t.c[1] = Fr::mul_full(t.c[1], p->beta); // s_1 is meant for beta sigma_3; sigma is stored unscaled
     bool first = true;
     for (int k = 0; k < p->num_selectors; ++k)
     {

@@ -41,9 +41,12 @@ def run(binary, log_gates, repeat=1, env=None, composer="standard"):
 
 
 @pytest.mark.parametrize("log_gates", [5, 8, 12, 14])  # 2^4 gives the recipe zero gates: the reference itself throws bad_alloc
-def test_prover_gpu_matches_cpu_reference(srs, log_gates):
+@pytest.mark.parametrize("repeat,env", [(1, {}), (2, {}), (2, {"BBG_PLONK_KEY_CACHE": "0"})])
+def test_prover_gpu_matches_cpu_reference(srs, log_gates, repeat, env):
+    """repeat 1: cold proving key; repeat 2: second proof after Prover::reset() with the circuit constants found unchanged
+    on the device (proving-key cache), or rebuilt when the cache is switched off"""
     cpu = run("prover_cpu", log_gates)
-    gpu = run("prover_gpu", log_gates, repeat=2)  # second proof after Prover::reset()
+    gpu = run("prover_gpu", log_gates, repeat=repeat, env=env)
     assert cpu["verified"] and gpu["verified"]
     assert gpu["n"] == cpu["n"]
     for k, v in cpu["proof"].items():
