@@ -275,8 +275,11 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT, 2) ntt_pas
     __syncthreads();
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x)
     {
-        const int tile = work % p.num_tiles;
-        const size_t b = (size_t)(work / p.num_tiles);
+        // polynomial-minor order: the CTAs in flight work on the same few tiles of all polynomials of the batch, so the
+        // inter-pass matrix tile (pass A; 128 MiB per 2^22 transform, more than L2 holds) is read from HBM once per batch
+        const int batch = p.total_work / p.num_tiles;
+        const int tile = work / batch;
+        const size_t b = (size_t)(work % batch);
         fe x[8];
         run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.scatter_shift ? p.dst + b : p.dst + b * p.batch_stride, tile, data, tw);
         NTT_SYNC(); // the last step's shared-memory reads finish before the next tile overwrites
