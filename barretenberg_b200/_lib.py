@@ -64,6 +64,8 @@ class Library:
         L.bbg_g1_generate_multiples_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.bbg_generate_pippenger_point_table_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.bbg_compute_lagrange_polynomial_fft.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
+        L.bbg_fr_domain_lookup_table.argtypes = [C.c_void_p, C.c_uint]
+        L.bbg_srs_from_transcript.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.bbg_profile_name.restype = C.c_char_p
         L.bbg_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         self.check(L.bbg_init(device))
@@ -214,6 +216,21 @@ class Library:
         out = np.zeros(12, dtype=np.uint64)
         self.check(self.lib.bbg_g1_fold_partials(p.ctypes.data_as(C.c_void_p), p.shape[0], out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def domain_lookup_table(self, log2_size):
+        """evaluation_domain::compute_lookup_table: (2 * size, 4) uint64, forward rounds then inverse rounds."""
+        out = np.zeros((2 << log2_size, 4), dtype=np.uint64)
+        self.check(self.lib.bbg_fr_domain_lookup_table(out.ctypes.data_as(C.c_void_p), log2_size))
+        return out
+
+    def srs_from_transcript(self, g1_bytes, n):
+        """The 2n-entry point table from the raw transcript bytes of points 1 .. n-1 (generator first); the returned array
+        is the host buffer the device copy is registered behind (keep it alive, srs_unregister() it when done)."""
+        raw = np.frombuffer(bytes(g1_bytes), dtype=np.uint8)
+        assert raw.size == 64 * (n - 1)
+        table = np.zeros((2 * n, 8), dtype=np.uint64)
+        self.check(self.lib.bbg_srs_from_transcript(raw.ctypes.data_as(C.c_void_p) if raw.size else None, n, table.ctypes.data_as(C.c_void_p)))
+        return table
 
     def generate_pippenger_point_table(self, points):
         p = _as_u64(points, (8,))

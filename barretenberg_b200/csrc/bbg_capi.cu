@@ -510,6 +510,61 @@ int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table
     return e;
 }
 
+// ---- prover construction helpers -----------------------------------------------
+int bbg_fr_domain_lookup_table(uint64_t* roots, unsigned log2_size)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (roots == nullptr) return BBG_E_BAD_ARGUMENT;
+    if (log2_size < 1 || log2_size > 28) return BBG_E_BAD_SIZE;
+    const size_t bytes = ((size_t)64) << log2_size;
+    BBG_CHECK(g_stage_coeffs.ensure(bytes));
+    BBG_CHECK(domain_lookup_table_device(g_stage_coeffs.p, log2_size, g_stream));
+    BBG_CHECK(bbg_hostcopy::d2h(roots, g_stage_coeffs.p, bytes, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+
+int bbg_srs_from_transcript(const uint8_t* g1_bytes, size_t n, uint64_t* table_2n)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (table_2n == nullptr || n == 0 || (g1_bytes == nullptr && n > 1)) return BBG_E_BAD_ARGUMENT;
+    // a table registered earlier behind the same host address is stale now
+    for (size_t i = 0; i < g_srs.size(); ++i)
+    {
+        if (g_srs[i].host_base == table_2n)
+        {
+            bbg_rt::sync(g_stream);
+            bbg_rt::dev_free(g_srs[i].d_table);
+            g_srs.erase(g_srs.begin() + (long)i);
+            break;
+        }
+    }
+    SrsEntry s;
+    s.host_base = table_2n;
+    s.n = n;
+    s.d_table = nullptr;
+    s.automatic = false;
+    BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
+    int e = 0;
+    if (n > 1)
+    {
+        e = g_stage_table.ensure((n - 1) * 64);
+        if (e == 0) e = bbg_hostcopy::h2d(g_stage_table.p, g1_bytes, (n - 1) * 64, g_stream);
+    }
+    if (e == 0) e = g1_table_from_transcript_device(g_stage_table.p, s.d_table, n, g_stream);
+    if (e == 0) e = bbg_hostcopy::d2h(table_2n, s.d_table, n * 128, g_stream);
+    if (e == 0) e = bbg_rt::sync(g_stream);
+    if (e != 0)
+    {
+        bbg_rt::dev_free(s.d_table);
+        return e;
+    }
+    s.fingerprint = table_fingerprint(table_2n, n);
+    g_srs.push_back(s); // the device copy IS the registered SRS: no second upload
+    return 0;
+}
+
 // ---- HBM-resident PLONK prover rounds (bbg_plonk.cu) -------------------------------------------------
 int bbg_plonk_create(unsigned log2_n, bbg_plonk_prover** out)
 {

@@ -41,6 +41,10 @@ int msm_release_workspace();
 size_t msm_launch_count();
 // d_points[i] = (start + i * step) * G (affine, canonical), i < n; start / step: Fr Montgomery limbs (host)
 int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* step_mont, void* d_points, size_t n, cudaStream_t stream);
+// raw transcript G1 bytes ((n - 1) x 64) -> the 2n-entry point table, generator first (io.hpp:157-182 + :131-140)
+int g1_table_from_transcript_device(const void* d_g1_bytes, void* d_table, size_t n, cudaStream_t stream);
+// evaluation_domain::compute_lookup_table (evaluation_domain.cpp:33-54, :172-178): 2 * 2^log_size elements on the device
+int domain_lookup_table_device(void* d_roots, unsigned log_size, cudaStream_t stream);
 // table[2i] = P_i, table[2i+1] = (beta x_i, -y_i) on device (generate_pippenger_point_table layout)
 int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cudaStream_t stream);
 } // namespace bbg

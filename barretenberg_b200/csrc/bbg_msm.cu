@@ -427,6 +427,46 @@ __global__ void endo_table_kernel(const fe* points, fe* table, size_t n)
     store_affine(table + 4 * i, p);
     store_affine(table + 4 * i + 2, G1::endo_table_entry(p));
 }
+// ---- SRS loader ------------------------------------------------------------------------------
+// io::read_transcript + read_g1_elements_from_buffer (io/io.hpp:76-98, :157-182) followed by
+// generate_pippenger_point_table (scalar_multiplication.cpp:131-140) in one pass over the raw transcript bytes:
+// monomials[0] = the G1 generator, monomials[i] = file point i - 1 (each coordinate: four 64-bit limbs, least significant
+// limb first, big-endian bytes inside a limb, plain value) -> Montgomery form -> table[2i] = P_i, table[2i+1] = (beta x_i, -y_i).
+BBG_D fe load_transcript_fq(const uint8_t* p)
+{
+    const uint4* q = (const uint4*)p;
+    const uint4 lo = q[0], hi = q[1];
+    const uint32_t w[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        // bswap64 of the limb (w[2k] low word, w[2k+1] high word as loaded on a little-endian machine)
+        r.v[2 * k] = __byte_perm(w[2 * k + 1], 0, 0x0123);
+        r.v[2 * k + 1] = __byte_perm(w[2 * k], 0, 0x0123);
+    }
+    return Fq::to_mont(r); // fq::__to_montgomery_form (field.hpp:224-232), canonical
+}
+__global__ void srs_from_transcript_kernel(const uint8_t* g1_bytes, fe* table, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_pt p;
+    if (i == 0)
+    {
+        p.x = Fq::one(); // g1::affine_one() (g1.hpp:13-15), io.hpp:177
+        p.y = Fq::reduce(Fq::dbl(Fq::one()));
+    }
+    else
+    {
+        const uint8_t* src = g1_bytes + (i - 1) * 64;
+        p.x = load_transcript_fq(src);
+        p.y = load_transcript_fq(src + 32);
+    }
+    store_affine(table + 4 * i, p);
+    store_affine(table + 4 * i + 2, G1::endo_table_entry(p));
+}
+
 // ---- synthetic point sets: (start + i * step) * G  (BASELINE configs[3]: "random multiples of the G1 generator") ----
 constexpr int GEN_RUN = 32;
 BBG_HD xyzz_pt scalar_mul_generator(const fe& k_mont)
@@ -733,6 +773,14 @@ int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* s
     const fe a0 = load_fe(start_mont), d = load_fe(step_mont);
     const size_t runs = (n + GEN_RUN - 1) / GEN_RUN;
     BBG_LAUNCH_NOSYNC(g1_progression_kernel, dim3((unsigned)((runs + 63) / 64)), dim3(64), st, a0, d, (fe*)d_points, n);
+    ++g_msm_launches;
+    return bbg_rt::last_error();
+}
+
+int g1_table_from_transcript_device(const void* d_g1_bytes, void* d_table, size_t n, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    BBG_LAUNCH_NOSYNC(srs_from_transcript_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const uint8_t*)d_g1_bytes, (fe*)d_table, n);
     ++g_msm_launches;
     return bbg_rt::last_error();
 }

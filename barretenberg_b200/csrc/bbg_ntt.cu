@@ -414,6 +414,33 @@ __global__ void scale_powers_kernel(fe* x, const fe* lo, const fe* hi, int lo_lo
     }
 }
 
+// evaluation_domain::compute_lookup_table (evaluation_domain.cpp:33-54, :172-178): per direction, round i (m = 2^(i+1),
+// i = 0 .. log2 size - 2) holds w_(2m)^j = root^(j size / 2m) for j < m at offset 2^(i+1) - 2; forward rounds fill
+// roots[0, size), inverse rounds roots[size, 2 size).  The reference builds every round with a serial chain of coarse
+// products; here each entry is one product of two table look-ups (canonical values: same field elements).
+__global__ void domain_lookup_kernel(fe* roots, const fe* lo, const fe* hi, const fe* ilo, const fe* ihi, int lo_log, int log_size)
+{
+    const size_t size = (size_t)1 << log_size;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * size; t += (size_t)gridDim.x * blockDim.x)
+    {
+        const bool inverse = t >= size;
+        const size_t u = inverse ? t - size : t;
+        fe v = Fr::zero(); // the last two slots of each half are unused (the reference leaves them uninitialised)
+        if (u + 2 < size)
+        {
+            const int i = 62 - __clzll((long long)(u + 2)); // round: 2^(i+1) <= u + 2 < 2^(i+2)
+            const size_t j = u + 2 - ((size_t)1 << (i + 1));
+            const size_t e = j << (log_size - i - 2); // < size / 2
+            const fe* l = inverse ? ilo : lo;
+            const fe* h = inverse ? ihi : hi;
+            v = load_fe(l + (e & (((size_t)1 << lo_log) - 1)));
+            if (h != nullptr) v = Fr::mul(v, load_fe(h + (e >> lo_log)));
+            v = Fr::reduce(v);
+        }
+        store_fe(roots + t, v);
+    }
+}
+
 // out[i] = in[i] * k
 __global__ void scale_vector_kernel(fe* out, const fe* in, fe k, unsigned count)
 {
@@ -692,6 +719,33 @@ int lagrange_fft_device(void* d_out, unsigned log_src, unsigned log_target, cuda
                       (const fe*)g_tables.tmp_vec.p, S - 1, T);
     ++g_ntt_launches;
     return bbg_rt::last_error();
+}
+
+int domain_lookup_table_device(void* d_roots, unsigned log_size, cudaStream_t st)
+{
+    if (log_size < 1 || log_size > 28) return 1002;
+    const int lo_log = (int)(log_size < (unsigned)LO_TABLE_LOG ? log_size : (unsigned)LO_TABLE_LOG);
+    const unsigned lo_count = 1u << lo_log, hi_count = log_size > (unsigned)lo_log ? 1u << (log_size - lo_log) : 0u;
+    fe* tab = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc((void**)&tab, (size_t)2 * (lo_count + hi_count + 1) * 32));
+    fe *lo = tab, *hi = lo + lo_count, *ilo = hi + hi_count, *ihi = ilo + lo_count;
+    const fe w = host_root_of_unity(log_size);
+    const fe wi = Fr::invert(w);
+    BBG_LAUNCH_NOSYNC(gen_powers_kernel, dim3((lo_count + 127) / 128), dim3(128), st, lo, w, Fr::one(), lo_count);
+    BBG_LAUNCH_NOSYNC(gen_powers_kernel, dim3((lo_count + 127) / 128), dim3(128), st, ilo, wi, Fr::one(), lo_count);
+    if (hi_count)
+    {
+        BBG_LAUNCH_NOSYNC(gen_powers_kernel, dim3((hi_count + 127) / 128), dim3(128), st, hi, host_pow(w, lo_count), Fr::one(), hi_count);
+        BBG_LAUNCH_NOSYNC(gen_powers_kernel, dim3((hi_count + 127) / 128), dim3(128), st, ihi, host_pow(wi, lo_count), Fr::one(), hi_count);
+    }
+    const int grid = 8 * bbg_rt::num_sms();
+    BBG_LAUNCH_NOSYNC(domain_lookup_kernel, dim3((unsigned)grid), dim3(256), st, (fe*)d_roots, (const fe*)lo, hi_count ? (const fe*)hi : (const fe*)nullptr,
+                      (const fe*)ilo, hi_count ? (const fe*)ihi : (const fe*)nullptr, lo_log, (int)log_size);
+    g_ntt_launches += hi_count ? 5 : 3;
+    int e = bbg_rt::last_error();
+    if (e == 0) e = bbg_rt::sync(st);
+    bbg_rt::dev_free(tab);
+    return e;
 }
 
 int ntt_release_tables()

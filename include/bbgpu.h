@@ -111,6 +111,20 @@ int bbg_generate_pippenger_point_table_dev(const void* d_points, void* d_table, 
  * memory (n x 64 bytes).  start / step are Fr elements in Montgomery form. */
 int bbg_g1_generate_multiples_dev(const uint64_t start[4], const uint64_t step[4], void* d_points, size_t n);
 
+/* ---- prover construction ----------------------------------------------------
+ * evaluation_domain::compute_lookup_table (polynomials/evaluation_domain.hpp:35, evaluation_domain.cpp:33-54, :172-178):
+ * roots = 2 * 2^log2_size field elements (host); per direction round i (m = 2^(i+1), i = 0 .. log2_size - 2) holds
+ * w_(2m)^j, j < m, at offset 2^(i+1) - 2: forward rounds in roots[0, size), inverse rounds in roots[size, 2 size).
+ * Canonical Montgomery values (the reference's serial chain leaves them lazily reduced in [0, 2p): same field elements).
+ * Shim: barretenberg_b200/shim/evaluation_domain_gpu.cpp. */
+int bbg_fr_domain_lookup_table(uint64_t* roots, unsigned log2_size);
+/* io::read_transcript's G1 part + generate_pippenger_point_table (io/io.hpp:76-98, :157-182, reference_string.cpp:20-23,
+ * scalar_multiplication.cpp:131-140): g1_bytes = the (n - 1) x 64 raw bytes that follow the transcript manifest (x then y,
+ * four 64-bit limbs each, least significant limb first, big-endian bytes inside a limb, plain values); writes the 2n-entry
+ * table [G, phi(G), P_1, phi(P_1), ...] to table_2n (host) and keeps the device copy registered as the SRS behind that
+ * address (as bbg_srs_register would, without a second upload).  Shim: barretenberg_b200/shim/reference_string_gpu.cpp. */
+int bbg_srs_from_transcript(const uint8_t* g1_bytes, size_t n, uint64_t* table_2n);
+
 /* ---- HBM-resident PLONK prover rounds -------------------------------------
  * Stand behind waffle::Prover::construct_proof (waffle/proof_system/prover/prover.cpp:657-666) for circuits built from
  * the arithmetic, bool, MiMC and sequential widgets (Standard / Bool / MiMC / Extended composers): the witness, the permutation mappings and the selectors are

@@ -134,5 +134,13 @@ inline unsigned __brev(unsigned x)
     return r;
 }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+inline int __clzll(long long x) { return x == 0 ? 64 : __builtin_clzll((unsigned long long)x); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
+{
+    const unsigned long long both = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((both >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }

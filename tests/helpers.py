@@ -223,3 +223,34 @@ class OracleDomain:
 
 NTT_OPS = {"fft": 0, "ifft": 1, "coset_fft": 2, "coset_ifft": 3, "fft_with_constant": 4,
            "ifft_with_constant": 5, "coset_fft_with_constant": 6}
+
+
+def expected_domain_lookup_table(log2_size):
+    """evaluation_domain.cpp:33-54, :172-178 as python integers: canonical Montgomery limbs, unused slots zero."""
+    size = 1 << log2_size
+    od = OracleDomain(size)
+    p = FR_MODULUS
+    out = np.zeros((2 * size, 4), dtype=np.uint64)
+    for half, which in ((0, 0), (1, 1)):
+        root = unmont(from_limbs(od.constant(which)))
+        off = half * size
+        for i in range(log2_size - 1):
+            m = 1 << (i + 1)
+            rr = pow(root, size // (2 * m), p)
+            cur = 1
+            for j in range(m):
+                out[off + m - 2 + j] = to_limbs(mont(cur))
+                cur = cur * rr % p
+    return out
+
+
+def transcript_g1_bytes(points_mont):
+    """io.hpp:76-98 inverted: affine points (k, 8) uint64 Montgomery limbs -> raw transcript bytes (x then y, limbs in
+    little-endian order, big-endian bytes inside a limb, plain values)."""
+    out = bytearray()
+    for pt in points_mont:
+        for c in (pt[:4], pt[4:]):
+            v = unmont(from_limbs(c), FQ)
+            for k in range(4):
+                out += ((v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF).to_bytes(8, "big")
+    return bytes(out)

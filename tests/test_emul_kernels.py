@@ -185,3 +185,27 @@ def test_compute_lagrange_polynomial_fft(emu, log_src, log_tgt):
     exp = np.zeros_like(got)
     H.oracle().orc_compute_lagrange_polynomial_fft(H.ptr(exp), log_src, log_tgt)
     assert (got == exp).all()
+
+
+@pytest.mark.parametrize("log2_size", [1, 2, 3, 5, 11, 12])
+def test_domain_lookup_table(emu, log2_size):
+    """evaluation_domain::compute_lookup_table on the device: every round of both directions as values"""
+    assert (emu.domain_lookup_table(log2_size) == H.expected_domain_lookup_table(log2_size)).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 300])
+def test_srs_from_transcript(emu, n):
+    """raw transcript bytes -> [G, phi(G), P_1, phi(P_1), ...]; the device copy serves MSMs behind the returned buffer"""
+    ref_table, _, _ = H.generator_multiples_table(77, max(n, 2))
+    pts = np.ascontiguousarray(ref_table[0:2 * n:2])
+    gen = np.zeros((1, 8), dtype=np.uint64)
+    gen[0, :4] = H.to_limbs(H.mont(1, H.FQ))
+    gen[0, 4:] = H.to_limbs(H.mont(2, H.FQ))
+    pts[0] = gen[0]
+    expect = np.zeros((2 * n, 8), dtype=np.uint64)
+    H.oracle().orc_generate_pippenger_point_table(H.ptr(pts), H.ptr(expect), n)
+    table = emu.srs_from_transcript(H.transcript_g1_bytes(pts[1:]), n)
+    assert (table == expect).all()
+    sc = H.random_scalars_mont(5, n)
+    assert (emu.msm(sc, table, n) == H.oracle_msm(sc, expect)).all()
+    emu.srs_unregister(table)

@@ -335,3 +335,44 @@ def test_compute_lagrange_polynomial_fft(lib, log_src, log_tgt):
         r.ref_compute_lagrange_polynomial_fft(p, 1 << log_src, t)
         assert (got == exp).all()
         r.ref_aligned_free(p)
+
+
+# ---- prover construction helpers ---------------------------------------------------------------
+@pytest.mark.parametrize("log2_size", [4, 11, 12, 16])
+def test_domain_lookup_table_full(lib, log2_size):
+    assert (lib.domain_lookup_table(log2_size) == H.expected_domain_lookup_table(log2_size)).all()
+
+
+def test_domain_lookup_table_2p22_sampled(lib):
+    """the 4n domain of a 2^20-gate circuit (256 MiB of tables): 2000 seeded entries of both directions against python
+    integers, and the structure: round i starts with one, its second entry is the round's root"""
+    lg = 22
+    size = 1 << lg
+    t = lib.domain_lookup_table(lg)
+    od = H.OracleDomain(size)
+    p = H.FR_MODULUS
+    rng = np.random.default_rng(22)
+    for half, which in ((0, 0), (1, 1)):
+        root = H.unmont(H.from_limbs(od.constant(which)))
+        for u in rng.integers(0, size - 2, size=1000):
+            u = int(u)
+            i = (u + 2).bit_length() - 2
+            j = u + 2 - (1 << (i + 1))
+            want = H.mont(pow(root, j * (size >> (i + 2)), p))
+            assert H.from_limbs(t[half * size + u]) == want, (half, u)
+    assert (t[size - 2:size] == 0).all() and (t[2 * size - 2:] == 0).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 1 << 16])
+def test_srs_from_transcript(lib, n):
+    ref_table, _, _ = H.generator_multiples_table(78, max(n, 2))
+    pts = np.ascontiguousarray(ref_table[0:2 * n:2])
+    pts[0, :4] = H.to_limbs(H.mont(1, H.FQ))
+    pts[0, 4:] = H.to_limbs(H.mont(2, H.FQ))
+    expect = np.zeros((2 * n, 8), dtype=np.uint64)
+    H.oracle().orc_generate_pippenger_point_table(H.ptr(pts), H.ptr(expect), n)
+    table = lib.srs_from_transcript(H.transcript_g1_bytes(pts[1:]), n)
+    assert (table == expect).all()
+    sc = H.random_scalars_mont(6, n)
+    assert (lib.msm(sc, table, n) == H.oracle_msm(sc, expect)).all()  # served by the device copy kept at load time
+    lib.srs_unregister(table)
