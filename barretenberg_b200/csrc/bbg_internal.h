@@ -26,6 +26,7 @@ enum ntt_op
 
 // device-resident NTT: batch polynomials of 2^log_n elements, `stride` elements apart, in place.
 int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int op, const uint64_t* constant, cudaStream_t stream);
+void ntt_use_side_scratch(bool on); // route the following ntt_device calls to a second scratch buffer (second stream)
 int ntt_release_tables();
 // coset evaluations of L_1 on the 2^log_target domain for a 2^log_src circuit (compute_lagrange_polynomial_fft)
 int lagrange_fft_device(void* d_out, unsigned log_src, unsigned log_target, cudaStream_t stream);

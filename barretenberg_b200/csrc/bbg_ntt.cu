@@ -507,10 +507,14 @@ struct NttTables
     std::map<int, fe*> matrix;          // key = log_n * 8 + variant
     std::map<int, fe*> vec;             // key = log_n * 8 + kind
     DeviceBuf scratch;                  // pass A output
+    DeviceBuf scratch_side;             // the same for transforms queued on a second stream (ntt_use_side_scratch)
+    bool use_side = false;
     DeviceBuf tmp_vec;                  // per-call scaled pre-scale vector
     std::vector<void*> owned;
     bool smem_configured = false;
 } g_tables;
+
+DeviceBuf& active_scratch() { return g_tables.use_side ? g_tables.scratch_side : g_tables.scratch; }
 
 int alloc_owned(void** p, size_t bytes)
 {
@@ -533,6 +537,7 @@ int get_sub_tw(int L, bool inverse, cudaStream_t st, const uint32_t** out)
         const unsigned half = L >= 1 ? (1u << (L - 1)) : 1u;
         BBG_LAUNCH_NOSYNC(gen_subtw_image_kernel, dim3((half + 127) / 128), dim3(128), st, img, root, half);
         ++g_ntt_launches;
+        BBG_CHECK(bbg_rt::sync(st)); // (one-off; callers on other streams may use the table next)
         it = g_tables.sub_tw.emplace(key, img).first;
     }
     *out = it->second;
@@ -607,6 +612,7 @@ int get_vec(unsigned log_n, int kind, cudaStream_t st, const fe** out)
         BBG_CHECK(alloc_owned((void**)&v, (size_t)count * 32));
         BBG_LAUNCH_NOSYNC(gen_powers_kernel, dim3((count + 127) / 128), dim3(128), st, v, base, scale, count);
         ++g_ntt_launches;
+        BBG_CHECK(bbg_rt::sync(st));
         it = g_tables.vec.emplace(key, v).first;
     }
     *out = it->second;
@@ -693,6 +699,10 @@ template <bool COLS_LOW> int launch_pass(int L, const PassParams& p, cudaStream_
 } // namespace
 
 size_t ntt_launch_count() { return g_ntt_launches; }
+// Transforms queued while this is on use a second scratch buffer, so they may run on another stream concurrently with
+// transforms queued while it is off (one host thread drives both streams).  Only for operations without a per-call scaled
+// vector (plain / coset forward and inverse): those share g_tables.tmp_vec.
+void ntt_use_side_scratch(bool on) { g_tables.use_side = on; }
 
 // d_out: T = 2^log_target field elements on the device
 int lagrange_fft_device(void* d_out, unsigned log_src, unsigned log_target, cudaStream_t st)
@@ -756,6 +766,7 @@ int ntt_release_tables()
     g_tables.matrix.clear();
     g_tables.vec.clear();
     g_tables.scratch.release();
+    g_tables.scratch_side.release();
     g_tables.tmp_vec.release();
     return 0;
 }
@@ -773,8 +784,8 @@ int ntt_three_pass(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, 
     int L1, L2;
     split((unsigned)LM, L1, L2);
     const size_t M = (size_t)1 << LM;
-    BBG_CHECK(g_tables.scratch.ensure(2 * n * 32));
-    fe* s1 = (fe*)g_tables.scratch.p;
+    BBG_CHECK(active_scratch().ensure(2 * n * 32));
+    fe* s1 = (fe*)active_scratch().p;
     fe* s2 = s1 + n;
     const fe *g_lo = nullptr, *g_hi = nullptr;
     if (coset)
@@ -907,10 +918,10 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
 
     int L1, L2;
     split(log_n, L1, L2);
-    BBG_CHECK(g_tables.scratch.ensure(batch * n * 32));
+    BBG_CHECK(active_scratch().ensure(batch * n * 32));
     PassParams a, b;
     a.src = (const fe*)d_coeffs;
-    a.dst = (fe*)g_tables.scratch.p;
+    a.dst = (fe*)active_scratch().p;
     a.batch_stride = stride;
     a.log_n = (int)log_n;
     a.num_tiles = (int)(n >> TILE_LOG);
@@ -921,7 +932,7 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
     a.scatter_shift = 0;
     b = a;
     // pass A writes polynomial i at scratch + i * n; pass B reads it back from there
-    b.src = (const fe*)g_tables.scratch.p;
+    b.src = (const fe*)active_scratch().p;
     b.dst = (fe*)d_coeffs;
     BBG_CHECK(get_sub_tw(L1, inverse, st, &a.sub_tw));
     BBG_CHECK(get_sub_tw(L2, inverse, st, &b.sub_tw));

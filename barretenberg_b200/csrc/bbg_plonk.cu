@@ -221,7 +221,9 @@ struct QuotientConsts
 {
     fe g;          // coset generator
     fe g_beta;     // g * beta
-    fe beta, gamma, alpha, alpha_sqr;
+    fe beta, gamma, alpha, alpha_sqr, alpha_cube;
+    fe one;          // Montgomery one
+    fe z_scale;      // alpha for the passes that have to scale Z's coset evaluations themselves (they are kept unscaled)
     fe neg_root_inv; // -w_n^-1 = -w_n^(n-1)  (divide_by_pseudo_vanishing_polynomial "numerator_constant")
     fe vinv[4];      // 1 / ((g w_S^j)^n - 1), j < S = 2 (mid domain) or 4 (large domain)
 };
@@ -247,8 +249,12 @@ template <bool DIVIDE> __global__ void quotient_large_kernel(fe* q, const fe* s4
         fe v = Fr::sub(id, pm);
         if (DIVIDE)
         {
-            v = Fr::mul(v, c.vinv[i & 3]);
+            v = Fr::mul(v, c.vinv[i & 3]); // (carries alpha: Z's coset evaluations are unscaled)
             v = Fr::mul(v, Fr::add(Fr::mul(root, c.g), c.neg_root_inv));
+        }
+        else
+        {
+            v = Fr::mul(v, c.z_scale);
         }
         store_fe(q + i, v);
     }
@@ -263,10 +269,11 @@ __global__ void quotient_mid_kernel(fe* q, const fe* z4, const fe* l1, const fe*
     const unsigned n4 = 2 * n2, mask2 = n2 - 1, mask4 = n4 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
     {
-        fe t6 = Fr::sub(load_fe(z4 + ((2 * i + 4) & mask4)), c.alpha);
-        t6 = Fr::mul(Fr::mul(t6, c.alpha), load_fe(l1 + ((i + 4) & mask2)));
-        fe t4 = Fr::sub(load_fe(z4 + 2 * i), c.alpha);
-        t4 = Fr::mul(Fr::mul(t4, c.alpha_sqr), load_fe(l1 + i));
+        // z4 holds Z itself (the reference transforms alpha Z, :275): (aZ - a) a = a^2 (Z - 1), (aZ - a) a^2 = a^3 (Z - 1)
+        fe t6 = Fr::sub(load_fe(z4 + ((2 * i + 4) & mask4)), c.one);
+        t6 = Fr::mul(Fr::mul(t6, c.alpha_sqr), load_fe(l1 + ((i + 4) & mask2)));
+        fe t4 = Fr::sub(load_fe(z4 + 2 * i), c.one);
+        t4 = Fr::mul(Fr::mul(t4, c.alpha_cube), load_fe(l1 + i));
         const fe wl = load_fe(w4 + 2 * i), wr = load_fe(w4 + (size_t)n4 + 2 * i), wo = load_fe(w4 + 2 * (size_t)n4 + 2 * i);
         fe a = Fr::mul(Fr::mul(wl, load_fe(q2 + i)), wr);
         a = Fr::add(a, Fr::mul(wl, load_fe(q2 + (size_t)n2 + i)));
@@ -289,10 +296,11 @@ __global__ void quotient_mid_base_kernel(fe* q, const fe* z4, const fe* l1, Quot
     const unsigned n4 = 2 * n2, mask2 = n2 - 1, mask4 = n4 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
     {
-        fe t6 = Fr::sub(load_fe(z4 + ((2 * i + 4) & mask4)), c.alpha);
-        t6 = Fr::mul(Fr::mul(t6, c.alpha), load_fe(l1 + ((i + 4) & mask2)));
-        fe t4 = Fr::sub(load_fe(z4 + 2 * i), c.alpha);
-        t4 = Fr::mul(Fr::mul(t4, c.alpha_sqr), load_fe(l1 + i));
+        // z4 holds Z itself (the reference transforms alpha Z, :275): (aZ - a) a = a^2 (Z - 1), (aZ - a) a^2 = a^3 (Z - 1)
+        fe t6 = Fr::sub(load_fe(z4 + ((2 * i + 4) & mask4)), c.one);
+        t6 = Fr::mul(Fr::mul(t6, c.alpha_sqr), load_fe(l1 + ((i + 4) & mask2)));
+        fe t4 = Fr::sub(load_fe(z4 + 2 * i), c.one);
+        t4 = Fr::mul(Fr::mul(t4, c.alpha_cube), load_fe(l1 + i));
         store_fe(q + i, Fr::add(t4, t6));
     }
 }
@@ -661,6 +669,12 @@ struct Prover
     cudaStream_t upload_stream = nullptr;
     cudaEvent_t ev_item[NUM_ITEMS] = {};
     cudaEvent_t ev_fence = nullptr;
+    // Second work stream: the coset transforms of round 3 that only need earlier rounds' results (wires after round 1,
+    // beta sigma + w + gamma after the beta / gamma challenge, Z after its ifft) are queued here as soon as their inputs
+    // exist and run in the shadow of the commitments' latency-bound phases.  BBG_PLONK_OVERLAP=0 keeps one stream.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_wire[3] = {}, ev_sigma = nullptr, ev_z = nullptr, ev_side = nullptr;
+    bool overlap = true;
     bbg_hostcopy::Ring upload_ring;
     std::thread uploader;
     std::atomic<int> uploaded{ 0 }; // items whose copies have all been queued (event recorded)
@@ -758,6 +772,15 @@ int create(unsigned log_n, Prover** out)
     e = (int)cudaStreamCreateWithFlags(&p->upload_stream, cudaStreamNonBlocking);
     for (int i = 0; i < Prover::NUM_ITEMS && e == 0; ++i) e = (int)cudaEventCreateWithFlags(&p->ev_item[i], cudaEventDisableTiming);
     if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_fence, cudaEventDisableTiming);
+    if (e == 0) e = (int)cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && e == 0; ++i) e = (int)cudaEventCreateWithFlags(&p->ev_wire[i], cudaEventDisableTiming);
+    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_sigma, cudaEventDisableTiming);
+    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_z, cudaEventDisableTiming);
+    if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_side, cudaEventDisableTiming);
+    {
+        const char* ov = getenv("BBG_PLONK_OVERLAP");
+        p->overlap = !(ov != nullptr && ov[0] == '0');
+    }
     if (e != 0)
     {
         destroy(p);
@@ -781,6 +804,16 @@ void destroy(Prover* p)
     for (int i = 0; i < Prover::NUM_ITEMS; ++i)
         if (p->ev_item[i]) cudaEventDestroy(p->ev_item[i]);
     if (p->ev_fence) cudaEventDestroy(p->ev_fence);
+    if (p->side)
+    {
+        cudaStreamSynchronize(p->side);
+        cudaStreamDestroy(p->side);
+    }
+    for (int i = 0; i < 3; ++i)
+        if (p->ev_wire[i]) cudaEventDestroy(p->ev_wire[i]);
+    if (p->ev_sigma) cudaEventDestroy(p->ev_sigma);
+    if (p->ev_z) cudaEventDestroy(p->ev_z);
+    if (p->ev_side) cudaEventDestroy(p->ev_side);
     p->upload_ring.release();
 #endif
     if (p->arena) bbg_rt::dev_free(p->arena);
@@ -1030,6 +1063,39 @@ static int commit(Prover* p, const fe* d_scalars, size_t stride, int count, uint
 
 // prover.cpp:126-135 compute_wire_coefficients + :65-89 compute_wire_commitments (and, off the critical path of the
 // transcript, permutation.hpp's sigma polynomials)
+// Side-stream plumbing (no-ops in the emulation build and with BBG_PLONK_OVERLAP=0: everything stays on `st`).
+static cudaStream_t side_stream(Prover* p, cudaStream_t st)
+{
+#ifndef BBG_EMULATE
+    if (p->overlap) return p->side;
+#endif
+    (void)p;
+    return st;
+}
+// `waiter` proceeds only after everything queued on `signaller` so far
+static int order_after(Prover* p, cudaStream_t waiter, cudaStream_t signaller, int which)
+{
+#ifndef BBG_EMULATE
+    if (waiter == signaller) return 0;
+    cudaEvent_t ev = which < 3 ? p->ev_wire[which] : (which == 3 ? p->ev_sigma : (which == 4 ? p->ev_z : p->ev_side));
+    BBG_CHECK(cudaEventRecord(ev, signaller));
+    BBG_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
+#else
+    (void)p;
+    (void)waiter;
+    (void)signaller;
+    (void)which;
+#endif
+    return 0;
+}
+// a transform queued on the side stream uses the NTT driver's second scratch buffer
+struct SideScratch
+{
+    bool on;
+    SideScratch(cudaStream_t side, cudaStream_t st) : on(side != st) { if (on) ntt_use_side_scratch(true); }
+    ~SideScratch() { if (on) ntt_use_side_scratch(false); }
+};
+
 // BBG_PLONK_TRACE=1: host-side timeline of the rounds on stderr (development aid)
 struct Trace
 {
@@ -1059,6 +1125,17 @@ int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
         BBG_CHECK(bbg_rt::d2d(p->w_coef + (size_t)k * n, p->w_lag + (size_t)k * n, n * 32, st));
         BBG_CHECK(ntt_device(p->w_coef + (size_t)k * n, n, 1, p->log_n, OP_IFFT, nullptr, st));
         tr.mark("wire ifft", st);
+        {
+            // the wire on the 4n coset (prover.cpp:400-414) only needs its coefficients: queued now, used in round 3
+            const size_t n4 = 4 * n;
+            cudaStream_t sd = side_stream(p, st);
+            BBG_CHECK(order_after(p, sd, st, k));
+            SideScratch scratch(sd, st);
+            BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 1), dim3(256), sd, p->w4 + (size_t)k * n4, (const fe*)(p->w_coef + (size_t)k * n),
+                              (unsigned)n, (unsigned)n4, n, n4);
+            ++g_plonk_launches;
+            BBG_CHECK(ntt_device(p->w4 + (size_t)k * n4, n4, 1, p->log_n + 2, OP_COSET_FFT, nullptr, sd));
+        }
         BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, n, 1, out_xyz + 12 * k, st));
         tr.mark("wire commitment", st);
     }
@@ -1088,6 +1165,23 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
         BBG_LAUNCH_NOSYNC(z_terms_kernel, dim3(grid_for(n, 128)), dim3(128), st, num, den, (const fe*)p->w_lag, (const fe*)p->sigma_lag, p->pow_small, beta,
                           gamma, (unsigned)n);
     }
+    const size_t n4 = 4 * n;
+    cudaStream_t sd = side_stream(p, st);
+    {
+        // beta sigma + w + gamma on the 4n coset (:246-273) needs nothing beyond beta and gamma: queued for round 3.
+        // (a cold proving key first brings sigma into coefficient form: a circuit constant, kept unscaled)
+        BBG_CHECK(order_after(p, sd, st, 3));
+        SideScratch scratch(sd, st);
+        if (!p->constants_cached)
+        {
+            BBG_CHECK(bbg_rt::d2d(p->sigma, p->sigma_lag, 3 * n * 32, sd));
+            BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT, nullptr, sd));
+        }
+        BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), sd, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, beta, gamma,
+                          (unsigned)n, (unsigned)n4);
+        ++g_plonk_launches;
+        BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, sd));
+    }
     const unsigned runs = (unsigned)((n + ZRUN - 1) / ZRUN);
     bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::PLONK_SCAN, st);
     BBG_LAUNCH_NOSYNC(prod_reduce_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, (const fe*)p->tmp, p->aggs, (unsigned)n, (unsigned)ZRUN, n, p->aggs_stride);
@@ -1097,6 +1191,14 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
     delete prof_scan;
     g_plonk_launches += 4;
     BBG_CHECK(ntt_device(p->z, n, 1, p->log_n, OP_IFFT, nullptr, st));
+    {
+        // Z on the 4n coset (:275; unscaled, alpha is applied by the quotient passes): queued behind the commitment
+        BBG_CHECK(order_after(p, sd, st, 4));
+        SideScratch scratch(sd, st);
+        BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 1), dim3(256), sd, p->z4, (const fe*)p->z, (unsigned)n, (unsigned)n4, n, n4);
+        ++g_plonk_launches;
+        BBG_CHECK(ntt_device(p->z4, n4, 1, p->log_n + 2, OP_COSET_FFT, nullptr, sd));
+    }
     BBG_CHECK(commit(p, p->z, n, 1, out_xyz, st));
     return bbg_rt::last_error();
 }
@@ -1111,25 +1213,10 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     if (!p->sigma_ready || !p->uploads_started) return 1007;
     BBG_CHECK(wait_item(p, Prover::ITEM_SEL, st)); // the selectors arrived behind rounds 1 and 2
     p->uploads_started = false;                    // every input of this proof is on the device
-    // wires on the 4n coset (prover.cpp:407-414)
-    BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->w4, (const fe*)p->w_coef, (unsigned)n, (unsigned)n4, n, n4);
-    BBG_CHECK(ntt_device(p->w4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
-    tr.mark("w4 coset_fft", st);
-    // sigma: Lagrange -> coefficients (:246-248; a circuit constant, kept unscaled), then beta sigma + w + gamma on the
-    // 4n coset (:252-273)
+    // the 4n coset evaluations of the wires, of beta sigma + w + gamma and of Z were queued in rounds 1 and 2
+    BBG_CHECK(order_after(p, st, side_stream(p, st), 5));
     const bool cached = p->constants_cached;
-    if (!cached)
-    {
-        BBG_CHECK(bbg_rt::d2d(p->sigma, p->sigma_lag, 3 * n * 32, st));
-        BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT, nullptr, st));
-    }
-    BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), st, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, beta, gamma,
-                      (unsigned)n, (unsigned)n4);
-    BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, st));
-    tr.mark("sigma ifft + s4 coset_fft", st);
-    // alpha Z on the 4n coset (:275)
-    BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 1), dim3(256), st, p->z4, (const fe*)p->z, (unsigned)n, (unsigned)n4, n, n4);
-    BBG_CHECK(ntt_device(p->z4, n4, 1, p->log_n + 2, OP_COSET_FFT_WITH_CONSTANT, alpha_, st));
+    tr.mark("side stream joined (w4, s4, z4)", st);
     // L_1 on the 2n coset (:349-351)
     if (!p->l1_ready) BBG_CHECK(lagrange_fft_device(p->l1, p->log_n, p->log_n + 1, st));
     p->l1_ready = true;
@@ -1144,6 +1231,9 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     c.gamma = gamma;
     c.alpha = alpha;
     c.alpha_sqr = Fr::reduce(Fr::sqr(alpha));
+    c.alpha_cube = Fr::reduce(Fr::mul(c.alpha_sqr, alpha));
+    c.one = Fr::one();
+    c.z_scale = alpha;
     c.g_beta = Fr::reduce(Fr::mul(c.g, beta));
     {
         const fe w = host_root_of_unity(p->log_n);
@@ -1177,6 +1267,7 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
         BBG_CHECK(to_coset(p->q2, 0, 5, n2, p->log_n + 1));
         tr.mark("selectors ifft + coset_fft", st);
         fill_vinv(2);
+        for (int j = 0; j < 4; ++j) c.vinv[j] = Fr::reduce(Fr::mul(c.vinv[j], alpha)); // Z's coset evaluations are unscaled
         BBG_LAUNCH_NOSYNC(quotient_large_kernel<true>, dim3(grid_for(n4, 128)), dim3(128), st, p->quot_large, (const fe*)p->s4, (const fe*)p->w4,
                           (const fe*)p->z4, p->pow_large, c, (unsigned)n4);
         fill_vinv(1);
