@@ -17,7 +17,7 @@
 //
 // Layout in HBM for a circuit of n = 2^k gates (field element = 32 B; n = 2^20 -> 2.3 GB in total):
 //   w_lag[3][n]  witness, Lagrange form          w_coef[3][n]   coefficient form       w4[3][4n]  coset evaluations
-//   sigma[3][n]  permutation polys (Lagrange -> beta-scaled coefficients in place)     s4[3][4n]
+//   sigma_lag[3][n], sigma[3][n]  permutation polys, Lagrange / coefficient form       s4[3][4n]  their coset evaluations
 //   z[n], z4[4n] grand product                   q[11][n], q2[9][2n], q4[2][4n]  selectors (all four widget kinds)   l1[2n]
 //   quot_large[4n], quot_mid[2n], r[n], tmp[2][n] (scan inputs / opening polynomials)
 #include "bbg_internal.h"
@@ -198,25 +198,6 @@ __global__ void pad_copy_kernel(fe* dst, const fe* src, unsigned n_src, unsigned
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += gridDim.x * blockDim.x)
         store_fe(d + i, i < n_src ? load_fe(s + i) : Fr::zero());
 }
-// prover.cpp:246-262: s4[b] = beta sigma_b(X) + w_b(X) + gamma in coefficient form, zero padded to 4n (the reference scales
-// sigma by beta inside its ifft; here the coefficient form is a cached circuit constant and beta is applied in this pass)
-__global__ void sigma_combine_pad_kernel(fe* s4, const fe* sigma_coef, const fe* w_coef, fe beta, fe gamma, unsigned n, unsigned n4)
-{
-    const fe* s = sigma_coef + (size_t)blockIdx.y * n;
-    const fe* w = w_coef + (size_t)blockIdx.y * n;
-    fe* d = s4 + (size_t)blockIdx.y * n4;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
-    {
-        fe v = Fr::zero();
-        if (i < n)
-        {
-            v = Fr::add(Fr::mul(load_fe(s + i), beta), load_fe(w + i)); // sigma_coef is kept unscaled (proving-key cache)
-            if (i == 0) v = Fr::add(v, gamma);
-        }
-        store_fe(d + i, v);
-    }
-}
-
 struct QuotientConsts
 {
     fe g;          // coset generator
@@ -231,20 +212,28 @@ struct QuotientConsts
 // prover.cpp:279-285 (permutation term), :296-323 (identity term), polynomial_arithmetic.cpp:478-560 (the division by
 // Z_H*(X) on the large domain), one pass:
 //   q[i] = ( (w_l + b x + c)(w_r + b k1 x + c)(w_o + b k2 x + c) aZ(x)  -  s1 s2 s3 aZ(x w) ) (x - w^(n-1)) / (x^n - 1),
-//   x = g w_4n^i
-template <bool DIVIDE> __global__ void quotient_large_kernel(fe* q, const fe* s4, const fe* w4, const fe* z4, PowTable large, QuotientConsts c, unsigned n4)
+//   x = g w_4n^i,  s_k = w_k + b sigma_k + c.
+// The reference transforms b sigma_k(X) + w_k(X) + c to the 4n coset every proof (:246-273).  The transform is linear and
+// sigma_k's coset evaluations are a circuit constant (sigma4, part of the proving-key cache), so s_k is formed here from
+// sigma4 and the wires' evaluations: three products per point instead of three 4n-point transforms per proof.
+template <bool DIVIDE>
+__global__ void quotient_large_kernel(fe* q, const fe* sigma4, const fe* w4, const fe* z4, PowTable large, QuotientConsts c, unsigned n4)
 {
     const unsigned mask = n4 - 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
     {
         const fe root = root_pow(large, i);
         const fe bx = Fr::mul(root, c.g_beta);
-        fe id = Fr::add(Fr::add(load_fe(w4 + i), c.gamma), bx);
-        id = Fr::mul(id, Fr::add(Fr::add(load_fe(w4 + (size_t)n4 + i), c.gamma), Fr::mul(bx, gen_k1())));
-        id = Fr::mul(id, Fr::add(Fr::add(load_fe(w4 + 2 * (size_t)n4 + i), c.gamma), Fr::mul(bx, gen_k2())));
+        const fe wl = Fr::add(load_fe(w4 + i), c.gamma);
+        const fe wr = Fr::add(load_fe(w4 + (size_t)n4 + i), c.gamma);
+        const fe wo = Fr::add(load_fe(w4 + 2 * (size_t)n4 + i), c.gamma);
+        fe id = Fr::add(wl, bx);
+        id = Fr::mul(id, Fr::add(wr, Fr::mul(bx, gen_k1())));
+        id = Fr::mul(id, Fr::add(wo, Fr::mul(bx, gen_k2())));
         id = Fr::mul(id, load_fe(z4 + i));
-        fe pm = Fr::mul(load_fe(s4 + i), load_fe(s4 + (size_t)n4 + i));
-        pm = Fr::mul(pm, load_fe(s4 + 2 * (size_t)n4 + i));
+        fe pm = Fr::add(wl, Fr::mul(load_fe(sigma4 + i), c.beta));
+        pm = Fr::mul(pm, Fr::add(wr, Fr::mul(load_fe(sigma4 + (size_t)n4 + i), c.beta)));
+        pm = Fr::mul(pm, Fr::add(wo, Fr::mul(load_fe(sigma4 + 2 * (size_t)n4 + i), c.beta)));
         pm = Fr::mul(pm, load_fe(z4 + ((i + 4) & mask)));
         fe v = Fr::sub(id, pm);
         if (DIVIDE)
@@ -1168,19 +1157,18 @@ int round_grand_product(Prover* p, const uint64_t* beta_, const uint64_t* gamma_
     const size_t n4 = 4 * n;
     cudaStream_t sd = side_stream(p, st);
     {
-        // beta sigma + w + gamma on the 4n coset (:246-273) needs nothing beyond beta and gamma: queued for round 3.
-        // (a cold proving key first brings sigma into coefficient form: a circuit constant, kept unscaled)
-        BBG_CHECK(order_after(p, sd, st, 3));
-        SideScratch scratch(sd, st);
+        // a cold proving key brings sigma into coefficient form and onto the 4n coset (circuit constants, kept unscaled:
+        // the quotient pass forms beta sigma + w + gamma itself); nothing to do when the key is cached
         if (!p->constants_cached)
         {
+            BBG_CHECK(order_after(p, sd, st, 3));
+            SideScratch scratch(sd, st);
             BBG_CHECK(bbg_rt::d2d(p->sigma, p->sigma_lag, 3 * n * 32, sd));
             BBG_CHECK(ntt_device(p->sigma, n, 3, p->log_n, OP_IFFT, nullptr, sd));
+            BBG_LAUNCH_NOSYNC(pad_copy_kernel, dim3(grid_for(n4, 256), 3), dim3(256), sd, p->s4, (const fe*)p->sigma, (unsigned)n, (unsigned)n4, n, n4);
+            ++g_plonk_launches;
+            BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, sd));
         }
-        BBG_LAUNCH_NOSYNC(sigma_combine_pad_kernel, dim3(grid_for(n4, 256), 3), dim3(256), sd, p->s4, (const fe*)p->sigma, (const fe*)p->w_coef, beta, gamma,
-                          (unsigned)n, (unsigned)n4);
-        ++g_plonk_launches;
-        BBG_CHECK(ntt_device(p->s4, n4, 3, p->log_n + 2, OP_COSET_FFT, nullptr, sd));
     }
     const unsigned runs = (unsigned)((n + ZRUN - 1) / ZRUN);
     bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::PLONK_SCAN, st);
@@ -1216,7 +1204,7 @@ int round_quotient(Prover* p, const uint64_t* beta_, const uint64_t* gamma_, con
     // the 4n coset evaluations of the wires, of beta sigma + w + gamma and of Z were queued in rounds 1 and 2
     BBG_CHECK(order_after(p, st, side_stream(p, st), 5));
     const bool cached = p->constants_cached;
-    tr.mark("side stream joined (w4, s4, z4)", st);
+    tr.mark("side stream joined (w4, z4)", st);
     // L_1 on the 2n coset (:349-351)
     if (!p->l1_ready) BBG_CHECK(lagrange_fft_device(p->l1, p->log_n, p->log_n + 1, st));
     p->l1_ready = true;
@@ -1528,7 +1516,7 @@ int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint6
     }
     BBG_LAUNCH_NOSYNC(kate_reduce_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, (const fe*)p->tmp, p->aggs, pts, (unsigned)n, run, p->aggs_stride);
     BBG_LAUNCH(kate_spine_kernel, dim3(2), dim3(SCAN_THREADS), 0, st, p->aggs, pts, runs, p->aggs_stride);
-    fe* quotients = p->s4; // free since the quotient round; 2 x n
+    fe* quotients = p->w4; // free since the quotient round; 2 x n
     BBG_LAUNCH_NOSYNC(kate_apply_kernel, dim3((runs + 127) / 128, 2), dim3(128), st, quotients, (const fe*)p->tmp, (const fe*)p->aggs, pts, (unsigned)n, run,
                       p->aggs_stride);
     g_plonk_launches += 4;
