@@ -18,7 +18,9 @@ def declared_symbols():
 def test_header_declares_the_boundary():
     syms = declared_symbols()
     for must in ("bbg_msm_g1", "bbg_msm_g1_batched", "bbg_ntt_fr", "bbg_ntt_fr_batched", "bbg_srs_register",
-                 "bbg_generate_pippenger_point_table", "bbg_init"):
+                 "bbg_generate_pippenger_point_table", "bbg_init", "bbg_plonk_create", "bbg_plonk_set_widgets",
+                 "bbg_plonk_round_wires", "bbg_plonk_round_grand_product", "bbg_plonk_round_quotient", "bbg_plonk_round_evaluations",
+                 "bbg_plonk_round_linearise", "bbg_plonk_round_openings", "bbg_fr_domain_lookup_table", "bbg_srs_from_transcript"):
         assert must in syms
 
 

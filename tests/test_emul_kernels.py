@@ -209,3 +209,28 @@ def test_srs_from_transcript(emu, n):
     sc = H.random_scalars_mont(5, n)
     assert (emu.msm(sc, table, n) == H.oracle_msm(sc, expect)).all()
     emu.srs_unregister(table)
+
+
+def test_plonk_rounds_reject_misuse(emu):
+    """the round entry points return BBG_E_BAD_ARGUMENT (1007) instead of running on missing inputs or out of order"""
+    import ctypes as C
+    L = emu.lib
+    L.bbg_plonk_create.argtypes = [C.c_uint, C.POINTER(C.c_void_p)]
+    L.bbg_plonk_destroy.argtypes = [C.c_void_p]
+    L.bbg_plonk_round_wires.argtypes = [C.c_void_p, C.c_void_p]
+    L.bbg_plonk_round_grand_product.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bbg_plonk_set_widgets.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    h = C.c_void_p()
+    assert L.bbg_plonk_create(1, C.byref(h)) == 1002   # at least 4 gates
+    assert L.bbg_plonk_create(30, C.byref(h)) == 1002  # beyond the supported size
+    assert L.bbg_plonk_create(4, C.byref(h)) == 0
+    out = np.zeros(36, dtype=np.uint64)
+    k = np.zeros(4, dtype=np.uint64)
+    assert L.bbg_plonk_round_wires(h, out.ctypes.data_as(C.c_void_p)) == 1007  # no witness / permutation / widgets / SRS yet
+    assert L.bbg_plonk_round_grand_product(h, k.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 1007
+    kinds = (C.c_int * 2)(0, 0)  # the same widget kind twice
+    sel = (C.c_void_p * 10)(*([k.ctypes.data] * 10))
+    assert L.bbg_plonk_set_widgets(h, kinds, 2, sel) == 1007
+    kinds = (C.c_int * 1)(9)     # unknown kind
+    assert L.bbg_plonk_set_widgets(h, kinds, 1, sel) == 1007
+    assert L.bbg_plonk_destroy(h) == 0
