@@ -454,7 +454,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) eval_final_kernel(EvalJobs jobs,
 struct OpeningConsts
 {
     fe nu[7];           // nu^1 .. nu^7
-    fe beta_inv;
     fe z_pow_n, z_pow_2n;
 };
 __global__ void opening_combine_kernel(fe* opening, fe* shifted, const fe* quot, const fe* r, const fe* w_coef, const fe* sigma, const fe* z,
@@ -1466,7 +1465,7 @@ int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint6
     const size_t n = p->n;
     OpeningConsts c;
     for (int i = 0; i < 7; ++i) c.nu[i] = from_u64(nu_powers + 4 * i);
-    c.beta_inv = from_u64(beta_inv_);
+    (void)beta_inv_; // the reference divides beta back out of its beta-scaled sigma (:586); sigma is stored unscaled here
     const fe zeta = from_u64(zeta_), zw = from_u64(zeta_omega_);
     c.z_pow_n = host_pow(zeta, n);
     c.z_pow_2n = host_pow(zeta, 2 * n);

@@ -180,7 +180,8 @@ int bbg_plonk_round_linearise(bbg_plonk_prover* p, const uint64_t* scalars, cons
 /* compute_opening_elements after the nu challenge (:505-655; compute_kate_opening_coefficients,
  * polynomial_arithmetic.cpp:562-591): nu_powers = nu^1..nu^7 (7 x 4); wire_shift_terms (3 x 4) = coefficients of w_l, w_r,
  * w_o in the shifted opening polynomial (:597-631, zero = wire not needed); selector_terms (selectors x 4) = coefficients
- * of the selectors in the opening polynomial (compute_opening_poly_contribution, zero for most);
+ * of the selectors in the opening polynomial (compute_opening_poly_contribution, zero for most); beta_inv is accepted
+ * for symmetry with the reference's formula and not used (sigma is held unscaled on the device);
  * out = PI_Z, PI_Z_OMEGA (2 x 12) */
 int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, const uint64_t beta_inv[4], const uint64_t zeta[4],
                              const uint64_t zeta_omega[4], const uint64_t* wire_shift_terms, const uint64_t* selector_terms, uint64_t* out_xyz);
