@@ -38,6 +38,10 @@ size_t ntt_launch_count();
 int msm_device(const void* d_scalars, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t stream);
 // `batch` same-size MSMs over one table in a single pipeline; out_xyzz_host: batch x 16 uint64
 int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t stream);
+// the same in two steps: msm_launch queues the kernels on `stream` using workspace 0 or 1 and hands back a ticket;
+// msm_finish waits for that MSM and folds its windows on the host (up to 6 tickets may be pending)
+int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const void* d_table, size_t n, cudaStream_t stream, int* ticket_out);
+int msm_finish(int ticket, void* out_xyzz_host);
 int msm_release_workspace();
 size_t msm_launch_count();
 // d_points[i] = (start + i * step) * G (affine, canonical), i < n; start / step: Fr Montgomery limbs (host)

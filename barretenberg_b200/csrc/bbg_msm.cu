@@ -549,7 +549,45 @@ struct Workspace
         if (e == 0) bytes = need;
         return e;
     }
-} g_ws;
+} g_ws_pool[2];
+
+// An MSM in flight: everything the host finish needs once the kernels are done.  msm_launch() queues the kernels and the
+// copy of the per-window reductions into a pinned host slot and returns a ticket; msm_finish() waits for that copy and folds
+// the windows.  Two workspaces let MSMs on two streams overlap (the latency-bound tail kernels of one under the accumulate
+// pass of the next); several tickets may be pending per workspace because the copy is ordered behind the kernels on the
+// launching stream.
+constexpr int MSM_TICKETS = 6;
+struct MsmTicket
+{
+    bool pending = false;
+    bool zero = false;   // n == 0: every sum is the point at infinity
+    Plan single{};
+    Plan pl{};
+    size_t batch = 0;
+    size_t red_count = 0;
+    void* host_red = nullptr;
+    size_t host_bytes = 0;
+#ifndef BBG_EMULATE
+    cudaEvent_t done = nullptr;
+#endif
+} g_tickets[MSM_TICKETS];
+
+int ticket_host_buffer(MsmTicket& t, size_t bytes)
+{
+    if (bytes <= t.host_bytes) return 0;
+#ifndef BBG_EMULATE
+    if (t.host_red) cudaFreeHost(t.host_red);
+    t.host_red = nullptr;
+    t.host_bytes = 0;
+    BBG_CHECK(cudaHostAlloc(&t.host_red, bytes, cudaHostAllocDefault));
+#else
+    free(t.host_red);
+    t.host_red = malloc(bytes);
+    if (t.host_red == nullptr) return 2;
+#endif
+    t.host_bytes = bytes;
+    return 0;
+}
 
 // Window plan.  Cost model in units of one mixed addition, fitted to B200 measurements (r01, 2^17 .. 2^26 points):
 //   per entry  1.13  (accumulate 0.16 ns + histogram / scatter atomics), + 0.15 when there are fewer than 2^16 buckets
@@ -614,9 +652,25 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t msm_launch_count() { return g_msm_launches; }
 int msm_release_workspace()
 {
-    if (g_ws.p) bbg_rt::dev_free(g_ws.p);
-    g_ws.p = nullptr;
-    g_ws.bytes = 0;
+    for (Workspace& w : g_ws_pool)
+    {
+        if (w.p) bbg_rt::dev_free(w.p);
+        w.p = nullptr;
+        w.bytes = 0;
+    }
+    for (MsmTicket& t : g_tickets)
+    {
+#ifndef BBG_EMULATE
+        if (t.host_red) cudaFreeHost(t.host_red);
+        if (t.done) cudaEventDestroy(t.done);
+        t.done = nullptr;
+#else
+        free(t.host_red);
+#endif
+        t.host_red = nullptr;
+        t.host_bytes = 0;
+        t.pending = false;
+    }
     return 0;
 }
 
@@ -625,15 +679,23 @@ int msm_release_workspace()
 // chunk, reduce) and the host round trip are paid once per batch (the prover commits 3 + 1 + 3 + 2 polynomials per
 // proof against the same SRS, prover.cpp:65-124, :640-652).
 // out_xyzz_host: HOST buffer of batch x 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sums
-int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t st)
+int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const void* d_table, size_t n, cudaStream_t st, int* ticket_out)
 {
-    if (batch == 0) return 0;
+    if (workspace < 0 || workspace > 1 || ticket_out == nullptr || batch == 0) return 1007;
+    int id = -1;
+    for (int i = 0; i < MSM_TICKETS && id < 0; ++i)
+        if (!g_tickets[i].pending) id = i;
+    if (id < 0) return 1007; // too many MSMs in flight
+    MsmTicket& tk = g_tickets[id];
+    tk.batch = batch;
+    tk.zero = (n == 0);
     if (n == 0)
     {
-        const hostg1::hxyzz inf = hostg1::infinity();
-        for (size_t b = 0; b < batch; ++b) memcpy((char*)out_xyzz_host + b * sizeof inf, &inf, sizeof inf);
+        tk.pending = true;
+        *ticket_out = id;
         return 0;
     }
+    Workspace& g_ws = g_ws_pool[workspace];
     if (2 * n > ((size_t)1 << 28)) return 1008;
     const Plan single = make_plan(n);
     if (single.c < 2 || single.c > 22 || single.W < 1 || single.W > 64 || (single.W - 1) * single.c >= 127 || single.W * single.c < 128)
@@ -724,10 +786,40 @@ int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d
     g_msm_launches += 9 + batch;
     BBG_CHECK(bbg_rt::last_error());
 
-    // ---- 7. host finish -----------------------------------------------------------------------------
-    std::vector<hostg1::hxyzz> r(red_count);
-    BBG_CHECK(bbg_rt::d2h(r.data(), red, red_count * 128, st));
-    BBG_CHECK(bbg_rt::sync(st));
+    // the per-window reductions travel to the ticket's pinned slot behind the kernels
+    BBG_CHECK(ticket_host_buffer(tk, red_count * 128));
+    BBG_CHECK(bbg_rt::d2h(tk.host_red, red, red_count * 128, st));
+#ifndef BBG_EMULATE
+    if (tk.done == nullptr) BBG_CHECK(cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming));
+    BBG_CHECK(cudaEventRecord(tk.done, st));
+#endif
+    tk.single = single;
+    tk.pl = pl;
+    tk.red_count = red_count;
+    tk.pending = true;
+    *ticket_out = id;
+    return 0;
+}
+
+// ---- 7. host finish: waits for the ticket's kernels, folds the windows of every MSM of the batch ---------------------
+int msm_finish(int ticket, void* out_xyzz_host)
+{
+    if (ticket < 0 || ticket >= MSM_TICKETS || !g_tickets[ticket].pending) return 1007;
+    MsmTicket& tk = g_tickets[ticket];
+    tk.pending = false;
+    const size_t batch = tk.batch;
+    if (tk.zero)
+    {
+        const hostg1::hxyzz inf = hostg1::infinity();
+        for (size_t b = 0; b < batch; ++b) memcpy((char*)out_xyzz_host + b * sizeof inf, &inf, sizeof inf);
+        return 0;
+    }
+#ifndef BBG_EMULATE
+    BBG_CHECK(cudaEventSynchronize(tk.done));
+#endif
+    const Plan& single = tk.single;
+    const Plan& pl = tk.pl;
+    const hostg1::hxyzz* r_data = (const hostg1::hxyzz*)tk.host_red;
     const auto host_t0 = std::chrono::steady_clock::now();
     const int bits = pl.reduce_outputs - 2;
     for (size_t b = 0; b < batch; ++b)
@@ -735,7 +827,7 @@ int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d
     hostg1::hxyzz result = hostg1::infinity();
     for (int w = single.W - 1; w >= 0; --w)
     {
-        const hostg1::hxyzz* rw = r.data() + (b * (size_t)single.W + (size_t)w) * pl.reduce_outputs;
+        const hostg1::hxyzz* rw = r_data + (b * (size_t)single.W + (size_t)w) * pl.reduce_outputs;
         // sum_t t * A_t = sum_r 2^r T_r   (Horner from the top bit)
         hostg1::hxyzz tsum = hostg1::infinity();
         for (int b = bits - 1; b >= 0; --b)
@@ -754,6 +846,14 @@ int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d
     }
     bbg_prof::add_host_ms(bbg_prof::MSM_HOST_FINISH, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
     return 0;
+}
+
+int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d_table, size_t n, void* out_xyzz_host, cudaStream_t st)
+{
+    if (batch == 0) return 0;
+    int ticket = -1;
+    BBG_CHECK(msm_launch(0, d_scalars, batch, d_table, n, st, &ticket));
+    return msm_finish(ticket, out_xyzz_host);
 }
 
 // d_out_xyzz: HOST buffer of 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sum

@@ -661,6 +661,8 @@ struct Prover
     // beta sigma + w + gamma after the beta / gamma challenge, Z after its ifft) are queued here as soon as their inputs
     // exist and run in the shadow of the commitments' latency-bound phases.  BBG_PLONK_OVERLAP=0 keeps one stream.
     cudaStream_t side = nullptr;
+    cudaStream_t msm_stream[2] = {}; // round 1: the three wire commitments alternate between two streams / MSM workspaces
+    cudaEvent_t ev_msm[3] = {};
     cudaEvent_t ev_wire[3] = {}, ev_sigma = nullptr, ev_z = nullptr, ev_side = nullptr;
     bool overlap = true;
     bbg_hostcopy::Ring upload_ring;
@@ -761,6 +763,8 @@ int create(unsigned log_n, Prover** out)
     for (int i = 0; i < Prover::NUM_ITEMS && e == 0; ++i) e = (int)cudaEventCreateWithFlags(&p->ev_item[i], cudaEventDisableTiming);
     if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_fence, cudaEventDisableTiming);
     if (e == 0) e = (int)cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == 0; ++i) e = (int)cudaStreamCreateWithFlags(&p->msm_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && e == 0; ++i) e = (int)cudaEventCreateWithFlags(&p->ev_msm[i], cudaEventDisableTiming);
     for (int i = 0; i < 3 && e == 0; ++i) e = (int)cudaEventCreateWithFlags(&p->ev_wire[i], cudaEventDisableTiming);
     if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_sigma, cudaEventDisableTiming);
     if (e == 0) e = (int)cudaEventCreateWithFlags(&p->ev_z, cudaEventDisableTiming);
@@ -797,6 +801,14 @@ void destroy(Prover* p)
         cudaStreamSynchronize(p->side);
         cudaStreamDestroy(p->side);
     }
+    for (int i = 0; i < 2; ++i)
+        if (p->msm_stream[i])
+        {
+            cudaStreamSynchronize(p->msm_stream[i]);
+            cudaStreamDestroy(p->msm_stream[i]);
+        }
+    for (int i = 0; i < 3; ++i)
+        if (p->ev_msm[i]) cudaEventDestroy(p->ev_msm[i]);
     for (int i = 0; i < 3; ++i)
         if (p->ev_wire[i]) cudaEventDestroy(p->ev_wire[i]);
     if (p->ev_sigma) cudaEventDestroy(p->ev_sigma);
@@ -1105,6 +1117,7 @@ int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
     BBG_CHECK(ensure_tables(p, st));
     const size_t n = p->n;
     BBG_CHECK(start_uploads(p, st));
+    int tickets[3] = { -1, -1, -1 };
     // wire by wire: the commitment to w_l is computed while w_r and w_o are still on the PCIe bus
     for (int k = 0; k < 3; ++k)
     {
@@ -1124,9 +1137,32 @@ int round_wires(Prover* p, uint64_t* out_xyz /* 3 x 12 */, cudaStream_t st)
             ++g_plonk_launches;
             BBG_CHECK(ntt_device(p->w4 + (size_t)k * n4, n4, 1, p->log_n + 2, OP_COSET_FFT, nullptr, sd));
         }
-        BBG_CHECK(commit(p, p->w_coef + (size_t)k * n, n, 1, out_xyz + 12 * k, st));
-        tr.mark("wire commitment", st);
+        {
+            // the commitment is only queued here — wires alternate between two streams and MSM workspaces, so the sort /
+            // fix-up / reduction kernels of one commitment run under the accumulate pass of the next — and finished below
+            cudaStream_t ms = st;
+            int workspace = 0;
+#ifndef BBG_EMULATE
+            if (p->overlap)
+            {
+                ms = p->msm_stream[k & 1];
+                workspace = k & 1;
+                BBG_CHECK(cudaEventRecord(p->ev_msm[k], st));
+                BBG_CHECK(cudaStreamWaitEvent(ms, p->ev_msm[k], 0));
+            }
+#endif
+            const void* scalars[1] = { p->w_coef + (size_t)k * n };
+            BBG_CHECK(msm_launch(workspace, scalars, 1, p->d_srs, n, ms, &tickets[k]));
+        }
+        tr.mark("wire commitment queued", st);
     }
+    for (int k = 0; k < 3; ++k)
+    {
+        hostg1::hxyzz r;
+        BBG_CHECK(msm_finish(tickets[k], &r));
+        hostg1::to_normalized_jacobian(r, out_xyz + 12 * k);
+    }
+    tr.mark("wire commitments", st);
     return bbg_rt::last_error();
 }
 
