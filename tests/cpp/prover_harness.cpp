@@ -155,8 +155,9 @@ template <typename Composer> static int run(Composer& composer, size_t log_gates
     waffle::Verifier verifier = waffle::preprocess(prover);
     const double vk_ms = ms_since(t0);
 
-    waffle::plonk_proof proof;
+    waffle::plonk_proof proof, first_proof;
     double best_prove_ms = 1e300, first_prove_ms = 0;
+    int repeat_mismatches = 0; // the prover draws no randomness: every repetition must reproduce the first proof exactly
     for (int r = 0; r < repeat; ++r)
     {
         if (r > 0) prover.reset();
@@ -165,14 +166,19 @@ template <typename Composer> static int run(Composer& composer, size_t log_gates
         const double ms = ms_since(t0);
         if (r == 0) first_prove_ms = ms;
         if (ms < best_prove_ms) best_prove_ms = ms;
+        if (r == 0) first_proof = proof;
+        else if (memcmp(&proof.W_L, &first_proof.W_L, 9 * sizeof(g1::affine_element)) != 0 ||
+                 memcmp(&proof.w_l_eval, &first_proof.w_l_eval, 7 * sizeof(fr::field_t)) != 0)
+            ++repeat_mismatches;
     }
     t0 = std::chrono::steady_clock::now();
     const bool ok = verifier.verify_proof(proof);
     const double verify_ms = ms_since(t0);
 
     printf("{\"log2_gates\": %zu, \"composer\": \"%s\", \"widgets\": %zu, \"n\": %zu, \"setup_ms\": %.3f, \"verifier_key_ms\": %.3f, \"prove_ms_first\": %.3f, "
-           "\"prove_ms_best\": %.3f, \"repeat\": %d, \"verify_ms\": %.3f, \"verified\": %s, \"proof\": {",
-           log_gates, kind, prover.widgets.size(), prover.n, setup_ms, vk_ms, first_prove_ms, best_prove_ms, repeat, verify_ms, ok ? "true" : "false");
+           "\"prove_ms_best\": %.3f, \"repeat\": %d, \"repeat_mismatches\": %d, \"verify_ms\": %.3f, \"verified\": %s, \"proof\": {",
+           log_gates, kind, prover.widgets.size(), prover.n, setup_ms, vk_ms, first_prove_ms, best_prove_ms, repeat, repeat_mismatches, verify_ms,
+           ok ? "true" : "false");
     print_pt("W_L", proof.W_L);
     print_pt("W_R", proof.W_R);
     print_pt("W_O", proof.W_O);
@@ -197,7 +203,7 @@ template <typename Composer> static int run(Composer& composer, size_t log_gates
     print_fe("linear_eval", proof.linear_eval.data, true);
     printf("}}\n");
     if (bbg_shim_report) bbg_shim_report();
-    return ok ? 0 : 1;
+    return (ok && repeat_mismatches == 0) ? 0 : 1;
 }
 
 int main(int argc, char** argv)
