@@ -76,3 +76,15 @@ def test_prover_classic_round_structure_matches_cpu_reference(srs, log_gates, bi
     assert cpu["verified"] and gpu["verified"]
     for k, v in cpu["proof"].items():
         assert gpu["proof"][k] == v, k
+
+
+@pytest.mark.parametrize("log_gates,repeat,composer", [(12, 60, "standard"), (14, 30, "mimc"), (14, 30, "extended")])
+def test_resident_prover_is_reproducible_across_streams(srs, log_gates, repeat, composer):
+    """The resident rounds run on four streams (work, second NTT stream, two commitment streams) plus an upload thread.
+    The prover draws no randomness, so every repetition must reproduce the first proof bit for bit: a missing ordering
+    between streams would show up here (the harness counts repetitions that differ)."""
+    gpu = run("prover_gpu", log_gates, repeat=repeat, composer=composer)
+    assert gpu["verified"] and gpu["repeat_mismatches"] == 0
+    cpu = run("prover_cpu", log_gates, composer=composer)
+    for k, v in cpu["proof"].items():
+        assert gpu["proof"][k] == v, k
