@@ -54,6 +54,8 @@ class Library:
         L.bbg_msm_g1_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.bbg_msm_g1_partial_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.bbg_g1_fold_partials.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.bbg_msm_g1_partial_dev_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.bbg_msm_g1_partial_finish.argtypes = [C.c_int, C.c_void_p]
         L.bbg_generate_pippenger_point_table.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.bbg_dev_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.bbg_dev_free.argtypes = [C.c_void_p]
@@ -209,6 +211,17 @@ class Library:
     def msm_partial_dev(self, d_scalars, d_table, n):
         out = np.zeros(16, dtype=np.uint64)
         self.check(self.lib.bbg_msm_g1_partial_dev(C.c_void_p(d_scalars), C.c_void_p(d_table), n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def msm_partial_dev_launch(self, d_scalars, d_table, n):
+        """Queue the MSM on the library's second stream; returns a ticket for msm_partial_finish()."""
+        t = C.c_int(-1)
+        self.check(self.lib.bbg_msm_g1_partial_dev_launch(C.c_void_p(d_scalars), C.c_void_p(d_table), n, C.byref(t)))
+        return t.value
+
+    def msm_partial_finish(self, ticket):
+        out = np.zeros(16, dtype=np.uint64)
+        self.check(self.lib.bbg_msm_g1_partial_finish(ticket, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def fold_partials(self, partials):

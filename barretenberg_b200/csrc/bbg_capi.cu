@@ -86,6 +86,8 @@ uint64_t table_fingerprint(const uint64_t* table, size_t n)
 cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 // copy engines for the host-buffer NTT path: uploads, kernels and downloads of different polynomials overlap
 cudaStream_t g_copy_in = nullptr, g_copy_out = nullptr;
+cudaStream_t g_msm_stream = nullptr; // bbg_msm_g1_partial_dev_launch: an MSM running beside the work stream
+cudaEvent_t g_msm_fence = nullptr;
 std::vector<cudaEvent_t> g_pipe_events;
 #endif
 
@@ -197,6 +199,8 @@ int bbg_init(int device)
     BBG_CHECK(cudaEventCreate(&g_ev_stop));
     BBG_CHECK(cudaStreamCreateWithFlags(&g_copy_in, cudaStreamNonBlocking));
     BBG_CHECK(cudaStreamCreateWithFlags(&g_copy_out, cudaStreamNonBlocking));
+    BBG_CHECK(cudaStreamCreateWithFlags(&g_msm_stream, cudaStreamNonBlocking));
+    BBG_CHECK(cudaEventCreateWithFlags(&g_msm_fence, cudaEventDisableTiming));
 #else
     (void)device;
 #endif
@@ -226,6 +230,14 @@ int bbg_shutdown(void)
     if (g_copy_in) cudaStreamDestroy(g_copy_in);
     if (g_copy_out) cudaStreamDestroy(g_copy_out);
     g_copy_in = g_copy_out = nullptr;
+    if (g_msm_stream)
+    {
+        cudaStreamSynchronize(g_msm_stream);
+        cudaStreamDestroy(g_msm_stream);
+    }
+    if (g_msm_fence) cudaEventDestroy(g_msm_fence);
+    g_msm_stream = nullptr;
+    g_msm_fence = nullptr;
     if (g_own_stream && g_stream) cudaStreamDestroy(g_stream);
     g_stream = nullptr;
     g_own_stream = false;
@@ -469,6 +481,30 @@ int bbg_msm_g1_partial_dev(const void* d_scalars, const void* d_table, size_t n,
     return msm_device(d_scalars, d_table, n, out_xyzz, g_stream);
 }
 
+int bbg_msm_g1_partial_dev_launch(const void* d_scalars, const void* d_table, size_t n, int* ticket)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (ticket == nullptr || (n > 0 && (d_scalars == nullptr || d_table == nullptr))) return BBG_E_BAD_ARGUMENT;
+    cudaStream_t st = g_stream;
+#ifndef BBG_EMULATE
+    // the MSM sees everything queued on the work stream so far, then runs beside whatever is queued next
+    BBG_CHECK(cudaEventRecord(g_msm_fence, g_stream));
+    BBG_CHECK(cudaStreamWaitEvent(g_msm_stream, g_msm_fence, 0));
+    st = g_msm_stream;
+#endif
+    const void* one[1] = { d_scalars };
+    return msm_launch(1, one, 1, d_table, n, st, ticket);
+}
+
+int bbg_msm_g1_partial_finish(int ticket, uint64_t out_xyzz[16])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (out_xyzz == nullptr) return BBG_E_BAD_ARGUMENT;
+    return msm_finish(ticket, out_xyzz);
+}
+
 int bbg_msm_g1_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyz[12])
 {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -699,6 +735,9 @@ int bbg_sync(void)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     BBG_CHECK(ensure_ready());
+#ifndef BBG_EMULATE
+    if (g_msm_stream) BBG_CHECK(cudaStreamSynchronize(g_msm_stream));
+#endif
     return bbg_rt::sync(g_stream);
 }
 int bbg_timer_start(void)

@@ -100,6 +100,12 @@ int bbg_msm_g1_dev(const void* d_scalars, const void* d_table, size_t n, uint64_
  * y = Y/ZZZ; ZZ = 0 <=> infinity) and the final fold of gathered partials into a normalised point */
 int bbg_msm_g1_partial_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyzz[16]);
 int bbg_g1_fold_partials(const uint64_t* partials_xyzz /* count x 16 */, size_t count, uint64_t out_xyz[12]);
+/* The same MSM in two steps, for device-resident callers with independent work to queue in between (a prover's wire
+ * commitment next to the transforms of the other wires): launch returns once the kernels are queued on a second stream,
+ * ordered behind everything queued on the work stream so far; finish waits for them and folds the windows.  d_scalars and
+ * d_table must not be modified in between.  Up to 6 tickets may be pending. */
+int bbg_msm_g1_partial_dev_launch(const void* d_scalars, const void* d_table, size_t n, int* ticket);
+int bbg_msm_g1_partial_finish(int ticket, uint64_t out_xyzz[16]);
 /* table[2i] = points[i], table[2i+1] = (beta x_i, -y_i): the layout of generate_pippenger_point_table
  * (scalar_multiplication.cpp:131-140) computed on the device; table may alias points */
 int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table_2n, size_t n);

@@ -234,3 +234,31 @@ def test_plonk_rounds_reject_misuse(emu):
     kinds = (C.c_int * 1)(9)     # unknown kind
     assert L.bbg_plonk_set_widgets(h, kinds, 1, sel) == 1007
     assert L.bbg_plonk_destroy(h) == 0
+
+
+def test_msm_launch_finish_tickets(emu):
+    """bbg_msm_g1_partial_dev_launch / _finish: several MSMs in flight (tickets finished out of order), an NTT queued in
+    between, results equal to the one-call form; an empty MSM gives infinity; a stale ticket is rejected"""
+    lib = emu
+    n = 200
+    table, _, _ = H.generator_multiples_table(41, n)
+    d_t = lib.dev_alloc(n * 128)
+    lib.h2d(d_t, table)
+    scs = [H.random_scalars_mont(50 + i, n) for i in range(3)]
+    d_s = []
+    for s in scs:
+        d = lib.dev_alloc(n * 32)
+        lib.h2d(d, s)
+        d_s.append(d)
+    tickets = [lib.msm_partial_dev_launch(d, d_t, n) for d in d_s]
+    x = H.random_scalars_mont(9, 1 << 10)
+    assert (lib.ntt("ifft", lib.ntt("fft", x.copy())) == x).all()  # work-stream traffic while the MSMs are in flight
+    empty = lib.msm_partial_dev_launch(d_s[0], d_t, 0)
+    for i in (2, 0, 1):
+        part = lib.msm_partial_finish(tickets[i])
+        assert (lib.fold_partials(part.reshape(1, 16)) == H.oracle_msm(scs[i], table)).all()
+    assert H.is_infinity(lib.fold_partials(lib.msm_partial_finish(empty).reshape(1, 16)))
+    with pytest.raises(bb.BbgError):
+        lib.msm_partial_finish(tickets[0])
+    for d in d_s + [d_t]:
+        lib.dev_free(d)
