@@ -67,6 +67,9 @@ class Library:
         L.bbg_generate_pippenger_point_table_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.bbg_compute_lagrange_polynomial_fft.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
         L.bbg_fr_domain_lookup_table.argtypes = [C.c_void_p, C.c_uint]
+        L.bbg_fr_evaluate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.bbg_fr_divide_by_pseudo_vanishing_polynomial.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
+        L.bbg_fr_compute_kate_opening_coefficients.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.bbg_srs_from_transcript.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.bbg_profile_name.restype = C.c_char_p
         L.bbg_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -229,6 +232,29 @@ class Library:
         out = np.zeros(12, dtype=np.uint64)
         self.check(self.lib.bbg_g1_fold_partials(p.ctypes.data_as(C.c_void_p), p.shape[0], out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def evaluate(self, coeffs, z):
+        """polynomial_arithmetic::evaluate: sum_i coeffs[i] z^i (canonical Montgomery limbs)."""
+        c, zz = _as_u64(coeffs, (4,)), _as_u64(z, (4,))
+        out = np.zeros(4, dtype=np.uint64)
+        self.check(self.lib.bbg_fr_evaluate(c.ctypes.data_as(C.c_void_p), c.shape[0], zz.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def divide_by_pseudo_vanishing_polynomial(self, coeffs, log2_src):
+        """In place on a C-contiguous (T, 4) uint64 array of coset evaluations; returns it."""
+        assert coeffs.dtype == np.uint64 and coeffs.flags["C_CONTIGUOUS"] and coeffs.shape[-1] == 4
+        log_t = coeffs.shape[0].bit_length() - 1
+        self.check(self.lib.bbg_fr_divide_by_pseudo_vanishing_polynomial(coeffs.ctypes.data_as(C.c_void_p), log2_src, log_t))
+        return coeffs
+
+    def compute_kate_opening_coefficients(self, src, z):
+        """Returns (quotient coefficients (n, 4), F(z))."""
+        c, zz = _as_u64(src, (4,)), _as_u64(z, (4,))
+        dest = np.zeros_like(c)
+        f = np.zeros(4, dtype=np.uint64)
+        self.check(self.lib.bbg_fr_compute_kate_opening_coefficients(c.ctypes.data_as(C.c_void_p), dest.ctypes.data_as(C.c_void_p),
+                                                                    zz.ctypes.data_as(C.c_void_p), c.shape[0], f.ctypes.data_as(C.c_void_p)))
+        return dest, f
 
     def domain_lookup_table(self, log2_size):
         """evaluation_domain::compute_lookup_table: (2 * size, 4) uint64, forward rounds then inverse rounds."""

@@ -215,6 +215,7 @@ int bbg_shutdown(void)
     bbg_rt::sync(g_stream);
     ntt_release_tables();
     msm_release_workspace();
+    plonk::release_helpers();
     g_stage_coeffs.release();
     g_stage_scalars.release();
     g_stage_table.release();
@@ -544,6 +545,45 @@ int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table
     bbg_rt::dev_free(d_pts);
     if (d_tab) bbg_rt::dev_free(d_tab);
     return e;
+}
+
+// ---- the reference's stand-alone polynomial helpers, host buffers ------------------
+int bbg_fr_evaluate(const uint64_t* coeffs, size_t n, const uint64_t z[4], uint64_t out[4])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if ((coeffs == nullptr && n > 0) || z == nullptr || out == nullptr) return BBG_E_BAD_ARGUMENT;
+    BBG_CHECK(g_stage_coeffs.ensure(n * 32 + 32));
+    BBG_CHECK(bbg_hostcopy::h2d(g_stage_coeffs.p, coeffs, n * 32, g_stream));
+    return plonk::evaluate_device(g_stage_coeffs.p, n, z, out, g_stream);
+}
+
+int bbg_fr_divide_by_pseudo_vanishing_polynomial(uint64_t* coeffs, unsigned log2_src, unsigned log2_target)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (coeffs == nullptr) return BBG_E_BAD_ARGUMENT;
+    if (log2_target > 28) return BBG_E_BAD_SIZE;
+    const size_t bytes = ((size_t)32) << log2_target;
+    BBG_CHECK(g_stage_coeffs.ensure(bytes));
+    BBG_CHECK(bbg_hostcopy::h2d(g_stage_coeffs.p, coeffs, bytes, g_stream));
+    BBG_CHECK(plonk::divide_by_pseudo_vanishing_device(g_stage_coeffs.p, log2_src, log2_target, g_stream));
+    BBG_CHECK(bbg_hostcopy::d2h(coeffs, g_stage_coeffs.p, bytes, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+
+int bbg_fr_compute_kate_opening_coefficients(const uint64_t* src, uint64_t* dest, const uint64_t z[4], size_t n, uint64_t f_out[4])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (src == nullptr || dest == nullptr || z == nullptr || f_out == nullptr || n == 0) return BBG_E_BAD_ARGUMENT;
+    BBG_CHECK(g_stage_coeffs.ensure(2 * n * 32));
+    char* d_src = (char*)g_stage_coeffs.p;
+    char* d_dest = d_src + n * 32;
+    BBG_CHECK(bbg_hostcopy::h2d(d_src, src, n * 32, g_stream));
+    BBG_CHECK(plonk::kate_opening_device(d_src, d_dest, n, z, f_out, g_stream));
+    BBG_CHECK(bbg_hostcopy::d2h(dest, d_dest, n * 32, g_stream));
+    return bbg_rt::sync(g_stream);
 }
 
 // ---- prover construction helpers -----------------------------------------------

@@ -350,13 +350,13 @@ __global__ void mimc_large_add_kernel(fe* q, const fe* w4, const fe* q4, fe alph
     }
 }
 // polynomial_arithmetic.cpp:478-560 on its own: v[i] *= (g w^i - w_n^(n-1)) / ((g w^i)^n - 1)
-__global__ void divide_vanishing_kernel(fe* v, PowTable table, QuotientConsts c, unsigned s_mask, unsigned count)
+__global__ void divide_vanishing_kernel(fe* v, PowTable table, QuotientConsts c, unsigned s_mask, unsigned count, int canonical = 0)
 {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
     {
         fe x = Fr::mul(load_fe(v + i), c.vinv[i & s_mask]);
         x = Fr::mul(x, Fr::add(Fr::mul(root_pow(table, i), c.g), c.neg_root_inv));
-        store_fe(v + i, x);
+        store_fe(v + i, canonical ? Fr::reduce(x) : x);
     }
 }
 // dst[i] (+)= sum_j c_j src_j[i]
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) kate_spine_kernel(fe* aggs_all, 
 }
 // out of place (in place the loads cannot be hoisted above the stores and every thread walks its run at memory latency)
 __global__ void kate_apply_kernel(fe* __restrict__ out, const fe* __restrict__ in, const fe* __restrict__ aggs, KatePoints pts, unsigned n, unsigned run,
-                                  unsigned aggs_stride)
+                                  unsigned aggs_stride, int canonical = 0)
 {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned first = k * run;
@@ -547,19 +547,19 @@ __global__ void kate_apply_kernel(fe* __restrict__ out, const fe* __restrict__ i
     for (; j >= first + 4; j -= 4)
     {
         const fe c0 = load_fe(f + j - 1), c1 = load_fe(f + j - 2), c2 = load_fe(f + j - 3), c3 = load_fe(f + j - 4);
-        store_fe(w + j - 1, carry);
+        store_fe(w + j - 1, canonical ? Fr::reduce(carry) : carry);
         carry = Fr::add(c0, Fr::mul(carry, z));
-        store_fe(w + j - 2, carry);
+        store_fe(w + j - 2, canonical ? Fr::reduce(carry) : carry);
         carry = Fr::add(c1, Fr::mul(carry, z));
-        store_fe(w + j - 3, carry);
+        store_fe(w + j - 3, canonical ? Fr::reduce(carry) : carry);
         carry = Fr::add(c2, Fr::mul(carry, z));
-        store_fe(w + j - 4, carry);
+        store_fe(w + j - 4, canonical ? Fr::reduce(carry) : carry);
         carry = Fr::add(c3, Fr::mul(carry, z));
     }
     for (; j > first; --j)
     {
         const fe c = load_fe(f + j - 1);
-        store_fe(w + j - 1, carry);
+        store_fe(w + j - 1, canonical ? Fr::reduce(carry) : carry);
         carry = Fr::add(c, Fr::mul(carry, z));
     }
 }
@@ -1556,6 +1556,123 @@ int round_openings(Prover* p, const uint64_t* nu_powers /* 7 x 4 */, const uint6
                       p->aggs_stride);
     g_plonk_launches += 4;
     BBG_CHECK(commit(p, quotients, n, 2, out_xyz, st));
+    return bbg_rt::last_error();
+}
+
+// =================================================================================================================
+// The same kernels behind the reference's stand-alone helpers (polynomial_arithmetic.cpp:337-373, :478-591), for callers
+// that keep the reference's round structure (shim/polynomial_arithmetic_gpu.cpp): device buffers in, no Prover object.
+// =================================================================================================================
+namespace
+{
+struct HelperBuf
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) bbg_rt::dev_free(p);
+        p = nullptr;
+        bytes = 0;
+        const int e = bbg_rt::dev_alloc(&p, need);
+        if (e == 0) bytes = need;
+        return e;
+    }
+} g_helper;
+} // namespace
+
+void release_helpers()
+{
+    if (g_helper.p) bbg_rt::dev_free(g_helper.p);
+    g_helper.p = nullptr;
+    g_helper.bytes = 0;
+}
+
+// F(z) = sum_i coeffs[i] z^i over len coefficients, canonical, to the host
+int evaluate_device(const void* d_poly, size_t len, const uint64_t* z, uint64_t out[4], cudaStream_t st)
+{
+    if (len >= ((size_t)1 << 32)) return 1002;
+    if (len == 0)
+    {
+        memset(out, 0, 32);
+        return 0;
+    }
+    const unsigned nb = (unsigned)((len + EVAL_SPAN - 1) / EVAL_SPAN);
+    BBG_CHECK(g_helper.ensure(((size_t)nb + 16) * 32));
+    fe* partial = (fe*)g_helper.p;
+    fe* result = partial + nb + 8;
+    EvalJobs jobs;
+    for (int j = 0; j < MAX_EVAL_JOBS; ++j)
+    {
+        jobs.poly[j] = nullptr;
+        jobs.len[j] = 0;
+        jobs.point[j] = Fr::zero();
+    }
+    jobs.poly[0] = (const fe*)d_poly;
+    jobs.len[0] = (unsigned)len;
+    jobs.point[0] = from_u64(z);
+    BBG_LAUNCH(eval_partial_kernel, dim3(nb, 1), dim3(EVAL_THREADS), 0, st, jobs, partial, nb + 8);
+    BBG_LAUNCH(eval_final_kernel, dim3(1), dim3(SCAN_THREADS), 0, st, jobs, (const fe*)partial, nb + 8, result);
+    g_plonk_launches += 2;
+    BBG_CHECK(bbg_rt::d2h(out, result, 32, st));
+    return bbg_rt::sync(st);
+}
+
+// coeffs[i] *= (g w_T^i - w_n^(n-1)) / ((g w_T^i)^n - 1) on the 2^log_target coset, n = 2^log_src; canonical, in place
+int divide_by_pseudo_vanishing_device(void* d_coeffs, unsigned log_src, unsigned log_target, cudaStream_t st)
+{
+    if (log_target < log_src || log_target - log_src > 2 || log_target > 28 || log_src < 1) return 1002; // subgroup of 1, 2 or 4
+    const unsigned log_s = log_target - log_src;
+    const size_t T = (size_t)1 << log_target;
+    const int lo_log = (int)(log_target < 11 ? log_target : 11);
+    const size_t lo_count = (size_t)1 << lo_log, hi_count = log_target > (unsigned)lo_log ? (size_t)1 << (log_target - lo_log) : 0;
+    BBG_CHECK(g_helper.ensure((lo_count + hi_count + 8) * 32));
+    fe* lo = (fe*)g_helper.p;
+    fe* hi = lo + lo_count;
+    const fe w = host_root_of_unity(log_target);
+    BBG_LAUNCH_NOSYNC(powers_kernel, dim3((unsigned)((lo_count + 127) / 128)), dim3(128), st, lo, w, (unsigned)lo_count);
+    if (hi_count) BBG_LAUNCH_NOSYNC(powers_kernel, dim3((unsigned)((hi_count + 127) / 128)), dim3(128), st, hi, host_pow(w, lo_count), (unsigned)hi_count);
+    PowTable table{ lo, hi_count ? hi : nullptr, lo_log };
+    QuotientConsts c;
+    c.g = gen_k1();
+    c.beta = c.gamma = c.alpha = c.alpha_sqr = c.alpha_cube = c.g_beta = c.z_scale = Fr::zero();
+    c.one = Fr::one();
+    c.neg_root_inv = Fr::reduce(Fr::neg(Fr::invert(host_root_of_unity(log_src))));
+    fe gn = c.g;
+    for (unsigned i = 0; i < log_src; ++i) gn = Fr::reduce(Fr::sqr(gn));
+    const fe ws = host_root_of_unity(log_s);
+    fe cur = gn;
+    for (unsigned j = 0; j < 4; ++j)
+    {
+        c.vinv[j] = j < (1u << log_s) ? Fr::invert(Fr::reduce(Fr::sub(cur, Fr::one()))) : Fr::zero();
+        cur = Fr::reduce(Fr::mul(cur, ws));
+    }
+    BBG_LAUNCH_NOSYNC(divide_vanishing_kernel, dim3(grid_for(T, 128)), dim3(128), st, (fe*)d_coeffs, table, c, (1u << log_s) - 1u, (unsigned)T, 1);
+    g_plonk_launches += 3;
+    return bbg_rt::last_error();
+}
+
+// d_dest = (F(X) - F(z)) / (X - z) for F = d_src (n coefficients; d_dest must not alias d_src), canonical; F(z) to the host
+int kate_opening_device(const void* d_src, void* d_dest, size_t n, const uint64_t* z_, uint64_t f_out[4], cudaStream_t st)
+{
+    if (n == 0 || n >= ((size_t)1 << 32) || d_src == d_dest) return 1007;
+    BBG_CHECK(evaluate_device(d_src, n, z_, f_out, st)); // (uses, then releases, the helper buffer before the scan does)
+    const unsigned run = ZRUN;
+    const unsigned runs = (unsigned)((n + run - 1) / run);
+    const unsigned per = (runs + SCAN_THREADS - 1) / SCAN_THREADS;
+    const unsigned stride = (runs + 7) & ~7u;
+    BBG_CHECK(g_helper.ensure(((size_t)stride + 8) * 32));
+    fe* aggs = (fe*)g_helper.p;
+    KatePoints pts;
+    pts.z[0] = pts.z[1] = from_u64(z_);
+    pts.z_run[0] = pts.z_run[1] = host_pow(pts.z[0], run);
+    pts.z_span[0] = pts.z_span[1] = host_pow(pts.z_run[0], per);
+    BBG_LAUNCH_NOSYNC(kate_reduce_kernel, dim3((runs + 127) / 128, 1), dim3(128), st, (const fe*)d_src, aggs, pts, (unsigned)n, run, stride);
+    BBG_LAUNCH(kate_spine_kernel, dim3(1), dim3(SCAN_THREADS), 0, st, aggs, pts, runs, stride);
+    BBG_LAUNCH_NOSYNC(kate_apply_kernel, dim3((runs + 127) / 128, 1), dim3(128), st, (fe*)d_dest, (const fe*)d_src, (const fe*)aggs, pts, (unsigned)n, run,
+                      stride, 1);
+    g_plonk_launches += 3;
     return bbg_rt::last_error();
 }
 

@@ -29,6 +29,11 @@ int round_evaluations(Prover* p, const uint64_t* zeta, const uint64_t* zeta_omeg
 int round_linearise(Prover* p, const uint64_t* scalars, const uint64_t* zeta, uint64_t out_eval[4], cudaStream_t st);
 int round_openings(Prover* p, const uint64_t* nu_powers, const uint64_t* beta_inv, const uint64_t* zeta, const uint64_t* zeta_omega,
                    const uint64_t* wire_shift, const uint64_t* selector_terms, uint64_t* out_xyz, cudaStream_t st);
+// stand-alone helpers on device buffers (polynomial_arithmetic.cpp:337-373, :478-560, :562-591)
+int evaluate_device(const void* d_poly, size_t len, const uint64_t* z, uint64_t out[4], cudaStream_t st);
+int divide_by_pseudo_vanishing_device(void* d_coeffs, unsigned log_src, unsigned log_target, cudaStream_t st);
+int kate_opening_device(const void* d_src, void* d_dest, size_t n, const uint64_t* z, uint64_t f_out[4], cudaStream_t st);
+void release_helpers();
 size_t launch_count();
 } // namespace plonk
 } // namespace bbg

@@ -9,8 +9,10 @@
 //   -Difft_with_constant=cpu_reference_ifft_with_constant -Dcoset_fft=cpu_reference_coset_fft
 //   -Dcoset_fft_with_constant=cpu_reference_coset_fft_with_constant -Dcoset_ifft=cpu_reference_coset_ifft
 //   -Dcompute_lagrange_polynomial_fft=cpu_reference_compute_lagrange_polynomial_fft
-// (its element-wise helpers — evaluate, divide_by_pseudo_vanishing_polynomial, compute_kate_opening_coefficients,
-// ... — keep their reference CPU bodies) and add this file for the seven names above.
+//   -Devaluate=cpu_reference_evaluate -Ddivide_by_pseudo_vanishing_polynomial=cpu_reference_divide_by_pseudo_vanishing_polynomial
+//   -Dcompute_kate_opening_coefficients=cpu_reference_compute_kate_opening_coefficients
+// (copy_polynomial, add, mul, compress_fft, get_lagrange_evaluations, ... keep their reference bodies: memory-bound or
+// scalar host code that a PCIe round trip would only slow down) and add this file for the names above.
 // evaluation_domain.cpp is unchanged: only domain.log2_size crosses the boundary; root, 1/n, the coset generator
 // and every twiddle are derived on the device from the curve constants.
 #include <cstdio>
@@ -90,6 +92,62 @@ void compute_lagrange_polynomial_fft(fr::field_t* l_1_coefficients, const evalua
         fprintf(stderr, "bbgpu shim: compute_lagrange_polynomial_fft failed: %s (no CPU fallback)\n", bbg_error_string(e));
         abort();
     }
+}
+
+// ---- the three heavy stand-alone helpers -------------------------------------------------------
+// Callers: polynomial::evaluate (polynomial.cpp), prover.cpp:443-444 / :638-640 and the widgets in the reference's round
+// structure.  Build the reference file additionally with
+//   -Devaluate=cpu_reference_evaluate -Ddivide_by_pseudo_vanishing_polynomial=cpu_reference_divide_by_pseudo_vanishing_polynomial
+//   -Dcompute_kate_opening_coefficients=cpu_reference_compute_kate_opening_coefficients
+namespace
+{
+int ensure_library()
+{
+    static bool ready = false;
+    if (ready) return 0;
+    const char* dev = getenv("BBG_DEVICE");
+    int e = bbg_init(dev ? atoi(dev) : 0);
+    if (e == 0) bbg_set_auto_srs_cache(1);
+    if (e == 0) bbg_shim::stats().after_init();
+    ready = (e == 0);
+    return e;
+}
+void die(const char* what, int e)
+{
+    fprintf(stderr, "bbgpu shim: %s failed: %s (no CPU fallback)\n", what, bbg_error_string(e));
+    abort();
+}
+} // namespace
+
+// polynomial_arithmetic.cpp:337-373
+fr::field_t evaluate(const fr::field_t* coeffs, const fr::field_t& z, const size_t n)
+{
+    int e = ensure_library();
+    bbg_shim::Timer timer("evaluate");
+    fr::field_t r;
+    if (e == 0) e = bbg_fr_evaluate((const uint64_t*)coeffs, n, z.data, r.data);
+    if (e != 0) die("evaluate", e);
+    return r;
+}
+
+// polynomial_arithmetic.cpp:478-560
+void divide_by_pseudo_vanishing_polynomial(fr::field_t* coeffs, const evaluation_domain& src_domain, const evaluation_domain& target_domain)
+{
+    int e = ensure_library();
+    bbg_shim::Timer timer("divide_by_pseudo_vanishing_polynomial");
+    if (e == 0) e = bbg_fr_divide_by_pseudo_vanishing_polynomial((uint64_t*)coeffs, (unsigned)src_domain.log2_size, (unsigned)target_domain.log2_size);
+    if (e != 0) die("divide_by_pseudo_vanishing_polynomial", e);
+}
+
+// polynomial_arithmetic.cpp:562-591 (dest may alias src: polynomial::compute_kate_opening_coefficients passes its own buffer twice)
+fr::field_t compute_kate_opening_coefficients(const fr::field_t* src, fr::field_t* dest, const fr::field_t& z, const size_t n)
+{
+    int e = ensure_library();
+    bbg_shim::Timer timer("compute_kate_opening_coefficients");
+    fr::field_t f;
+    if (e == 0) e = bbg_fr_compute_kate_opening_coefficients((const uint64_t*)src, (uint64_t*)dest, z.data, n, f.data);
+    if (e != 0) die("compute_kate_opening_coefficients", e);
+    return f;
 }
 } // namespace polynomial_arithmetic
 } // namespace barretenberg

@@ -117,6 +117,19 @@ int bbg_generate_pippenger_point_table_dev(const void* d_points, void* d_table, 
  * memory (n x 64 bytes).  start / step are Fr elements in Montgomery form. */
 int bbg_g1_generate_multiples_dev(const uint64_t start[4], const uint64_t step[4], void* d_points, size_t n);
 
+/* ---- the reference's stand-alone polynomial helpers on host buffers ------------------------------
+ * For callers that keep the reference's round structure (shim/polynomial_arithmetic_gpu.cpp); the resident rounds below
+ * use the same kernels without leaving HBM.
+ * polynomial_arithmetic::evaluate (polynomial_arithmetic.hpp:41, .cpp:337-373): out = sum_i coeffs[i] z^i, canonical */
+int bbg_fr_evaluate(const uint64_t* coeffs, size_t n, const uint64_t z[4], uint64_t out[4]);
+/* divide_by_pseudo_vanishing_polynomial (.hpp:57, .cpp:478-560): coeffs = 2^log2_target coset evaluations, multiplied in
+ * place by (x - w_n^(n-1)) / (x^n - 1), n = 2^log2_src, x = g w_T^i; log2_target - log2_src in {0, 1, 2}; canonical */
+int bbg_fr_divide_by_pseudo_vanishing_polynomial(uint64_t* coeffs, unsigned log2_src, unsigned log2_target);
+/* compute_kate_opening_coefficients (.hpp:61, .cpp:562-591): dest = (F(X) - F(z)) / (X - z) for F = src (n coefficients),
+ * canonical (the reference's serial recurrence leaves lazily reduced values: same field elements); f_out = F(z);
+ * dest may alias src */
+int bbg_fr_compute_kate_opening_coefficients(const uint64_t* src, uint64_t* dest, const uint64_t z[4], size_t n, uint64_t f_out[4]);
+
 /* ---- prover construction ----------------------------------------------------
  * evaluation_domain::compute_lookup_table (polynomials/evaluation_domain.hpp:35, evaluation_domain.cpp:33-54, :172-178):
  * roots = 2 * 2^log2_size field elements (host); per direction round i (m = 2^(i+1), i = 0 .. log2_size - 2) holds

@@ -291,6 +291,20 @@ void ref_compute_lagrange_polynomial_fft(uint64_t* l_1, size_t src_n, size_t tar
     polynomial_arithmetic::compute_lagrange_polynomial_fft((fr::field_t*)l_1, s, t);
 }
 
+// polynomial_arithmetic.cpp:478-560; coeffs holds target_n elements (caller-aligned), in place
+void ref_divide_by_pseudo_vanishing_polynomial(uint64_t* coeffs, size_t src_n, size_t target_n)
+{
+    evaluation_domain s(src_n), t(target_n);
+    polynomial_arithmetic::divide_by_pseudo_vanishing_polynomial((fr::field_t*)coeffs, s, t);
+}
+// polynomial_arithmetic.cpp:562-591; returns F(z) in f_out, the quotient in dest (caller-aligned, n elements, lazily reduced)
+void ref_compute_kate_opening_coefficients(const uint64_t* src, uint64_t* dest, const uint64_t* z, size_t n, uint64_t* f_out)
+{
+    fr::field_t zz = ldr(z);
+    fr::field_t f = polynomial_arithmetic::compute_kate_opening_coefficients((const fr::field_t*)src, (fr::field_t*)dest, zz, n);
+    memcpy(f_out, &f, 32);
+}
+
 void* ref_aligned_alloc(size_t bytes) { return aligned_alloc(64, (bytes + 63) & ~(size_t)63); }
 void ref_aligned_free(void* p) { free(p); }
 

@@ -98,6 +98,9 @@ def ref():
         lib.ref_g1_arith_progression.argtypes = [u64p, u64p, u64p, C.c_size_t]
         lib.ref_g1_batch_normalize.argtypes = [u64p, C.c_size_t]
         lib.ref_poly_evaluate.argtypes = [u64p, u64p, C.c_size_t, u64p]
+        if hasattr(lib, "ref_divide_by_pseudo_vanishing_polynomial"):
+            lib.ref_divide_by_pseudo_vanishing_polynomial.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
+            lib.ref_compute_kate_opening_coefficients.argtypes = [C.c_void_p, C.c_void_p, u64p, C.c_size_t, u64p]
         lib.ref_r_inv.restype = C.c_uint64
         lib.ref_compute_lagrange_polynomial_fft.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
         lib.ref_aligned_alloc.restype = C.c_void_p

@@ -404,3 +404,60 @@ def test_msm_launch_finish_tickets(lib):
         lib.msm_partial_finish(tickets[0])
     for d in d_s + [d_t]:
         lib.dev_free(d)
+
+
+# ---- the reference's stand-alone polynomial helpers (polynomial_arithmetic.cpp:337-373, :478-591) ----------------------
+def _canonical(a):
+    """lazily reduced (k, 4) limbs -> canonical limbs"""
+    out = a.copy()
+    for i in range(a.shape[0]):
+        out[i] = H.to_limbs(H.from_limbs(a[i]) % H.FR_MODULUS)
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 31, 4097, 1 << 16, 3 << 18, (1 << 20) + 5])
+def test_poly_evaluate(lib, n):
+    lib = lib
+    c = H.random_scalars_mont(70 + n % 97, n)
+    z = H.random_scalars_mont(71, 1)[0]
+    want = np.zeros(4, dtype=np.uint64)
+    H.oracle().orc_poly_evaluate(H.ptr(c), H.ptr(z), n, H.ptr(want))
+    assert (lib.evaluate(c, z) == _canonical(want.reshape(1, 4))[0]).all()
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("log_src,log_target", [(3, 5), (12, 13), (16, 18), (20, 21), (20, 22)])
+def test_divide_by_pseudo_vanishing_polynomial(lib, log_src, log_target):
+    lib = lib
+    T = 1 << log_target
+    x = H.random_scalars_mont(80 + log_target, T)
+    r = H.ref()
+    buf = r.ref_aligned_alloc(T * 32)
+    import ctypes as C
+    C.memmove(buf, x.ctypes.data, T * 32)
+    r.ref_divide_by_pseudo_vanishing_polynomial(buf, 1 << log_src, T)
+    want = np.frombuffer((C.c_uint64 * (4 * T)).from_address(buf), dtype=np.uint64).reshape(T, 4).copy()
+    r.ref_aligned_free(buf)
+    got = lib.divide_by_pseudo_vanishing_polynomial(x.copy(), log_src)
+    assert (got == want).all()
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("n", [1, 33, 5000, 1 << 16, (1 << 20) - 3, 1 << 20])
+def test_compute_kate_opening_coefficients(lib, n):
+    """dest = (F(X) - F(z)) / (X - z): the reference's serial recurrence vs the suffix scan, as values; F(z) limb-equal"""
+    lib = lib
+    import ctypes as C
+    src = H.random_scalars_mont(90 + n % 89, n)
+    z = H.random_scalars_mont(91, 1)[0]
+    r = H.ref()
+    a, b = r.ref_aligned_alloc(n * 32), r.ref_aligned_alloc(n * 32)
+    C.memmove(a, src.ctypes.data, n * 32)
+    f_ref = np.zeros(4, dtype=np.uint64)
+    r.ref_compute_kate_opening_coefficients(a, b, H.ptr(z), n, H.ptr(f_ref))
+    want = np.frombuffer((C.c_uint64 * (4 * n)).from_address(b), dtype=np.uint64).reshape(n, 4).copy()
+    r.ref_aligned_free(a)
+    r.ref_aligned_free(b)
+    got, f = lib.compute_kate_opening_coefficients(src, z)
+    assert (f == f_ref).all()
+    assert (got == _canonical(want)).all()
