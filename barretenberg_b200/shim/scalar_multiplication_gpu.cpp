@@ -7,8 +7,9 @@
 // How to link (INTEGRATION.md has the CMake lines): build the reference's scalar_multiplication.cpp with
 //   -Dpippenger=cpu_reference_pippenger -Dbatched_scalar_multiplications=cpu_reference_batched_scalar_multiplications
 //   -Dgenerate_pippenger_point_table=cpu_reference_generate_pippenger_point_table
-// so its ten experimental / helper symbols (pippenger_low_memory, alt_pippenger, pippenger_precomputed, ...) keep
-// their reference CPU bodies, and add this file for the three names above.  Replace pippenger and
+//   -Dalt_pippenger=cpu_reference_alt_pippenger -Dpippenger_low_memory=cpu_reference_pippenger_low_memory
+// so its other helper symbols (compute_wnaf_state, pippenger_internal, pippenger_precomputed, ...) keep their reference
+// CPU bodies, and add this file for the five names above.  Replace pippenger and
 // batched_scalar_multiplications TOGETHER (the reference's batched version calls pippenger from inside an OpenMP
 // region with sub-range pointers, scalar_multiplication.cpp:731-738).
 //
@@ -80,6 +81,18 @@ g1::element pippenger(fr::field_t* scalars, g1::affine_element* points, size_t n
     int e = bbg_msm_g1((const uint64_t*)scalars, (const uint64_t*)points, num_initial_points, (uint64_t*)&out);
     if (e != 0) die("pippenger", e);
     return out;
+}
+
+// scalar_multiplication.cpp:317-455 (bucket-ordered prototype) and :142-263 (in-place, scalar-mutating variant): the same
+// group element as pippenger, called only by the reference's benchmarks (bench_barretenberg.cpp:487-498).  Forwarded to
+// the same GPU MSM; unlike the reference's pippenger_low_memory the scalars are NOT overwritten.
+g1::element alt_pippenger(fr::field_t* scalars, g1::affine_element* points, size_t num_initial_points, size_t forced_bucket_width)
+{
+    return pippenger(scalars, points, num_initial_points, forced_bucket_width);
+}
+g1::element pippenger_low_memory(fr::field_t* scalars, g1::affine_element* points, size_t num_points)
+{
+    return pippenger(scalars, points, num_points, 0);
 }
 
 // scalar_multiplication.cpp:650-772: writes only mul_state[i].output, normalised
