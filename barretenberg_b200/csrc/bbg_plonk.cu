@@ -1,8 +1,8 @@
-// HBM-resident standard-PLONK prover rounds for sm_100a (device-resident polynomials,
-// the prover's element-wise loops, and its two serial recurrences as parallel scans).
+// HBM-resident PLONK prover rounds for sm_100a (device-resident polynomials, the prover's
+// element-wise loops, and its two serial recurrences as parallel scans).
 //
-// Replaces the data-parallel body of waffle::Prover::construct_proof for circuits built from the arithmetic widget
-//   waffle/proof_system/prover/prover.cpp:65-690, widgets/arithmetic_widget.cpp:60-122, permutation.hpp:13-88,
+// Replaces the data-parallel body of waffle::Prover::construct_proof for circuits built from the reference's four widgets
+//   waffle/proof_system/prover/prover.cpp:65-690, widgets/{arithmetic,bool,mimc,sequential}_widget.cpp, permutation.hpp:13-88,
 //   polynomials/polynomial_arithmetic.cpp:337-373 (evaluate), :478-560 (divide_by_pseudo_vanishing_polynomial),
 //   :562-591 (compute_kate_opening_coefficients), fields/field.hpp:503-522 (batch_invert)
 // The Fiat-Shamir transcript (keccak, challenge.hpp) and the handful of scalar formulas (linearizer.hpp,
@@ -15,7 +15,12 @@
 // (tests/test_gpu_prover_dropin.py, tests/test_emul_prover.py).  Intermediate polynomials live in [0, 2p) ("coarse");
 // everything that leaves the device is canonical.
 //
-// Layout in HBM for a circuit of n = 2^k gates (field element = 32 B; n = 2^20 -> 2.3 GB in total):
+// Streams: the work stream the C ABI hands in, a second stream for the 4n coset transforms that only need earlier rounds'
+// results, two streams for the pipelined wire commitments of round 1, and an upload stream fed by a helper thread.
+// Circuit constants (permutation / selector polynomials in all the forms the rounds need) stay on the device between
+// proofs behind a fingerprint of the host buffers (proving-key cache).
+//
+// Layout in HBM for a circuit of n = 2^k gates (field element = 32 B; 86 n elements, n = 2^20 -> 2.9 GB in total):
 //   w_lag[3][n]  witness, Lagrange form          w_coef[3][n]   coefficient form       w4[3][4n]  coset evaluations
 //   sigma_lag[3][n], sigma[3][n]  permutation polys, Lagrange / coefficient form       s4[3][4n]  their coset evaluations
 //   z[n], z4[4n] grand product                   q[11][n], q2[9][2n], q4[2][4n]  selectors (all four widget kinds)   l1[2n]
