@@ -30,6 +30,7 @@
 #include "bbg_host_g1.h"
 
 #include <chrono>
+#include <stdlib.h>
 #include <vector>
 
 namespace bbg
@@ -276,7 +277,7 @@ BBG_D affine_pt fetch_point(const fe* table, uint32_t entry)
     return p;
 }
 
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* sorted, const uint32_t* offsets, uint32_t total_buckets,
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* sorted, const uint32_t* offsets, uint32_t total_buckets,
                                                             const fe* table, uint32_t S, fe* buckets, fe* head, fe* tail)
 {
     const uint32_t E = offsets[total_buckets];
@@ -627,6 +628,28 @@ void pick_windows(size_t n, int& c_out, int& W_out)
     }
 }
 
+// Slice length of the accumulate pass.  Every thread performs exactly S mixed additions, so the pass runs in waves of
+// 128 x 4 x #SM threads and a partly filled last wave is pure loss: 2^24 entries at S = 64 are 3.46 waves, i.e. 87%
+// (what ncu showed for the multiply pipe).  S is chosen so that the slices fill a whole number of waves, near 64 entries
+// per thread for large inputs and down to 16 for small ones (which otherwise occupy a fraction of the machine).
+uint32_t pick_slice(size_t max_entries)
+{
+    if (const char* e = getenv("BBG_MSM_SLICE")) // development override
+    {
+        const int v = atoi(e);
+        if (v >= 8 && v <= 512) return (uint32_t)v;
+    }
+    const double wave = 128.0 * 4.0 * (double)bbg_rt::num_sms();
+    const double per_wave_thread = (double)max_entries / wave; // entries per thread if everything ran in ONE wave
+    if (per_wave_thread <= 16.0) return 16;
+    const double target = max_entries >= ((size_t)1 << 26) ? 128.0 : 64.0;
+    size_t k = (size_t)(per_wave_thread / target + 0.999); // waves at ~target entries per thread
+    if (k < 1) k = 1;
+    uint32_t S = (uint32_t)(per_wave_thread / (double)k + 0.999);
+    if (S < 16) S = 16;
+    return S;
+}
+
 Plan make_plan(size_t n)
 {
     Plan pl;
@@ -636,7 +659,7 @@ Plan make_plan(size_t n)
     pl.NB = 1u << (pl.c - 1);
     pl.total_buckets = pl.NB * (uint32_t)pl.W;
     pl.max_entries = pl.num_points * (size_t)pl.W;
-    pl.S = pl.max_entries >= ((size_t)1 << 26) ? 128 : (pl.max_entries >= ((size_t)1 << 20) ? 64 : 16);
+    pl.S = pick_slice(pl.max_entries);
     pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
     pl.chunk_log = CHUNK_LOG < pl.c - 1 ? CHUNK_LOG : pl.c - 1;
     pl.chunks_per_window = pl.NB >> pl.chunk_log;
