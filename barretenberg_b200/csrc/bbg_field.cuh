@@ -54,6 +54,7 @@ struct FqParams
     // cube root of unity beta (fq.hpp:53-56), Montgomery form
     BBG_CONST8(CUBE, 0xD782E155u, 0x71930C11u, 0xFFBE3323u, 0xA6BB947Cu, 0xD4741444u, 0xAA303344u, 0x26594943u, 0x2C3B3F0Du)
     static constexpr uint32_t NINV = 0xE4866389u; // low word of r_inv (fq.hpp:64): -p^-1 mod 2^32
+    BBG_CONST8(NPRIME, 0xE4866389u, 0x87D20782u, 0x1ECA6AC9u, 0x9EDE7D65u, 0x1833DA80u, 0xD8AFCBD0u, 0x91888C6Bu, 0xF57A22B7u) // -p^-1 mod 2^256
 };
 struct FrParams
 {
@@ -64,6 +65,7 @@ struct FrParams
     // lambda (fr.hpp:54-57, stored by the reference as fr::beta), Montgomery form
     BBG_CONST8(CUBE, 0x4A0329B3u, 0x93E7CEDEu, 0x7A96C167u, 0x7D4FDCA7u, 0xB19A750Au, 0x8BE4BA08u, 0xA5661C25u, 0x1CBD5653u)
     static constexpr uint32_t NINV = 0xEFFFFFFFu; // low word of r_inv (fr.hpp:81)
+    BBG_CONST8(NPRIME, 0xEFFFFFFFu, 0xC2E1F593u, 0x4C6911B3u, 0x6586864Bu, 0x99062391u, 0xE39A9828u, 0x0D8341B2u, 0x73F82F1Du) // -p^-1 mod 2^256
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -228,6 +230,36 @@ BBG_HD void shift_mad_row(uint32_t* sh, uint32_t& e0, const uint32_t* x, uint32_
     }
 #endif
 }
+
+// ---- single-instruction carry-chain pieces (device only; used by the truncated products of Field::mul_const) -------
+#if defined(__CUDA_ARCH__)
+BBG_D void mad_lo_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b)); }
+BBG_D void madc_lo_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b)); }
+BBG_D void madc_hi_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b)); }
+BBG_D void addc_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+BBG_D void add_cc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+BBG_D void addc(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+
+// acc[LIMB ..] += x[J] * y * 2^(32 LIMB) + x[J+2] * y * 2^(32 (LIMB+2)) + ...  as ONE carry chain over the products whose
+// low word lies below limb END; the product that straddles END contributes its low word only.  FIRST starts the chain.
+template <int J, int LIMB, int END, bool FIRST> BBG_D void mad_chain(uint32_t* acc, const uint32_t* x, uint32_t y)
+{
+    if constexpr (J < 8 && LIMB < END)
+    {
+        if constexpr (FIRST) mad_lo_cc(acc[LIMB], x[J], y);
+        else madc_lo_cc(acc[LIMB], x[J], y);
+        if constexpr (LIMB + 1 < END)
+        {
+            madc_hi_cc(acc[LIMB + 1], x[J], y);
+            mad_chain<J + 2, LIMB + 2, END, false>(acc, x, y);
+        }
+    }
+    else if constexpr (LIMB < END)
+    {
+        addc(acc[LIMB], acc[LIMB], 0u); // ran out of words of x below END: park the carry in the next (so far small) limb
+    }
+}
+#endif
 } // namespace cc
 
 // ---------------------------------------------------------------------------------------------
@@ -309,6 +341,138 @@ template <typename FP> struct Field
         return r;
     }
     static BBG_HD fe sqr(const fe& a) { return mul(a, a); }
+
+    // Product with a constant known in advance (NTT twiddles): r = a * w mod p as a residue in [0, 2p), for ANY a < 4p
+    // and w < p given in PLAIN form together with wq = floor(w * 2^256 / p).  When a is a Montgomery-form value, so is
+    // the result (a R * w = (a w) R), i.e. this replaces mul(a, to_mont(w)) and returns the same residue class.
+    //   q = floor(a * wq / 2^256) from the product columns >= 6 only (the dropped columns are worth < 2^-28 of a unit),
+    //   r = a * w - q * p  (mod 2^256);   a w / p - (a wq + dropped) / 2^256 < 4p / 2^256 + 2^-28 < 1  =>  r in [0, 2p).
+    // 43 + 28 + 28 wide products and 16 low-word products instead of the Montgomery product's 128 + 8: the multiply pipe
+    // has ~25% less to issue (the quotient needs no low half, the remainder no high half).
+    static BBG_HD fe mul_const(const fe& a, const fe& w, const fe& wq)
+    {
+        fe r;
+#if defined(__CUDA_ARCH__)
+        // ---- q: limbs 8..15 of a * wq; E holds the products at even limb positions (limbs 6..15), O the odd (7..15)
+        uint32_t E[16], O[16];
+#pragma unroll
+        for (int i = 6; i < 16; ++i) E[i] = O[i] = 0;
+        mul_const_hi<0>(E, O, a.v, wq.v);
+        uint32_t q[8], t7;
+        cc::add_cc(t7, E[7], O[7]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) cc::addc_cc(q[i], E[8 + i], O[8 + i]);
+        cc::addc(q[7], E[15], O[15]);
+        (void)t7;
+        // ---- r = low 256 bits of a * w + q * (2^256 - p)
+        uint32_t L[8], M[8], np[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            L[i] = M[i] = 0;
+            np[i] = i == 0 ? 0u - FP::P(0) : ~FP::P(i);
+        }
+        mul_const_lo<0>(L, M, a.v, w.v);
+        mul_const_lo<0>(L, M, np, q);
+        r.v[0] = L[0];
+        cc::add_cc(r.v[1], L[1], M[1]);
+#pragma unroll
+        for (int i = 2; i < 7; ++i) cc::addc_cc(r.v[i], L[i], M[i]);
+        cc::addc(r.v[7], L[7], M[7]);
+#else
+        // portable restatement with the same truncation (columns >= 6 of a * wq)
+        uint64_t col[17];
+        for (int k = 0; k < 17; ++k) col[k] = 0;
+        for (int i = 0; i < 8; ++i)
+        {
+            for (int j = 0; j < 8; ++j)
+            {
+                if (i + j < 6) continue;
+                const uint64_t t = (uint64_t)a.v[j] * wq.v[i];
+                col[i + j] += (uint32_t)t;
+                col[i + j + 1] += t >> 32;
+            }
+        }
+        uint32_t q[8];
+        uint64_t carry = 0;
+        for (int k = 6; k < 16; ++k)
+        {
+            const uint64_t t = col[k] + carry;
+            if (k >= 8) q[k - 8] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        uint64_t low[9];
+        for (int k = 0; k < 9; ++k) low[k] = 0;
+        for (int i = 0; i < 8; ++i)
+        {
+            const uint32_t np_i = i == 0 ? 0u - FP::P(0) : ~FP::P(i);
+            for (int j = 0; i + j < 8; ++j)
+            {
+                const uint64_t t = (uint64_t)a.v[j] * w.v[i];
+                const uint64_t u = (uint64_t)q[j] * np_i;
+                low[i + j] += (uint64_t)(uint32_t)t + (uint32_t)u;
+                low[i + j + 1] += (t >> 32) + (u >> 32);
+            }
+        }
+        carry = 0;
+        for (int k = 0; k < 8; ++k)
+        {
+            const uint64_t t = low[k] + carry;
+            r.v[k] = (uint32_t)t;
+            carry = t >> 32;
+        }
+#endif
+        return r;
+    }
+    // wq = floor(w * 2^256 / p) for mul_const, from the canonical Montgomery form of w:  w 2^256 = wq p + w_mont, so
+    // wq = -w_mont / p = w_mont * NPRIME (mod 2^256).  Table generation only - plain 64-bit arithmetic.
+    static BBG_HD fe const_quotient(const fe& w_mont)
+    {
+        uint64_t low[9];
+        for (int k = 0; k < 9; ++k) low[k] = 0;
+        for (int i = 0; i < 8; ++i)
+        {
+            for (int j = 0; i + j < 8; ++j)
+            {
+                const uint64_t t = (uint64_t)w_mont.v[j] * FP::NPRIME(i);
+                low[i + j] += (uint32_t)t;
+                low[i + j + 1] += t >> 32;
+            }
+        }
+        fe r;
+        uint64_t carry = 0;
+        for (int k = 0; k < 8; ++k)
+        {
+            const uint64_t t = low[k] + carry;
+            r.v[k] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        return r;
+    }
+#if defined(__CUDA_ARCH__)
+    // rows of the quotient estimate: word I of wq times the words of a that reach column 6 or above
+    template <int I> static BBG_D void mul_const_hi(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* wq)
+    {
+        if constexpr (I < 8)
+        {
+            constexpr int JE = I <= 6 ? 6 - I : 1; // first word of a with i + j even and >= 6
+            constexpr int JO = 7 - I;              // first word of a with i + j odd and >= 7
+            cc::mad_chain<JE, I + JE, 16, true>(E, a, wq[I]);
+            cc::mad_chain<JO, I + JO, 16, true>(O, a, wq[I]);
+            mul_const_hi<I + 1>(E, O, a, wq);
+        }
+    }
+    // rows of a low (mod 2^256) product: L += even-position products, M += odd-position products
+    template <int I> static BBG_D void mul_const_lo(uint32_t* L, uint32_t* M, const uint32_t* x, const uint32_t* y)
+    {
+        if constexpr (I < 8)
+        {
+            cc::mad_chain<(I & 1), I + (I & 1), 8, true>(L, x, y[I]);
+            cc::mad_chain<((I + 1) & 1), I + ((I + 1) & 1), 8, true>(M, x, y[I]);
+            mul_const_lo<I + 1>(L, M, x, y);
+        }
+    }
+#endif
 
     // [0,2p) -> [0,p)   (reference: reduce_once)
     static BBG_HD fe reduce(const fe& a)

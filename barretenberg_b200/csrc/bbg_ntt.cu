@@ -41,7 +41,16 @@ constexpr int TILE = 1 << TILE_LOG;
 constexpr int NT = 256;
 constexpr int PLANE = TILE;                 // words per limb plane
 constexpr int TWP = (TILE >> 1) + (TILE >> 6); // words per twiddle limb plane (padded)
-constexpr size_t SMEM_BYTES = (size_t)(8 * PLANE + 8 * TWP) * 4;
+// Tiles per CTA: the twiddle image holds every twiddle twice (plain value and precomputed quotient, Fr::mul_const), 66 KiB,
+// so two 256-thread halves of one 512-thread CTA share it, each half working on its own tile with its own named barrier
+// (2 x 64 KiB data + 66 KiB twiddles = 194 KiB, one CTA per SM; before: two 256-thread CTAs with a 33 KiB image each).
+#ifdef BBG_EMULATE
+constexpr int TPC = 1; // (the emulation has one barrier per block and no shared-memory limit)
+#else
+constexpr int TPC = 2;
+#endif
+constexpr size_t SMEM_BYTES = (size_t)(TPC * 8 * PLANE + 16 * TWP) * 4;
+constexpr size_t SMEM_BYTES_SMALL = (size_t)(8 * PLANE + 16 * TWP) * 4;
 constexpr int LO_TABLE_LOG = 11; // w^e = Thi[e >> 11] * Tlo[e & 2047] when generating matrices
 
 #if defined(__CUDA_ARCH__) && defined(BBG_NTT_NOINLINE_MUL)
@@ -59,6 +68,9 @@ __device__ __noinline__ fe fr_mul_shared(const fe a, const fe b) { return Fr::mu
 #endif
 #if BBG_NTT_ABLATE == 1 || BBG_NTT_ABLATE == 2
 #define NTT_SYNC() ((void)0)
+#elif defined(__CUDA_ARCH__)
+// barrier over the 256 threads of this half of the CTA (ids 1 and 2; 0 is __syncthreads)
+#define NTT_SYNC() asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x / NT) + 1), "n"(NT) : "memory")
 #else
 #define NTT_SYNC() __syncthreads()
 #endif
@@ -80,6 +92,15 @@ BBG_D fe sm_load(const uint32_t* data, int q)
     fe r;
 #pragma unroll
     for (int l = 0; l < 8; ++l) r.v[l] = data[l * PLANE + p];
+    return r;
+}
+// twiddle e of the image: planes 0..7 = w^e in PLAIN form, planes 8..15 = floor(w^e 2^256 / p)  (Fr::mul_const)
+BBG_D fe twq_load(const uint32_t* tw, int e)
+{
+    const int p = pad(e);
+    fe r;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) r.v[l] = tw[(8 + l) * TWP + p];
     return r;
 }
 BBG_D fe tw_load(const uint32_t* tw, int e)
@@ -148,9 +169,9 @@ template <int L, int B, int R> BBG_D void radix_step(fe (&x)[8], int base_low, c
             }
             else
             {
-                // the sub-transform twiddles are canonical (< p), so the difference may stay in (0, 4p)
+                // the difference may stay in (0, 4p): mul_const takes any multiplicand below 4p
                 const int e = (base_low | (jm << B)) << (L - 1 - s);
-                x[m | half] = NTT_MUL(NTT_SUB_LAZY(u, v), tw_load(tw, e));
+                x[m | half] = Fr::mul_const(NTT_SUB_LAZY(u, v), tw_load(tw, e), twq_load(tw, e));
             }
         }
     }
@@ -174,7 +195,7 @@ template <int L, bool COLS_LOW, int B, int R, bool FIRST, bool LAST>
 BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int tile, uint32_t* data, const uint32_t* tw)
 {
     typedef TileMap<L, COLS_LOW> TM;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x & (NT - 1);
     const int rest = p.log_n - L; // log2 of the other dimension
     if (FIRST)
     {
@@ -266,14 +287,15 @@ BBG_D void run_from(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int
     }
 }
 
-template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT, 2) ntt_pass_kernel(PassParams p)
+template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) ntt_pass_kernel(PassParams p)
 {
     BBG_DYN_SMEM(smem_raw);
-    uint32_t* data = (uint32_t*)smem_raw;
-    uint32_t* tw = data + 8 * PLANE;
-    for (int i = threadIdx.x; i < 8 * TWP; i += NT) tw[i] = p.sub_tw[i];
+    const int half = (int)threadIdx.x / NT; // which of the CTA's tiles this thread works on
+    uint32_t* data = (uint32_t*)smem_raw + half * 8 * PLANE;
+    uint32_t* tw = (uint32_t*)smem_raw + TPC * 8 * PLANE;
+    for (int i = threadIdx.x; i < 16 * TWP; i += NT * TPC) tw[i] = p.sub_tw[i];
     __syncthreads();
-    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x)
+    for (int work = blockIdx.x * TPC + half; work < p.total_work; work += gridDim.x * TPC)
     {
         // polynomial-minor order: the CTAs in flight work on the same few tiles of all polynomials of the batch, so the
         // inter-pass matrix tile (pass A; 128 MiB per 2^22 transform, more than L2 holds) is read from HBM once per batch
@@ -308,7 +330,7 @@ __global__ void __launch_bounds__(NT) ntt_small_kernel(SmallParams p)
     uint32_t* tw = data + 8 * PLANE;
     const int L = p.log_n, n = 1 << L, t = threadIdx.x;
     fe* poly = p.coeffs + (size_t)blockIdx.x * p.batch_stride;
-    for (int i = t; i < 8 * TWP; i += NT) tw[i] = p.sub_tw[i];
+    for (int i = t; i < 16 * TWP; i += NT) tw[i] = p.sub_tw[i];
     for (int i = t; i < n; i += NT)
     {
         fe x = load_fe(poly + i);
@@ -325,7 +347,8 @@ __global__ void __launch_bounds__(NT) ntt_small_kernel(SmallParams p)
             const int q0 = ((i >> s) << (s + 1)) | j;
             const fe u = sm_load(data, q0), v = sm_load(data, q0 | h);
             sm_store(data, q0, Fr::add(u, v));
-            const fe d = j != 0 ? Fr::mul(Fr::sub_lazy(u, v), tw_load(tw, j << (L - 1 - s))) : Fr::sub(u, v);
+            const int e = j << (L - 1 - s);
+            const fe d = j != 0 ? Fr::mul_const(Fr::sub_lazy(u, v), tw_load(tw, e), twq_load(tw, e)) : Fr::sub(u, v);
             sm_store(data, q0 | h, d);
         }
     }
@@ -350,15 +373,21 @@ __global__ void gen_powers_kernel(fe* out, fe base, fe scale, unsigned count)
     if (i >= count) return;
     store_fe(out + i, Fr::mul(Fr::pow_u64(base, i), scale));
 }
-// padded limb-plane image of root^e, e < half
+// padded limb-plane image of root^e, e < half: planes 0..7 the plain (non-Montgomery) value, planes 8..15 its quotient
+// floor(w 2^256 / p) - the two constants Fr::mul_const multiplies by
 __global__ void gen_subtw_image_kernel(uint32_t* img, fe root, unsigned half)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= half) return;
-    const fe w = Fr::reduce(Fr::pow_u64(root, e)); // canonical: the butterflies rely on w < p (Fr::sub_lazy)
+    const fe w = Fr::reduce(Fr::pow_u64(root, e)); // canonical Montgomery form
+    const fe plain = Fr::from_mont(w), quot = Fr::const_quotient(w);
     const int p = pad((int)e);
 #pragma unroll
-    for (int l = 0; l < 8; ++l) img[l * TWP + p] = w.v[l];
+    for (int l = 0; l < 8; ++l)
+    {
+        img[l * TWP + p] = plain.v[l];
+        img[(8 + l) * TWP + p] = quot.v[l];
+    }
 }
 // M[i1][j2] = lo[e & 2047] * hi[e >> 11] * rf[i1] * cf[j2],  e = i1 * j2 < n
 __global__ void gen_matrix_kernel(fe* M, const fe* lo, const fe* hi, const fe* rf, const fe* cf, int log_n, int log_cols)
@@ -530,8 +559,8 @@ int get_sub_tw(int L, bool inverse, cudaStream_t st, const uint32_t** out)
     if (it == g_tables.sub_tw.end())
     {
         uint32_t* img = nullptr;
-        BBG_CHECK(alloc_owned((void**)&img, (size_t)8 * TWP * 4));
-        BBG_CHECK(bbg_rt::dev_memset(img, 0, (size_t)8 * TWP * 4, st));
+        BBG_CHECK(alloc_owned((void**)&img, (size_t)16 * TWP * 4));
+        BBG_CHECK(bbg_rt::dev_memset(img, 0, (size_t)16 * TWP * 4, st));
         fe root = host_root_of_unity((unsigned)L);
         if (inverse) root = Fr::invert(root);
         const unsigned half = L >= 1 ? (1u << (L - 1)) : 1u;
@@ -675,11 +704,11 @@ template <int L, bool COLS_LOW> int launch_pass_L(const PassParams& p, cudaStrea
         BBG_CHECK(bbg_rt::set_smem_limit((const void*)ntt_pass_kernel<L, COLS_LOW>, SMEM_BYTES));
         configured = true;
     }
-    int grid = 2 * bbg_rt::num_sms();
-    if (grid > p.total_work) grid = p.total_work;
+    int grid = (2 / TPC) * bbg_rt::num_sms();
+    if (grid > (p.total_work + TPC - 1) / TPC) grid = (p.total_work + TPC - 1) / TPC;
     auto kernel = ntt_pass_kernel<L, COLS_LOW>; // (alias: the template's comma would split the macro argument)
     bbg_prof::Scope prof(COLS_LOW ? bbg_prof::NTT_PASS_A : bbg_prof::NTT_PASS_B, st);
-    BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT), SMEM_BYTES, st, p);
+    BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT * TPC), SMEM_BYTES, st, p);
     ++g_ntt_launches;
     return bbg_rt::last_error();
 }
@@ -905,11 +934,11 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
         }
         if (!g_tables.smem_configured)
         {
-            BBG_CHECK(bbg_rt::set_smem_limit((const void*)ntt_small_kernel, SMEM_BYTES));
+            BBG_CHECK(bbg_rt::set_smem_limit((const void*)ntt_small_kernel, SMEM_BYTES_SMALL));
             g_tables.smem_configured = true;
         }
         bbg_prof::Scope prof(bbg_prof::NTT_SMALL, st);
-        BBG_LAUNCH(ntt_small_kernel, dim3((unsigned)batch), dim3(NT), SMEM_BYTES, st, sp);
+        BBG_LAUNCH(ntt_small_kernel, dim3((unsigned)batch), dim3(NT), SMEM_BYTES_SMALL, st, sp);
         ++g_ntt_launches;
         return bbg_rt::last_error();
     }
