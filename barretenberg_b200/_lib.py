@@ -227,6 +227,21 @@ class Library:
         self.check(self.lib.bbg_msm_g1_partial_finish(ticket, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def msm_launch(self, scalars, table, n):
+        """bbg_msm_g1_launch: host buffers, MSM queued on the library's second stream; returns a ticket for msm_finish()."""
+        s = _as_u64(scalars, (4,))
+        t = table if (isinstance(table, np.ndarray) and table.dtype == np.uint64 and table.flags["C_CONTIGUOUS"]) else _as_u64(table, (8,))
+        if t.shape[0] < 2 * n:
+            raise ValueError("point table must hold 2n entries")
+        ticket = C.c_int(-1)
+        self.check(self.lib.bbg_msm_g1_launch(s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), n, C.byref(ticket)))
+        return ticket.value
+
+    def msm_finish(self, ticket):
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.lib.bbg_msm_g1_finish(ticket, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def fold_partials(self, partials):
         p = _as_u64(partials, (16,))
         out = np.zeros(12, dtype=np.uint64)

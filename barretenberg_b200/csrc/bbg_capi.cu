@@ -48,6 +48,7 @@ struct GrowBuf
 };
 GrowBuf g_stage_coeffs;  // NTT host path: polynomial staging
 GrowBuf g_stage_scalars; // MSM host path: scalar staging
+GrowBuf g_stage_scalars_async; // bbg_msm_g1_launch: scalar staging of the MSMs queued on the second stream
 GrowBuf g_stage_table;   // MSM host path: unregistered point tables
 
 struct SrsEntry
@@ -218,6 +219,7 @@ int bbg_shutdown(void)
     plonk::release_helpers();
     g_stage_coeffs.release();
     g_stage_scalars.release();
+    g_stage_scalars_async.release();
     g_stage_table.release();
     for (SrsEntry& s : g_srs) bbg_rt::dev_free(s.d_table);
     g_srs.clear();
@@ -504,6 +506,39 @@ int bbg_msm_g1_partial_finish(int ticket, uint64_t out_xyzz[16])
     BBG_CHECK(ensure_ready());
     if (out_xyzz == nullptr) return BBG_E_BAD_ARGUMENT;
     return msm_finish(ticket, out_xyzz);
+}
+
+int bbg_msm_g1_launch(const uint64_t* scalars, const uint64_t* points_table, size_t n, int* ticket)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (ticket == nullptr) return BBG_E_BAD_ARGUMENT;
+    *ticket = -1; // (n == 0: nothing to wait for, finish returns the point at infinity)
+    if (n == 0) return 0;
+    if (scalars == nullptr || points_table == nullptr) return BBG_E_BAD_ARGUMENT;
+    const void* d_table = nullptr;
+    BBG_CHECK(resolve_table(points_table, n, &d_table));
+    // own staging buffer, own stream: uploads and kernels of successive launches are ordered by that stream, and the
+    // calls made on the work stream in between (transforms with their own copies) run beside them
+    BBG_CHECK(g_stage_scalars_async.ensure(n * 32));
+    cudaStream_t st = g_stream;
+#ifndef BBG_EMULATE
+    st = g_msm_stream;
+#endif
+    BBG_CHECK(bbg_hostcopy::h2d(g_stage_scalars_async.p, scalars, n * 32, st));
+    const void* one[1] = { g_stage_scalars_async.p };
+    return msm_launch(1, one, 1, d_table, n, st, ticket);
+}
+
+int bbg_msm_g1_finish(int ticket, uint64_t out_xyz[12])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (out_xyz == nullptr) return BBG_E_BAD_ARGUMENT;
+    hostg1::hxyzz r = hostg1::infinity();
+    if (ticket != -1) BBG_CHECK(msm_finish(ticket, &r));
+    hostg1::to_normalized_jacobian(r, out_xyz);
+    return 0;
 }
 
 int bbg_msm_g1_dev(const void* d_scalars, const void* d_table, size_t n, uint64_t out_xyz[12])

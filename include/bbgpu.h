@@ -106,6 +106,14 @@ int bbg_g1_fold_partials(const uint64_t* partials_xyzz /* count x 16 */, size_t 
  * d_table must not be modified in between.  Up to 6 tickets may be pending. */
 int bbg_msm_g1_partial_dev_launch(const void* d_scalars, const void* d_table, size_t n, int* ticket);
 int bbg_msm_g1_partial_finish(int ticket, uint64_t out_xyzz[16]);
+/* bbg_msm_g1 in two steps with HOST buffers (what a caller of pippenger() with independent transforms to run in between
+ * would use: prover.cpp:65-124 commits to a wire while the next wires are still being transformed): launch copies the
+ * scalars to the device and queues the MSM on the library's second stream, then returns; the NTT / MSM calls made before
+ * finish run beside it (their PCIe copies hide the MSM, whose own traffic is 32 bytes per point).  finish waits, folds the
+ * windows on the host and writes the normalised Jacobian point like bbg_msm_g1.  scalars may be reused once launch
+ * returns when they are pageable, after finish when they are pinned; up to 6 tickets may be pending. */
+int bbg_msm_g1_launch(const uint64_t* scalars, const uint64_t* points_table, size_t n, int* ticket);
+int bbg_msm_g1_finish(int ticket, uint64_t out_xyz[12]);
 /* table[2i] = points[i], table[2i+1] = (beta x_i, -y_i): the layout of generate_pippenger_point_table
  * (scalar_multiplication.cpp:131-140) computed on the device; table may alias points */
 int bbg_generate_pippenger_point_table(const uint64_t* points_n, uint64_t* table_2n, size_t n);

@@ -406,6 +406,24 @@ def test_msm_launch_finish_tickets(lib):
         lib.dev_free(d)
 
 
+def test_msm_host_launch_finish(lib):
+    """bbg_msm_g1_launch / _finish (host buffers): two MSMs queued, host-buffer transforms run in between, results equal
+    to bbg_msm_g1; n = 0 gives infinity without a ticket; a ticket cannot be finished twice"""
+    n = 6000
+    table, _, _ = H.generator_multiples_table(43, n)
+    scs = [H.random_scalars_mont(70 + i, n) for i in range(2)]
+    tickets = [lib.msm_launch(s, table, n) for s in scs]
+    x = H.random_scalars_mont(11, 1 << 13)
+    assert (lib.ntt("coset_ifft", lib.ntt("coset_fft", x.copy())) == x).all()
+    for i in (1, 0):
+        got = lib.msm_finish(tickets[i])
+        assert (got == H.oracle_msm(scs[i], table)).all()
+        assert (got == lib.msm(scs[i], table, n)).all()
+    assert H.is_infinity(lib.msm_finish(lib.msm_launch(scs[0], table, 0)))
+    with pytest.raises(bb.BbgError):
+        lib.msm_finish(tickets[0])
+
+
 # ---- the reference's stand-alone polynomial helpers (polynomial_arithmetic.cpp:337-373, :478-591) ----------------------
 def _canonical(a):
     """lazily reduced (k, 4) limbs -> canonical limbs"""
