@@ -260,6 +260,73 @@ template <int J, int LIMB, int END, bool FIRST> BBG_D void mad_chain(uint32_t* a
     }
 }
 #endif
+
+// ---- rows with the first SKIP products known to be zero (Field::sqr: row i only has the words j >= i) ---------------
+// acc += sum_{j >= SKIP} x[2j] * y * 2^(64 j), carry out of bit 256 added to `top`
+template <int SKIP> BBG_HD void mad_row_carry_skip(uint32_t* acc, uint32_t& top, const uint32_t* x, uint32_t y)
+{
+    if constexpr (SKIP >= 4) return;
+#if defined(__CUDA_ARCH__)
+    mad_lo_cc(acc[2 * SKIP], x[2 * SKIP], y);
+    madc_hi_cc(acc[2 * SKIP + 1], x[2 * SKIP], y);
+    if constexpr (SKIP < 3) { madc_lo_cc(acc[2 * SKIP + 2], x[2 * SKIP + 2], y); madc_hi_cc(acc[2 * SKIP + 3], x[2 * SKIP + 2], y); }
+    if constexpr (SKIP < 2) { madc_lo_cc(acc[2 * SKIP + 4], x[2 * SKIP + 4], y); madc_hi_cc(acc[2 * SKIP + 5], x[2 * SKIP + 4], y); }
+    if constexpr (SKIP < 1) { madc_lo_cc(acc[2 * SKIP + 6], x[2 * SKIP + 6], y); madc_hi_cc(acc[2 * SKIP + 7], x[2 * SKIP + 6], y); }
+    addc(top, top, 0u);
+#else
+    uint64_t carry = 0;
+    for (int j = 2 * SKIP; j < 8; j += 2)
+    {
+        uint64_t prod = (uint64_t)x[j] * y;
+        uint64_t lo = (uint64_t)acc[j] + (uint32_t)prod + carry;
+        acc[j] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[j + 1] + (uint32_t)(prod >> 32) + (lo >> 32);
+        acc[j + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+    top += (uint32_t)carry;
+#endif
+}
+// shift_mad_row with the first SKIP products zero: those columns are plain shifted adds
+template <int SKIP> BBG_HD void shift_mad_row_skip(uint32_t* sh, uint32_t& e0, const uint32_t* x, uint32_t y)
+{
+#if defined(__CUDA_ARCH__)
+    add_cc(e0, e0, sh[1]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const uint32_t lo_in = (2 * j + 2 < 8) ? sh[2 * j + 2] : 0u;
+        const uint32_t hi_in = (2 * j + 3 < 8) ? sh[2 * j + 3] : 0u;
+        if (j < SKIP)
+        {
+            addc_cc(sh[2 * j], lo_in, 0u);
+            addc_cc(sh[2 * j + 1], hi_in, 0u);
+        }
+        else
+        {
+            sh[2 * j] = lo_in;
+            madc_lo_cc(sh[2 * j], x[2 * j], y);
+            sh[2 * j + 1] = hi_in;
+            madc_hi_cc(sh[2 * j + 1], x[2 * j], y);
+        }
+    }
+#else
+    uint64_t t = (uint64_t)e0 + sh[1];
+    e0 = (uint32_t)t;
+    uint64_t carry = t >> 32;
+    for (int j = 0; j < 8; j += 2)
+    {
+        uint64_t prod = (j >= 2 * SKIP) ? (uint64_t)x[j] * y : 0;
+        uint32_t in_lo = (j + 2 < 8) ? sh[j + 2] : 0u;
+        uint32_t in_hi = (j + 3 < 8) ? sh[j + 3] : 0u;
+        uint64_t lo = (uint64_t)in_lo + (uint32_t)prod + carry;
+        uint64_t hi = (uint64_t)in_hi + (uint32_t)(prod >> 32) + (lo >> 32);
+        sh[j] = (uint32_t)lo;
+        sh[j + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+#endif
+}
 } // namespace cc
 
 // ---------------------------------------------------------------------------------------------
@@ -340,7 +407,76 @@ template <typename FP> struct Field
         cc::add8(r.v, A, hi);
         return r;
     }
-    static BBG_HD fe sqr(const fe& a) { return mul(a, a); }
+    // Montgomery square, result in [0, 2p) for a in [0, 2p): the same interleaved reduction as mul, but row i multiplies
+    // a_i by  a_i B^i + 2 (a div B^(i+1)) B^(i+1)  (B = 2^32), i.e. by the words  a_i, a_(i+1) << 1, dd_(i+2) .. dd_7  with
+    // dd_j = (a_j << 1) | (a_(j-1) >> 31) the words of 2a (2a < 2^256 since a < 2p < 2^255): every product a_i a_j is issued
+    // once instead of twice - 36 + 64 wide products instead of 64 + 64; the skipped columns of the shifting accumulator
+    // become plain carry adds.  Same integer (a^2 + M p) / 2^256 as mul(a, a).
+    static BBG_HD fe sqr(const fe& a)
+    {
+        uint32_t A[8], B[8], X[9];
+        uint32_t pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = FP::P(i);
+        const uint32_t* pe = pl;
+        const uint32_t* po = pl + 1;
+        uint32_t dd[8];
+        dd[0] = 0;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) dd[j] = (a.v[j] << 1) | (a.v[j - 1] >> 31);
+        X[8] = 0;
+        // word 0: X = a_0, a_1 << 1, dd_2 .. dd_7
+        X[0] = a.v[0];
+        X[1] = a.v[1] << 1;
+#pragma unroll
+        for (int j = 2; j < 8; ++j) X[j] = dd[j];
+        cc::mul_row(A, X, a.v[0]);
+        cc::mul_row(B, X + 1, a.v[0]);
+        {
+            uint32_t m = A[0] * FP::NINV;
+            cc::mad_row(B, po, m);
+            cc::mad_row_carry(A, B[7], pe, m);
+        }
+        sqr_words<1>(A, B, X, a.v, pe, po);
+        fe r;
+        uint32_t hi[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) hi[k] = B[k + 1];
+        hi[7] = 0;
+        cc::add8(r.v, A, hi);
+        return r;
+    }
+    // words I (odd) and I + 1 (even) of the square; X[j] still holds dd_j for j >= I + 1 (a row only rewrites X[i], X[i+1])
+    template <int I> static BBG_HD void sqr_words(uint32_t* A, uint32_t* B, uint32_t* X, const uint32_t* a, const uint32_t* pe, const uint32_t* po)
+    {
+        if constexpr (I < 8)
+        {
+            {
+                // odd word I: even accumulator = B, odd accumulator = A (shifted down two words on the way)
+                X[I] = a[I];
+                if constexpr (I + 1 < 8) X[I + 1] = a[I + 1] << 1;
+                const uint32_t y = a[I];
+                cc::shift_mad_row_skip<(I - 1) / 2>(A, B[0], X + 1, y);
+                cc::mad_row_carry_skip<(I + 1) / 2>(B, A[7], X, y);
+                uint32_t m = B[0] * FP::NINV;
+                cc::mad_row(A, po, m);
+                cc::mad_row_carry(B, A[7], pe, m);
+            }
+            if constexpr (I + 1 < 8)
+            {
+                constexpr int E = I + 1;
+                X[E] = a[E];
+                if constexpr (E + 1 < 8) X[E + 1] = a[E + 1] << 1;
+                const uint32_t y = a[E];
+                cc::shift_mad_row_skip<E / 2>(B, A[0], X + 1, y);
+                cc::mad_row_carry_skip<E / 2>(A, B[7], X, y);
+                uint32_t m = A[0] * FP::NINV;
+                cc::mad_row(B, po, m);
+                cc::mad_row_carry(A, B[7], pe, m);
+            }
+            sqr_words<I + 2>(A, B, X, a, pe, po);
+        }
+    }
 
     // Product with a constant known in advance (NTT twiddles): r = a * w mod p as a residue in [0, 2p), for ANY a < 4p
     // and w < p given in PLAIN form together with wq = floor(w * 2^256 / p).  When a is a Montgomery-form value, so is

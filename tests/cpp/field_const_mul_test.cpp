@@ -45,9 +45,32 @@ template <typename F> static int run(const char* name, int count)
     printf("%s: %d cases, %d bad\n", name, count, bad);
     return bad;
 }
+// sqr(a) must be the same integer as mul(a, a) (not just the same residue) for every a < 2p
+template <typename F> static int run_sqr(const char* name, int count)
+{
+    int bad = 0;
+    fe p2 = F::modulus(); { fe n; cc::add8(n.v, p2.v, p2.v); p2 = n; }
+    for (int it = 0; it < count; ++it)
+    {
+        fe a = rnd_below_p<F>();
+        if (it & 1) { fe n; fe pm = F::modulus(); cc::add8(n.v, a.v, pm.v); a = n; } // [p, 2p)
+        if (it == 0) a = F::zero();
+        if (it == 1) { a = p2; a.v[0] -= 1; }                         // 2p - 1
+        if (it == 2) { a = F::modulus(); }
+        if (it == 3) { for (int l = 0; l < 8; ++l) a.v[l] = 0xffffffffu; a.v[7] = F::params::P2(7) - 1; } // all-ones words below 2p
+        if (it == 4) { for (int l = 0; l < 8; ++l) a.v[l] = 0x80000000u; a.v[7] = 0x40000000u; }        // every shifted-out bit set
+        if (it == 5) { for (int l = 0; l < 8; ++l) a.v[l] = 0xffffffffu; a.v[7] = 0x3fffffffu; }
+        if (it == 6) { a = F::zero(); a.v[0] = 0xffffffffu; }
+        if (it == 7) { a = F::zero(); a.v[7] = F::params::P2(7) - 1; }
+        const fe want = F::mul(a, a), got = F::sqr(a);
+        if (!F::eq_raw(want, got)) { ++bad; if (bad < 5) printf("%s sqr: mismatch at %d\n", name, it); }
+    }
+    printf("%s sqr: %d cases, %d bad\n", name, count, bad);
+    return bad;
+}
 int main(int argc, char** argv)
 {
     const int count = argc > 1 ? atoi(argv[1]) : 200000;
-    int bad = run<Fr>("Fr", count) + run<Fq>("Fq", count);
+    int bad = run<Fr>("Fr", count) + run<Fq>("Fq", count) + run_sqr<Fr>("Fr", count) + run_sqr<Fq>("Fq", count);
     return bad ? 1 : 0;
 }

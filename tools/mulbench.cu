@@ -1,5 +1,6 @@
 // Development aid: device throughput of the Montgomery product (Fr::mul) against the precomputed-quotient product
-// (Fr::mul_const), alone and inside a DIF butterfly, plus a device-vs-device agreement check of the two.
+// (Fr::mul_const), alone and inside a DIF butterfly, and of the dedicated square (Fr::sqr) against mul(x, x), plus a
+// device-vs-device agreement check of each pair.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/mulbench tools/mulbench.cu && build/mulbench
 #include <cstdio>
 #include <cstdint>
@@ -23,6 +24,8 @@ template <int MODE> __global__ void __launch_bounds__(256, 2) bench_kernel(fe* o
             if (MODE == 1) x[c] = Fr::mul_const(x[c], wp, wq);
             if (MODE == 2) { const fe u = x[c], v = y[c]; x[c] = Fr::add(u, v); y[c] = Fr::mul(Fr::sub_lazy(u, v), wm); }
             if (MODE == 3) { const fe u = x[c], v = y[c]; x[c] = Fr::add(u, v); y[c] = Fr::mul_const(Fr::sub_lazy(u, v), wp, wq); }
+            if (MODE == 4) x[c] = Fr::mul(x[c], x[c]);
+            if (MODE == 5) x[c] = Fr::sqr(x[c]);
         }
     }
     fe acc = x[0];
@@ -34,10 +37,10 @@ template <int MODE> __global__ void __launch_bounds__(256, 2) bench_kernel(fe* o
 int main()
 {
     const int blocks = 148 * 8, threads = 256, n = blocks * threads, iters = 512;
-    fe *d_in, *d_tw, *d_out[4];
+    fe *d_in, *d_tw, *d_out[6];
     cudaMalloc(&d_in, 4096 * sizeof(fe));
     cudaMalloc(&d_tw, 3 * sizeof(fe));
-    for (int m = 0; m < 4; ++m) cudaMalloc(&d_out[m], n * sizeof(fe));
+    for (int m = 0; m < 6; ++m) cudaMalloc(&d_out[m], n * sizeof(fe));
     fe* h_in = new fe[4096];
     uint64_t s = 12345;
     for (int i = 0; i < 4096; ++i)
@@ -55,16 +58,18 @@ int main()
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    float ms[4];
+    float ms[6];
     for (int rep = 0; rep < 3; ++rep)
     {
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 6; ++m)
         {
             cudaEventRecord(e0);
             if (m == 0) bench_kernel<0><<<blocks, threads>>>(d_out[0], d_in, d_tw, iters);
             if (m == 1) bench_kernel<1><<<blocks, threads>>>(d_out[1], d_in, d_tw, iters);
             if (m == 2) bench_kernel<2><<<blocks, threads>>>(d_out[2], d_in, d_tw, iters);
             if (m == 3) bench_kernel<3><<<blocks, threads>>>(d_out[3], d_in, d_tw, iters);
+            if (m == 4) bench_kernel<4><<<blocks, threads>>>(d_out[4], d_in, d_tw, iters);
+            if (m == 5) bench_kernel<5><<<blocks, threads>>>(d_out[5], d_in, d_tw, iters);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             cudaEventElapsedTime(&ms[m], e0, e1);
@@ -72,17 +77,18 @@ int main()
     }
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(err)); return 2; }
-    fe* h[4];
-    for (int m = 0; m < 4; ++m) { h[m] = new fe[n]; cudaMemcpy(h[m], d_out[m], n * sizeof(fe), cudaMemcpyDeviceToHost); }
-    size_t bad01 = 0, bad23 = 0;
+    fe* h[6];
+    for (int m = 0; m < 6; ++m) { h[m] = new fe[n]; cudaMemcpy(h[m], d_out[m], n * sizeof(fe), cudaMemcpyDeviceToHost); }
+    size_t bad01 = 0, bad23 = 0, bad45 = 0;
     for (int i = 0; i < n; ++i)
     {
         if (!Fr::eq_raw(h[0][i], h[1][i])) ++bad01;
         if (!Fr::eq_raw(h[2][i], h[3][i])) ++bad23;
+        if (!Fr::eq_raw(h[4][i], h[5][i])) ++bad45;
     }
     const double muls = (double)n * CHAINS * iters;
-    const char* names[4] = { "mul (Montgomery)", "mul_const", "butterfly + mul", "butterfly + mul_const" };
-    for (int m = 0; m < 4; ++m) printf("{\"mode\": \"%s\", \"ms\": %.4f, \"products_per_s\": %.4e}\n", names[m], ms[m], muls / (ms[m] * 1e-3));
-    printf("{\"mismatch_mul\": %zu, \"mismatch_butterfly\": %zu, \"of\": %d}\n", bad01, bad23, n);
-    return (bad01 || bad23) ? 1 : 0;
+    const char* names[6] = { "mul (Montgomery)", "mul_const", "butterfly + mul", "butterfly + mul_const", "mul(x, x)", "sqr(x)" };
+    for (int m = 0; m < 6; ++m) printf("{\"mode\": \"%s\", \"ms\": %.4f, \"products_per_s\": %.4e}\n", names[m], ms[m], muls / (ms[m] * 1e-3));
+    printf("{\"mismatch_mul\": %zu, \"mismatch_butterfly\": %zu, \"mismatch_sqr\": %zu, \"of\": %d}\n", bad01, bad23, bad45, n);
+    return (bad01 || bad23 || bad45) ? 1 : 0;
 }
