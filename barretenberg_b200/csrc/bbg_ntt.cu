@@ -66,6 +66,9 @@ __device__ __noinline__ fe fr_mul_shared(const fe a, const fe b) { return Fr::mu
 #ifndef BBG_NTT_ABLATE
 #define BBG_NTT_ABLATE 0
 #endif
+#ifndef BBG_NTT_PREFETCH
+#define BBG_NTT_PREFETCH 1
+#endif
 #if BBG_NTT_ABLATE == 1 || BBG_NTT_ABLATE == 2
 #define NTT_SYNC() ((void)0)
 #elif defined(__CUDA_ARCH__)
@@ -79,6 +82,16 @@ BBG_HD int pad(int q) { return q + (q >> 5); }          // twiddle planes: power
 // access pattern of every radix step conflict-free (checked exhaustively for all sub-transform lengths and both
 // tile layouts; the padded layout q + q/32 left 2- and 4-way conflicts in the low-bit steps, ncu r01).
 BBG_HD int dswz(int q) { return q ^ ((q >> 3) & 31); }
+
+// hint: bring the line holding p into L2 (no register, no scoreboard entry)
+BBG_D void prefetch_l2(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 BBG_D void sm_store(uint32_t* data, int q, const fe& x)
 {
@@ -191,8 +204,9 @@ template <int L, bool COLS_LOW> struct TileMap
     static BBG_D int c_of(int q) { return COLS_LOW ? (q & ((1 << CLOG) - 1)) : (q >> L); }
 };
 
+// (nsrc, ntile): the tile this half of the CTA works on next, or nsrc == nullptr - prefetched into L2 by the first step
 template <int L, bool COLS_LOW, int B, int R, bool FIRST, bool LAST>
-BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int tile, uint32_t* data, const uint32_t* tw)
+BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int tile, uint32_t* data, const uint32_t* tw, const fe* nsrc, int ntile)
 {
     typedef TileMap<L, COLS_LOW> TM;
     const int t = threadIdx.x & (NT - 1);
@@ -212,6 +226,18 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             x[m].v[0] = (uint32_t)g;
 #else
             x[m] = load_fe(src + g);
+#endif
+#if BBG_NTT_PREFETCH
+            // the matrix entries of this tile are the same index set as its inputs: start them towards L2 now, ten stages
+            // before they are multiplied in; and the inputs of the next tile
+            if (COLS_LOW && p.mat != nullptr) prefetch_l2(p.mat + g);
+            if (BBG_NTT_PREFETCH > 1 && nsrc != nullptr)
+            {
+                size_t gn;
+                if (COLS_LOW) gn = ((size_t)k << rest) + ((size_t)ntile << TM::CLOG) + c;
+                else gn = ((((size_t)ntile << TM::CLOG) + c) << L) + k;
+                prefetch_l2(nsrc + gn);
+            }
 #endif
             if (COLS_LOW && p.vec != nullptr) x[m] = NTT_MUL(x[m], load_fe(p.vec + k));
         }
@@ -273,17 +299,17 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
 }
 
 template <int L, bool COLS_LOW, int B, bool FIRST>
-BBG_D void run_from(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int tile, uint32_t* data, const uint32_t* tw)
+BBG_D void run_from(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int tile, uint32_t* data, const uint32_t* tw, const fe* nsrc, int ntile)
 {
     if constexpr (B == 0)
     {
-        do_step<L, COLS_LOW, 0, 3, FIRST, true>(x, p, src, dst, tile, data, tw);
+        do_step<L, COLS_LOW, 0, 3, FIRST, true>(x, p, src, dst, tile, data, tw, nsrc, ntile);
     }
     else
     {
-        do_step<L, COLS_LOW, B, 3, FIRST, false>(x, p, src, dst, tile, data, tw);
-        if constexpr (B >= 3) run_from<L, COLS_LOW, B - 3, false>(x, p, src, dst, tile, data, tw);
-        else do_step<L, COLS_LOW, 0, B, false, true>(x, p, src, dst, tile, data, tw);
+        do_step<L, COLS_LOW, B, 3, FIRST, false>(x, p, src, dst, tile, data, tw, nsrc, ntile);
+        if constexpr (B >= 3) run_from<L, COLS_LOW, B - 3, false>(x, p, src, dst, tile, data, tw, nsrc, ntile);
+        else do_step<L, COLS_LOW, 0, B, false, true>(x, p, src, dst, tile, data, tw, nsrc, ntile);
     }
 }
 
@@ -302,8 +328,11 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
         const int batch = p.total_work / p.num_tiles;
         const int tile = work / batch;
         const size_t b = (size_t)(work % batch);
+        const int nwork = work + (int)gridDim.x * TPC;
+        const fe* nsrc = nwork < p.total_work ? p.src + (size_t)(nwork % batch) * p.batch_stride : nullptr;
         fe x[8];
-        run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.scatter_shift ? p.dst + b : p.dst + b * p.batch_stride, tile, data, tw);
+        run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.scatter_shift ? p.dst + b : p.dst + b * p.batch_stride, tile, data, tw, nsrc,
+                                           nwork / batch);
         NTT_SYNC(); // the last step's shared-memory reads finish before the next tile overwrites
     }
 }
