@@ -16,10 +16,13 @@
 //               to natural order X[i1 + N1 i2], canonical reduction fused into the store.
 //     A tile is 2048 elements (64 KiB as eight 32-bit limb planes, XOR-swizzled against bank conflicts)
 //     processed by 256 threads holding 8 elements each: radix-8 butterflies in registers, one shared
-//     memory exchange per 3 stages.  Sub-transform twiddles live in shared memory (33 KiB image);
-//     2 CTAs/SM (2 x 99 KiB smem, <=128 regs).  Work per element: (log2 n)/2 products + 1 for the
-//     inter-pass twiddle (+1 per fused coset / constant scaling), i.e. IMAD-bound, ~2 x 64 B of HBM
-//     traffic per element per pass.
+//     memory exchange per 3 stages.  Sub-transform twiddles live in shared memory as (plain value,
+//     quotient) pairs for Fr::mul_const (66 KiB image: 19% fewer multiply-pipe slots per twiddle product
+//     than a Montgomery product); one 512-thread CTA per SM whose two halves share the image and each
+//     work on their own tile with their own named barrier (194 KiB smem, <=128 regs).  Work per element:
+//     (log2 n)/2 products + 1 for the inter-pass twiddle (+1 per fused coset / constant scaling), i.e.
+//     IMAD-bound, ~2 x 64 B of HBM traffic per element per pass.  Pass A starts its
+//     tile's inter-pass matrix entries towards L2 when it loads the tile.
 //   n >= 2^23 (up to the field's 2^28 two-adicity): one more outer split n = N0 * M, M <= 2^22: an outer pass A over
 //       columns of length N0 (same kernel, matrix w_n^(i0 j)), then the two passes above on the N0 contiguous blocks of
 //       M elements, whose last pass scatters block i0's output u to natural position i0 + N0 u.  THREE HBM passes;
