@@ -131,7 +131,8 @@ BBG_HD uint32_t window_bits(const uint32_t k[4], int pos, int c)
 }
 
 // ---- 1. digits -------------------------------------------------------------------------------------
-__global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uint32_t NB, uint32_t* digits, uint32_t* counts)
+// (the counting atomic returns the entry's rank inside its bucket: the scatter then needs no atomics of its own)
+__global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uint32_t NB, uint32_t* digits, uint32_t* ranks, uint32_t* counts)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -142,7 +143,7 @@ __global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uin
     uint32_t carry[2] = { 0, 0 };
     for (int w = 0; w < W; ++w)
     {
-        uint32_t packed[2];
+        uint32_t packed[2], rank[2] = { 0, 0 };
 #pragma unroll
         for (int h = 0; h < 2; ++h)
         {
@@ -161,7 +162,7 @@ __global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uin
                 // same assumption, wnaf.hpp:11); clamp defensively so no bucket index is ever out of range
                 if (d > NB) d = NB;
                 packed[h] = (d - 1) | neg;
-                atomicAdd(&counts[(size_t)w * NB + (d - 1)], 1u);
+                rank[h] = atomicAdd(&counts[(size_t)w * NB + (d - 1)], 1u);
             }
             else
             {
@@ -172,6 +173,10 @@ __global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uin
         pair.x = packed[0];
         pair.y = packed[1];
         *(uint2*)(digits + (size_t)w * num_points + 2 * i) = pair;
+        uint2 rpair;
+        rpair.x = rank[0];
+        rpair.y = rank[1];
+        *(uint2*)(ranks + (size_t)w * num_points + 2 * i) = rpair;
     }
 }
 
@@ -255,8 +260,8 @@ __global__ void scan_apply_kernel(const uint32_t* in, uint32_t count, const uint
 }
 
 // ---- 3. scatter ------------------------------------------------------------------------------------
-__global__ void msm_scatter_kernel(const uint32_t* digits, size_t num_points, int W, uint32_t NB, const uint32_t* offsets,
-                                   uint32_t* fill, uint32_t* sorted)
+__global__ void msm_scatter_kernel(const uint32_t* digits, const uint32_t* ranks, size_t num_points, int W, uint32_t NB, const uint32_t* offsets,
+                                   uint32_t* sorted)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= num_points * (size_t)W) return;
@@ -265,7 +270,7 @@ __global__ void msm_scatter_kernel(const uint32_t* digits, size_t num_points, in
     const size_t w = e / num_points;
     const uint32_t j = (uint32_t)(e - w * num_points);
     const size_t b = w * NB + (d & 0x7fffffffu);
-    const uint32_t pos = offsets[b] + atomicAdd(&fill[b], 1u);
+    const uint32_t pos = offsets[b] + ranks[e];
     sorted[pos] = j | (d & 0x80000000u);
 }
 
@@ -734,10 +739,10 @@ int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const 
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o_digits = carve(pl.max_entries * 4);
+    const size_t o_ranks = carve(pl.max_entries * 4);
     const size_t o_sorted = carve(pl.max_entries * 4 + 16);
     const size_t o_counts = carve((size_t)pl.total_buckets * 4);
-    const size_t o_fill = carve((size_t)pl.total_buckets * 4);
-    const size_t o_work_count = carve(256); // directly after fill: zeroed by the same memset
+    const size_t o_work_count = carve(256); // directly after counts: zeroed by the same memset
     const size_t o_offsets = carve(((size_t)pl.total_buckets + 1) * 4);
     const uint32_t scan_blocks = (pl.total_buckets + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
     const size_t o_spine = carve(((size_t)scan_blocks + 1) * 4);
@@ -753,9 +758,9 @@ int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const 
     BBG_CHECK(g_ws.ensure(off));
     char* ws = (char*)g_ws.p;
     uint32_t* digits = (uint32_t*)(ws + o_digits);
+    uint32_t* ranks = (uint32_t*)(ws + o_ranks);
     uint32_t* sorted = (uint32_t*)(ws + o_sorted);
     uint32_t* counts = (uint32_t*)(ws + o_counts);
-    uint32_t* fill = (uint32_t*)(ws + o_fill);
     uint32_t* offsets = (uint32_t*)(ws + o_offsets);
     uint32_t* spine = (uint32_t*)(ws + o_spine);
     fe* buckets = (fe*)(ws + o_buckets);
@@ -767,13 +772,13 @@ int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const 
     fe* V = (fe*)(ws + o_V);
     fe* red = (fe*)(ws + o_red);
 
-    // counts, fill and the fix-up work counter are adjacent: one memset
+    // counts and the fix-up work counter are adjacent: one memset
     BBG_CHECK(bbg_rt::dev_memset(counts, 0, (o_work_count - o_counts) + 256, st));
     {
         bbg_prof::Scope prof(bbg_prof::MSM_DIGITS, st);
         for (size_t b = 0; b < batch; ++b)
             BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars[b], n, pl.c, single.W, pl.NB,
-                              digits + b * single.max_entries, counts + b * single.total_buckets);
+                              digits + b * single.max_entries, ranks + b * single.max_entries, counts + b * single.total_buckets);
     }
     bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::MSM_SCAN, st);
     BBG_LAUNCH(scan_block_sums_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, spine);
@@ -782,8 +787,8 @@ int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const 
     delete prof_scan;
     {
         bbg_prof::Scope prof(bbg_prof::MSM_SCATTER, st);
-        BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, pl.num_points, pl.W,
-                          pl.NB, (const uint32_t*)offsets, fill, sorted);
+        BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, (const uint32_t*)ranks,
+                          pl.num_points, pl.W, pl.NB, (const uint32_t*)offsets, sorted);
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_ACCUMULATE, st);
