@@ -32,7 +32,9 @@ class Library:
     OPS = {"fft": 0, "ifft": 1, "coset_fft": 2, "coset_ifft": 3, "fft_with_constant": 4,
            "ifft_with_constant": 5, "coset_fft_with_constant": 6}
 
-    def __init__(self, path=None, device=0):
+    def __init__(self, path=None, device=0, devices=None):
+        """device: the CUDA device of a single-GPU instance.  devices: a list — devices[0] primary, the rest take point
+        ranges of large MSMs over registered tables (bbg_init_multi)."""
         path = path or library_path()
         if not os.path.exists(path):
             raise BbgError(-1, "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -73,7 +75,50 @@ class Library:
         L.bbg_srs_from_transcript.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.bbg_profile_name.restype = C.c_char_p
         L.bbg_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
-        self.check(L.bbg_init(device))
+        L.bbg_msm_g1_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.bbg_msm_g1_finish.argtypes = [C.c_int, C.c_void_p]
+        L.bbg_init_multi.argtypes = [C.POINTER(C.c_int), C.c_int]
+        L.bbg_host_buffer_forget.argtypes = [C.c_void_p]
+        L.bbg_field_selftest.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.bbg_g1_selftest.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        if devices is not None and len(devices) > 1:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.check(L.bbg_init_multi(arr, len(devices)))
+        else:
+            self.check(L.bbg_init(device if devices is None else int(devices[0])))
+
+    FIELD_OPS = {"mul_coarse": 0, "sqr_coarse": 1, "mul_const": 2, "add_coarse": 3, "sub_coarse": 4, "reduce_once": 5, "neg": 6,
+                 "to_mont": 7, "from_mont": 8, "invert": 9, "sub_lazy": 10, "mul": 11, "mul_const_raw": 12}
+    G1_OPS = {"mixed_add": 0, "add_doubled": 1, "dbl_dbl": 2, "accumulate": 3, "add": 4, "endo_entry": 5, "dbl_affine": 6}
+
+    def device_count(self):
+        return int(self.lib.bbg_device_count())
+
+    def set_host_register_cache(self, on=True):
+        self.check(self.lib.bbg_set_host_register_cache(1 if on else 0))
+
+    def host_buffer_forget(self, array_or_ptr):
+        p = array_or_ptr.ctypes.data if isinstance(array_or_ptr, np.ndarray) else int(array_or_ptr)
+        self.check(self.lib.bbg_host_buffer_forget(C.c_void_p(p)))
+
+    def field_selftest(self, field, op, a, b=None):
+        """Device field primitive `op` (FIELD_OPS) element-wise on (count, 4) uint64 arrays; field 0 = Fq, 1 = Fr."""
+        a = _as_u64(a, (4,))
+        bp = None
+        if b is not None:
+            b = _as_u64(b, (4,))
+            assert b.shape == a.shape
+            bp = b.ctypes.data_as(C.c_void_p)
+        out = np.zeros_like(a)
+        self.check(self.lib.bbg_field_selftest(field, self.FIELD_OPS[op], a.ctypes.data_as(C.c_void_p), bp, out.ctypes.data_as(C.c_void_p), a.shape[0]))
+        return out
+
+    def g1_selftest(self, op, p, q):
+        p, q = _as_u64(p, (8,)), _as_u64(q, (8,))
+        assert p.shape == q.shape
+        out = np.zeros_like(p)
+        self.check(self.lib.bbg_g1_selftest(self.G1_OPS[op], p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), p.shape[0]))
+        return out
 
     # ------------------------------------------------------------------ plumbing
     def check(self, code):

@@ -13,6 +13,9 @@
 namespace bbg
 {
 int microbench_launch(int mode, int iters, uint32_t* d_out, int blocks, double* ops, cudaStream_t st);
+int field_selftest_device(int field, int op, const void* d_a, const void* d_b, void* d_out, size_t count, cudaStream_t st);
+int g1_selftest_device(int op, const void* d_p, const void* d_q, void* d_out, size_t count, cudaStream_t st);
+size_t selftest_launch_count();
 }
 
 namespace
@@ -48,8 +51,14 @@ struct GrowBuf
 };
 GrowBuf g_stage_coeffs;  // NTT host path: polynomial staging
 GrowBuf g_stage_scalars; // MSM host path: scalar staging
-GrowBuf g_stage_scalars_async; // bbg_msm_g1_launch: scalar staging of the MSMs queued on the second stream
 GrowBuf g_stage_table;   // MSM host path: unregistered point tables
+// bbg_msm_g1_launch: each MSM queued on the second stream owns its scalar staging until its ticket is finished (in a
+// multi-GPU instance the other devices pull their ranges out of it on their own streams)
+struct AsyncSlot
+{
+    GrowBuf scalars;
+    int ticket = -1;
+} g_async_slots[6];
 
 struct SrsEntry
 {
@@ -58,7 +67,9 @@ struct SrsEntry
     void* d_table;
     uint64_t fingerprint; // of sampled host entries, re-checked on every cache hit
     bool automatic;       // created by the auto cache (may be evicted)
+    int pins;             // resident provers holding d_table (bbg_plonk_set_srs): never evicted while > 0
 };
+std::vector<std::pair<const void*, const uint64_t*>> g_prover_srs; // prover -> host_base of the entry it pins
 std::vector<SrsEntry> g_srs;
 bool g_auto_srs = false;
 constexpr size_t AUTO_SRS_MIN_POINTS = 1024; // below this an upload per call is cheaper than bookkeeping
@@ -89,6 +100,7 @@ cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 cudaStream_t g_copy_in = nullptr, g_copy_out = nullptr;
 cudaStream_t g_msm_stream = nullptr; // bbg_msm_g1_partial_dev_launch: an MSM running beside the work stream
 cudaEvent_t g_msm_fence = nullptr;
+bbg_hostcopy::Ring g_msm_ring; // pageable scalars of bbg_msm_g1_launch: their chunks wait behind MSM kernels, not behind the work stream
 std::vector<cudaEvent_t> g_pipe_events;
 #endif
 
@@ -106,8 +118,54 @@ int ensure_ready()
 #endif
 }
 
-// device pointer for a host point-table pointer: registered SRS (sub-range allowed) or a fresh upload
-int resolve_table(const uint64_t* points, size_t n, const void** d_table)
+// nothing queued by this library is still running on any device (before device memory is handed back)
+void quiesce_all()
+{
+    bbg_rt::sync(g_stream);
+#ifndef BBG_EMULATE
+    if (g_msm_stream) cudaStreamSynchronize(g_msm_stream);
+#endif
+    msm_multi_quiesce();
+}
+
+void srs_drop(size_t i)
+{
+    quiesce_all();
+    msm_multi_drop_replica(g_srs[i].d_table);
+    bbg_rt::dev_free(g_srs[i].d_table);
+    for (size_t k = 0; k < g_prover_srs.size();)
+    {
+        if (g_prover_srs[k].second == g_srs[i].host_base) g_prover_srs.erase(g_prover_srs.begin() + (long)k);
+        else ++k;
+    }
+    g_srs.erase(g_srs.begin() + (long)i);
+}
+
+// d_table: filled (or being filled on the work stream) by the caller; ownership moves to the cache
+int srs_add(const uint64_t* host_base, size_t n, void* d_table, bool automatic)
+{
+    SrsEntry s;
+    s.host_base = host_base;
+    s.n = n;
+    s.d_table = d_table;
+    s.automatic = automatic;
+    s.pins = 0;
+    s.fingerprint = table_fingerprint(host_base, n);
+    const int e = msm_multi_replicate(d_table, n * 128, g_stream); // no-op with one device
+    if (e != 0)
+    {
+        bbg_rt::sync(g_stream);
+        bbg_rt::dev_free(d_table);
+        return e;
+    }
+    g_srs.push_back(s);
+    return 0;
+}
+
+// device pointer for a host point-table pointer: registered SRS (sub-range allowed) or a fresh upload.
+// keep: the caller will use the pointer beyond this call (a launched MSM, a resident prover), so an unknown table is
+// cached whatever its size and whether or not the auto cache is on — never the shared staging buffer.
+int resolve_table(const uint64_t* points, size_t n, const void** d_table, bool keep = false)
 {
     for (size_t i = 0; i < g_srs.size(); ++i)
     {
@@ -117,16 +175,14 @@ int resolve_table(const uint64_t* points, size_t n, const void** d_table)
             if (table_fingerprint(s.host_base, s.n) != s.fingerprint)
             {
                 // the host buffer changed under a cached address: drop the stale copy and fall through
-                bbg_rt::sync(g_stream);
-                bbg_rt::dev_free(s.d_table);
-                g_srs.erase(g_srs.begin() + (long)i);
+                srs_drop(i);
                 break;
             }
             *d_table = (const char*)s.d_table + ((const char*)points - (const char*)s.host_base);
             return 0;
         }
     }
-    if (g_auto_srs && n >= AUTO_SRS_MIN_POINTS)
+    if (keep || (g_auto_srs && n >= AUTO_SRS_MIN_POINTS))
     {
         // first sight of a large table: keep it on the device (prover.cpp calls the MSM 9 times per proof on the same
         // ReferenceString::monomials buffer; copies of a ReferenceString get their own entry)
@@ -136,25 +192,23 @@ int resolve_table(const uint64_t* points, size_t n, const void** d_table)
         {
             for (size_t i = 0; i < g_srs.size(); ++i)
             {
-                if (g_srs[i].automatic)
+                if (g_srs[i].automatic && g_srs[i].pins == 0)
                 {
-                    bbg_rt::sync(g_stream);
-                    bbg_rt::dev_free(g_srs[i].d_table);
-                    g_srs.erase(g_srs.begin() + (long)i);
+                    srs_drop(i);
                     break;
                 }
             }
         }
-        SrsEntry s;
-        s.host_base = points;
-        s.n = n;
-        s.d_table = nullptr;
-        s.automatic = true;
-        s.fingerprint = table_fingerprint(points, n);
-        BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
-        BBG_CHECK(bbg_hostcopy::h2d(s.d_table, points, n * 128, g_stream));
-        g_srs.push_back(s);
-        *d_table = s.d_table;
+        void* d = nullptr;
+        BBG_CHECK(bbg_rt::dev_alloc(&d, n * 128));
+        const int e = bbg_hostcopy::h2d(d, points, n * 128, g_stream);
+        if (e != 0)
+        {
+            bbg_rt::dev_free(d);
+            return e;
+        }
+        BBG_CHECK(srs_add(points, n, d, true));
+        *d_table = d;
         return 0;
     }
     BBG_CHECK(g_stage_table.ensure(n * 128));
@@ -163,19 +217,35 @@ int resolve_table(const uint64_t* points, size_t n, const void** d_table)
     return 0;
 }
 
-int msm_host(const uint64_t* scalars, const uint64_t* points, size_t n, hostg1::hxyzz* out)
+// `batch` same-size MSMs of host scalars over one host table; each device of the instance uploads its own point range
+int msm_host_batched(const uint64_t* const* scalars, size_t batch, const uint64_t* points, size_t n, hostg1::hxyzz* out)
 {
     if (n == 0)
     {
-        *out = hostg1::infinity();
+        for (size_t b = 0; b < batch; ++b) out[b] = hostg1::infinity();
         return 0;
     }
-    if (scalars == nullptr || points == nullptr) return BBG_E_BAD_ARGUMENT;
+    if (points == nullptr) return BBG_E_BAD_ARGUMENT;
+    for (size_t b = 0; b < batch; ++b)
+        if (scalars[b] == nullptr) return BBG_E_BAD_ARGUMENT;
     const void* d_table = nullptr;
     BBG_CHECK(resolve_table(points, n, &d_table));
-    BBG_CHECK(g_stage_scalars.ensure(n * 32));
-    BBG_CHECK(bbg_hostcopy::h2d(g_stage_scalars.p, scalars, n * 32, g_stream));
-    return msm_device(g_stage_scalars.p, d_table, n, out, g_stream);
+    BBG_CHECK(g_stage_scalars.ensure(batch * n * 32));
+#ifndef BBG_EMULATE
+    // the other devices' workers copy straight out of the caller's buffers: page-lock them here, once, as a whole
+    if (msm_multi_device_count() > 1)
+        for (size_t b = 0; b < batch; ++b) (void)bbg_hostcopy::direct_copy_ok(scalars[b], n * 32);
+#endif
+    int ticket = -1;
+    BBG_CHECK(msm_launch_any(0, (const void* const*)scalars, true, g_stage_scalars.p, batch, d_table, n, g_stream, &ticket));
+    return msm_finish(ticket, out);
+}
+
+int msm_host(const uint64_t* scalars, const uint64_t* points, size_t n, hostg1::hxyzz* out)
+{
+    const uint64_t* one[1] = { scalars };
+    if (n > 0 && scalars == nullptr) return BBG_E_BAD_ARGUMENT;
+    return msm_host_batched(one, 1, points, n, out);
 }
 } // namespace
 
@@ -209,20 +279,48 @@ int bbg_init(int device)
     return 0;
 }
 
+int bbg_init_multi(const int* devices, int count)
+{
+    if (devices == nullptr || count < 1) return BBG_E_BAD_ARGUMENT;
+    BBG_CHECK(bbg_init(devices[0]));
+    std::lock_guard<std::mutex> lock(g_mutex);
+#ifndef BBG_EMULATE
+    int current = -1, visible = 0;
+    BBG_CHECK(cudaGetDevice(&current));
+    BBG_CHECK(cudaGetDeviceCount(&visible));
+    if (current != devices[0]) return BBG_E_BAD_ARGUMENT; // already initialised on another device
+    for (int i = 0; i < count; ++i)
+        if (devices[i] < 0 || devices[i] >= visible) return BBG_E_BAD_ARGUMENT;
+#endif
+    if (count == 1) return 0;
+    BBG_CHECK(msm_multi_init(devices, count));
+    // tables registered before the other devices joined
+    for (const SrsEntry& s : g_srs) BBG_CHECK(msm_multi_replicate(s.d_table, s.n * 128, g_stream));
+    return 0;
+}
+
+int bbg_device_count(void) { return msm_multi_device_count(); }
+
 int bbg_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_ready) return 0;
-    bbg_rt::sync(g_stream);
+    quiesce_all();
     ntt_release_tables();
-    msm_release_workspace();
+    msm_release_workspace(); // also stops the other devices' workers and frees their table replicas
     plonk::release_helpers();
     g_stage_coeffs.release();
     g_stage_scalars.release();
-    g_stage_scalars_async.release();
+    for (AsyncSlot& a : g_async_slots)
+    {
+        a.scalars.release();
+        a.ticket = -1;
+    }
     g_stage_table.release();
     for (SrsEntry& s : g_srs) bbg_rt::dev_free(s.d_table);
     g_srs.clear();
+    g_prover_srs.clear();
+    bbg_hostcopy::reg_cache().release();
 #ifndef BBG_EMULATE
     if (g_ev_start) cudaEventDestroy(g_ev_start);
     if (g_ev_stop) cudaEventDestroy(g_ev_stop);
@@ -230,6 +328,7 @@ int bbg_shutdown(void)
     for (cudaEvent_t ev : g_pipe_events) cudaEventDestroy(ev);
     g_pipe_events.clear();
     bbg_hostcopy::ring().release();
+    g_msm_ring.release();
     if (g_copy_in) cudaStreamDestroy(g_copy_in);
     if (g_copy_out) cudaStreamDestroy(g_copy_out);
     g_copy_in = g_copy_out = nullptr;
@@ -285,7 +384,7 @@ const char* bbg_error_string(int code)
 
 uint64_t bbg_launch_count(void)
 {
-    return (uint64_t)ntt_launch_count() + (uint64_t)msm_launch_count() + (uint64_t)plonk::launch_count() + g_misc_launches;
+    return (uint64_t)ntt_launch_count() + (uint64_t)msm_launch_count() + (uint64_t)plonk::launch_count() + (uint64_t)selftest_launch_count() + g_misc_launches;
 }
 
 // ---- NTT ----------------------------------------------------------------------------------------
@@ -385,22 +484,20 @@ int bbg_srs_register(const uint64_t* table_2n, size_t n)
     {
         if (g_srs[i].host_base == table_2n)
         {
-            bbg_rt::dev_free(g_srs[i].d_table);
-            g_srs.erase(g_srs.begin() + (long)i);
+            srs_drop(i);
             break;
         }
     }
-    SrsEntry s;
-    s.host_base = table_2n;
-    s.n = n;
-    s.d_table = nullptr;
-    s.automatic = false;
-    s.fingerprint = table_fingerprint(table_2n, n);
-    BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
-    BBG_CHECK(bbg_hostcopy::h2d(s.d_table, table_2n, n * 128, g_stream));
-    BBG_CHECK(bbg_rt::sync(g_stream));
-    g_srs.push_back(s);
-    return 0;
+    void* d = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc(&d, n * 128));
+    int e = bbg_hostcopy::h2d(d, table_2n, n * 128, g_stream);
+    if (e == 0) e = bbg_rt::sync(g_stream);
+    if (e != 0)
+    {
+        bbg_rt::dev_free(d);
+        return e;
+    }
+    return srs_add(table_2n, n, d, false);
 }
 
 int bbg_set_auto_srs_cache(int enable)
@@ -417,9 +514,7 @@ int bbg_srs_unregister(const uint64_t* table_2n)
     {
         if (g_srs[i].host_base == table_2n)
         {
-            bbg_rt::sync(g_stream);
-            bbg_rt::dev_free(g_srs[i].d_table);
-            g_srs.erase(g_srs.begin() + (long)i);
+            srs_drop(i);
             return 0;
         }
     }
@@ -432,6 +527,30 @@ int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, 
     BBG_CHECK(ensure_ready());
     hostg1::hxyzz r;
     BBG_CHECK(msm_host(scalars, points_table, n, &r));
+    hostg1::to_normalized_jacobian(r, out_xyz);
+    return 0;
+}
+
+// pippenger_low_memory / pippenger_precomputed take the n plain points and apply the endomorphism on the fly
+// (scalar_multiplication.cpp:142-263, :478-573); here the 2n-entry table is built on the device next to the upload
+int bbg_msm_g1_points(const uint64_t* scalars, const uint64_t* points_n, size_t n, uint64_t out_xyz[12])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (out_xyz == nullptr) return BBG_E_BAD_ARGUMENT;
+    hostg1::hxyzz r = hostg1::infinity();
+    if (n > 0)
+    {
+        if (scalars == nullptr || points_n == nullptr) return BBG_E_BAD_ARGUMENT;
+        BBG_CHECK(g_stage_table.ensure(n * 192));
+        char* d_table = (char*)g_stage_table.p;
+        char* d_points = d_table + n * 128;
+        BBG_CHECK(bbg_hostcopy::h2d(d_points, points_n, n * 64, g_stream));
+        BBG_CHECK(g1_build_endo_table_device(d_points, d_table, n, g_stream));
+        BBG_CHECK(g_stage_scalars.ensure(n * 32));
+        BBG_CHECK(bbg_hostcopy::h2d(g_stage_scalars.p, scalars, n * 32, g_stream));
+        BBG_CHECK(msm_device(g_stage_scalars.p, d_table, n, &r, g_stream));
+    }
     hostg1::to_normalized_jacobian(r, out_xyz);
     return 0;
 }
@@ -457,19 +576,8 @@ int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* po
         }
         else
         {
-            const void* d_table = nullptr;
-            if (points_tables[i] == nullptr) return BBG_E_BAD_ARGUMENT;
-            BBG_CHECK(resolve_table(points_tables[i], n, &d_table));
-            BBG_CHECK(g_stage_scalars.ensure(same * n * 32));
-            const void* ptrs[GROUP];
-            for (size_t k = 0; k < same; ++k)
-            {
-                if (scalars[i + k] == nullptr) return BBG_E_BAD_ARGUMENT;
-                ptrs[k] = (char*)g_stage_scalars.p + k * n * 32;
-                BBG_CHECK(bbg_hostcopy::h2d((void*)ptrs[k], scalars[i + k], n * 32, g_stream));
-            }
             hostg1::hxyzz r[GROUP];
-            BBG_CHECK(msm_device_batched(ptrs, same, d_table, n, r, g_stream));
+            BBG_CHECK(msm_host_batched(scalars + i, same, points_tables[i], n, r));
             for (size_t k = 0; k < same; ++k) hostg1::to_normalized_jacobian(r[k], out_xyz + 12 * (i + k));
         }
         i += same;
@@ -517,17 +625,35 @@ int bbg_msm_g1_launch(const uint64_t* scalars, const uint64_t* points_table, siz
     if (n == 0) return 0;
     if (scalars == nullptr || points_table == nullptr) return BBG_E_BAD_ARGUMENT;
     const void* d_table = nullptr;
-    BBG_CHECK(resolve_table(points_table, n, &d_table));
-    // own staging buffer, own stream: uploads and kernels of successive launches are ordered by that stream, and the
-    // calls made on the work stream in between (transforms with their own copies) run beside them
-    BBG_CHECK(g_stage_scalars_async.ensure(n * 32));
+    // keep: the MSM outlives this call, so the table must not be the shared staging buffer
+    BBG_CHECK(resolve_table(points_table, n, &d_table, /*keep=*/true));
+    // own staging buffer per pending launch, own stream: uploads and kernels of successive launches are ordered by that
+    // stream, and the calls made on the work stream in between (transforms with their own copies) run beside them
+    AsyncSlot* slot = nullptr;
+    for (AsyncSlot& a : g_async_slots)
+    {
+        if (a.ticket >= 0 && !msm_ticket_pending(a.ticket)) a.ticket = -1;
+        if (slot == nullptr && a.ticket < 0) slot = &a;
+    }
+    if (slot == nullptr) return BBG_E_BAD_ARGUMENT; // too many MSMs in flight
     cudaStream_t st = g_stream;
 #ifndef BBG_EMULATE
     st = g_msm_stream;
+    // a table uploaded just now travels on the work stream: the MSM stream must see it
+    BBG_CHECK(cudaEventRecord(g_msm_fence, g_stream));
+    BBG_CHECK(cudaStreamWaitEvent(g_msm_stream, g_msm_fence, 0));
+    if (slot->scalars.bytes < n * 32) BBG_CHECK(cudaStreamSynchronize(g_msm_stream)); // growing frees the old buffer
 #endif
-    BBG_CHECK(bbg_hostcopy::h2d(g_stage_scalars_async.p, scalars, n * 32, st));
-    const void* one[1] = { g_stage_scalars_async.p };
-    return msm_launch(1, one, 1, d_table, n, st, ticket);
+    BBG_CHECK(slot->scalars.ensure(n * 32));
+#ifndef BBG_EMULATE
+    BBG_CHECK(bbg_hostcopy::h2d_ring(g_msm_ring, slot->scalars.p, scalars, n * 32, st));
+#else
+    BBG_CHECK(bbg_hostcopy::h2d(slot->scalars.p, scalars, n * 32, st));
+#endif
+    const void* one[1] = { slot->scalars.p };
+    BBG_CHECK(msm_launch(1, one, 1, d_table, n, st, ticket));
+    slot->ticket = *ticket;
+    return 0;
 }
 
 int bbg_msm_g1_finish(int ticket, uint64_t out_xyz[12])
@@ -645,17 +771,14 @@ int bbg_srs_from_transcript(const uint8_t* g1_bytes, size_t n, uint64_t* table_2
     {
         if (g_srs[i].host_base == table_2n)
         {
-            bbg_rt::sync(g_stream);
-            bbg_rt::dev_free(g_srs[i].d_table);
-            g_srs.erase(g_srs.begin() + (long)i);
+            srs_drop(i);
             break;
         }
     }
-    SrsEntry s;
-    s.host_base = table_2n;
-    s.n = n;
-    s.d_table = nullptr;
-    s.automatic = false;
+    struct
+    {
+        void* d_table;
+    } s = { nullptr };
     BBG_CHECK(bbg_rt::dev_alloc(&s.d_table, n * 128));
     int e = 0;
     if (n > 1)
@@ -671,9 +794,7 @@ int bbg_srs_from_transcript(const uint8_t* g1_bytes, size_t n, uint64_t* table_2
         bbg_rt::dev_free(s.d_table);
         return e;
     }
-    s.fingerprint = table_fingerprint(table_2n, n);
-    g_srs.push_back(s); // the device copy IS the registered SRS: no second upload
-    return 0;
+    return srs_add(table_2n, n, s.d_table, false); // the device copy IS the registered SRS: no second upload
 }
 
 // ---- HBM-resident PLONK prover rounds (bbg_plonk.cu) -------------------------------------------------
@@ -691,7 +812,18 @@ int bbg_plonk_destroy(bbg_plonk_prover* p)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (p == nullptr) return 0;
-    bbg_rt::sync(g_stream);
+    quiesce_all();
+    for (size_t k = 0; k < g_prover_srs.size();)
+    {
+        if (g_prover_srs[k].first != (const void*)p)
+        {
+            ++k;
+            continue;
+        }
+        for (SrsEntry& s : g_srs)
+            if (s.host_base == g_prover_srs[k].second && s.pins > 0) --s.pins;
+        g_prover_srs.erase(g_prover_srs.begin() + (long)k);
+    }
     plonk::destroy((plonk::Prover*)p);
     return 0;
 }
@@ -729,7 +861,30 @@ int bbg_plonk_set_srs(bbg_plonk_prover* p, const uint64_t* points_table, size_t 
     BBG_CHECK(ensure_ready());
     if (p == nullptr || points_table == nullptr) return BBG_E_BAD_ARGUMENT;
     const void* d_table = nullptr;
-    BBG_CHECK(resolve_table(points_table, n, &d_table));
+    // the prover keeps the device pointer: the table is cached whatever its size and pinned against eviction until the
+    // prover is destroyed or handed another table.  (A table whose host buffer is rewritten in place is dropped by the
+    // fingerprint check of the next MSM that names it; call bbg_plonk_set_srs again after changing it.)
+    BBG_CHECK(resolve_table(points_table, n, &d_table, /*keep=*/true));
+    for (size_t k = 0; k < g_prover_srs.size();)
+    {
+        if (g_prover_srs[k].first != (const void*)p)
+        {
+            ++k;
+            continue;
+        }
+        for (SrsEntry& s : g_srs)
+            if (s.host_base == g_prover_srs[k].second && s.pins > 0) --s.pins;
+        g_prover_srs.erase(g_prover_srs.begin() + (long)k);
+    }
+    for (SrsEntry& s : g_srs)
+    {
+        if (points_table >= s.host_base && points_table + 16 * n <= s.host_base + 16 * s.n)
+        {
+            ++s.pins;
+            g_prover_srs.push_back({ (const void*)p, s.host_base });
+            break;
+        }
+    }
     return plonk::set_srs((plonk::Prover*)p, d_table);
 }
 int bbg_plonk_round_wires(bbg_plonk_prover* p, uint64_t* out_xyz)
@@ -779,6 +934,57 @@ int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, con
     return plonk::round_openings((plonk::Prover*)p, nu_powers, beta_inv, zeta, zeta_omega, wire_shift_terms, selector_terms, out_xyz, g_stream);
 }
 
+// ---- device self test of the field / group primitives (bbg_selftest.cu) ---------------------------------
+namespace
+{
+int selftest_run(bool group, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count)
+{
+    const size_t elem = group ? 64 : 32;
+    if (count == 0) return 0;
+    if (a == nullptr || out == nullptr || (group && b == nullptr)) return BBG_E_BAD_ARGUMENT;
+    BBG_CHECK(g_stage_coeffs.ensure(3 * count * elem));
+    char* d_a = (char*)g_stage_coeffs.p;
+    char* d_b = d_a + count * elem;
+    char* d_o = d_b + count * elem;
+    BBG_CHECK(bbg_hostcopy::h2d(d_a, a, count * elem, g_stream));
+    if (b != nullptr) BBG_CHECK(bbg_hostcopy::h2d(d_b, b, count * elem, g_stream));
+    if (group) BBG_CHECK(g1_selftest_device(op, d_a, d_b, d_o, count, g_stream));
+    else BBG_CHECK(field_selftest_device(field, op, d_a, b != nullptr ? d_b : nullptr, d_o, count, g_stream));
+    BBG_CHECK(bbg_hostcopy::d2h(out, d_o, count * elem, g_stream));
+    return bbg_rt::sync(g_stream);
+}
+} // namespace
+int bbg_field_selftest(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (field < 0 || field > 1 || op < 0 || op > 12) return BBG_E_BAD_ARGUMENT;
+    return selftest_run(false, field, op, a, b, out, count);
+}
+int bbg_g1_selftest(int op, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t count)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (op < 0 || op > 6) return BBG_E_BAD_ARGUMENT;
+    return selftest_run(true, 0, op, p, q, out, count);
+}
+
+// ---- caller-owned host buffers ----------------------------------------------------------------------
+int bbg_set_host_register_cache(int enable)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (!enable) quiesce_all();
+    bbg_hostcopy::reg_cache().enable(enable != 0);
+    return 0;
+}
+int bbg_host_buffer_forget(const void* host_ptr)
+{
+    // no library lock: free() wrappers call this from any thread, usually for blocks the library never saw
+    if (host_ptr != nullptr) bbg_hostcopy::reg_cache().forget(host_ptr);
+    return 0;
+}
+
 // ---- device memory helpers ------------------------------------------------------------------------
 int bbg_dev_alloc(void** d_ptr, size_t bytes)
 {
@@ -789,7 +995,7 @@ int bbg_dev_alloc(void** d_ptr, size_t bytes)
 int bbg_dev_free(void* d_ptr)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    bbg_rt::sync(g_stream);
+    quiesce_all();
     return bbg_rt::dev_free(d_ptr);
 }
 int bbg_copy_h2d(void* d_dst, const void* h_src, size_t bytes)

@@ -5,15 +5,25 @@
 // against ~55 GB/s for pinned memory), which made the PLONK prover's NTT calls copy-bound.  Here pageable buffers
 // go through a small ring of pinned chunks filled / drained by several host threads while the previous chunk is on
 // the wire; buffers that are already pinned (bench.py, cudaHostRegister'ed memory) are copied directly.
+//
+// Registration cache (off by default, bbg_set_host_register_cache; the shims switch it on): the reference's callers
+// reuse the same long-lived buffers call after call (barretenberg::polynomial members of the prover and the proving key,
+// ReferenceString::monomials), so a pageable buffer of >= 1 MiB that is seen a SECOND time behind the same address is
+// page-locked in place with cudaHostRegister and from then on copied at the pinned rate without the staging memcpy.
+// The caller's side of the contract: a registered buffer must be handed to bbg_host_buffer_forget() before it is freed
+// (the prover link wraps free() to do that, shim/host_buffer_free_wrap.cpp) — the driver keeps DMA mappings of the
+// physical pages, and an address range that was unmapped and mapped again would be read / written through the old ones.
 #pragma once
 #include "bbg_rt.h"
 
 #include <string.h>
 
 #ifndef BBG_EMULATE
+#include <atomic>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <stdlib.h>
 #include <thread>
 #include <vector>
 
@@ -99,6 +109,175 @@ class CopyPool
     size_t bytes_ = 0, part_ = 0;
 };
 
+
+inline bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- cudaHostRegister cache for caller-owned pageable buffers -----------------------------------------------------------
+class RegCache
+{
+  public:
+    void enable(bool on)
+    {
+        std::lock_guard<std::mutex> lock(m_);
+        enabled_ = on;
+        if (const char* e = getenv("BBG_HOST_REGISTER_MAX_MB"))
+        {
+            const long v = atol(e);
+            if (v >= 0) max_bytes_ = (size_t)v << 20;
+        }
+        if (!on) drop_all_locked();
+    }
+    bool enabled() const { return enabled_; }
+    // Called for a pageable buffer about to be copied.  Returns true when [p, p + bytes) is page-locked now (registered
+    // by an earlier call or by this one: second sighting of the same address and size).
+    bool note(const void* p, size_t bytes)
+    {
+        if (!enabled_) return false;
+        std::lock_guard<std::mutex> lock(m_);
+        ++clock_;
+        for (Entry& e : entries_)
+        {
+            if ((const char*)p >= e.base && (const char*)p + bytes <= e.base + e.bytes && e.registered)
+            {
+                e.used = clock_;
+                return true;
+            }
+        }
+        for (Entry& e : entries_)
+        {
+            if (e.base == (const char*)p && e.bytes == bytes)
+            {
+                e.used = clock_;
+                return try_register_locked(e);
+            }
+        }
+        if (entries_.size() >= MAX_ENTRIES) evict_locked(/*registered_only=*/false);
+        Entry n;
+        n.base = (const char*)p;
+        n.bytes = bytes;
+        n.used = clock_;
+        entries_.push_back(n);
+        count_.store(entries_.size(), std::memory_order_release);
+        return false;
+    }
+    // the caller is about to free (or has remapped) the buffer that starts at / contains p
+    void forget(const void* p)
+    {
+        if (count_.load(std::memory_order_acquire) == 0) return; // fast path: free() wrappers call this for every block
+        std::lock_guard<std::mutex> lock(m_);
+        for (size_t i = 0; i < entries_.size();)
+        {
+            Entry& e = entries_[i];
+            if ((const char*)p >= e.base && (const char*)p < e.base + e.bytes)
+            {
+                unregister_locked(e);
+                entries_.erase(entries_.begin() + (long)i);
+            }
+            else
+                ++i;
+        }
+        count_.store(entries_.size(), std::memory_order_release);
+    }
+    void release()
+    {
+        std::lock_guard<std::mutex> lock(m_);
+        drop_all_locked();
+    }
+    size_t registered_bytes() const { return total_; }
+
+  private:
+    struct Entry
+    {
+        const char* base = nullptr;
+        size_t bytes = 0;
+        unsigned long used = 0;
+        bool registered = false;
+        bool failed = false;
+        char* reg_base = nullptr; // page-rounded range actually registered
+        size_t reg_bytes = 0;
+    };
+    static constexpr size_t MAX_ENTRIES = 96;
+    bool try_register_locked(Entry& e)
+    {
+        if (e.failed) return false;
+        const size_t page = 4096;
+        char* lo = (char*)((uintptr_t)e.base & ~(uintptr_t)(page - 1));
+        char* hi = (char*)(((uintptr_t)e.base + e.bytes + page - 1) & ~(uintptr_t)(page - 1));
+        const size_t len = (size_t)(hi - lo);
+        while (total_ + len > max_bytes_ && evict_locked(/*registered_only=*/true)) {}
+        if (total_ + len > max_bytes_)
+        {
+            e.failed = true;
+            return false;
+        }
+        const cudaError_t err = cudaHostRegister(lo, len, cudaHostRegisterPortable);
+        if (err != cudaSuccess)
+        {
+            cudaGetLastError();
+            e.failed = true;
+            // neighbouring heap blocks may share our first / last page with an earlier registration
+            return is_pinned(e.base) && is_pinned(e.base + e.bytes - 1) && err == cudaErrorHostMemoryAlreadyRegistered;
+        }
+        e.registered = true;
+        e.reg_base = lo;
+        e.reg_bytes = len;
+        total_ += len;
+        return true;
+    }
+    void unregister_locked(Entry& e)
+    {
+        if (!e.registered) return;
+        cudaDeviceSynchronize(); // nothing may still be on the wire from / to these pages
+        cudaHostUnregister(e.reg_base);
+        cudaGetLastError();
+        total_ -= e.reg_bytes;
+        e.registered = false;
+    }
+    bool evict_locked(bool registered_only)
+    {
+        long best = -1;
+        for (size_t i = 0; i < entries_.size(); ++i)
+        {
+            if (registered_only && !entries_[i].registered) continue;
+            if (best < 0 || entries_[i].used < entries_[(size_t)best].used) best = (long)i;
+        }
+        if (best < 0) return false;
+        unregister_locked(entries_[(size_t)best]);
+        entries_.erase(entries_.begin() + best);
+        count_.store(entries_.size(), std::memory_order_release);
+        return true;
+    }
+    void drop_all_locked()
+    {
+        for (Entry& e : entries_) unregister_locked(e);
+        entries_.clear();
+        count_.store(0, std::memory_order_release);
+    }
+    std::mutex m_;
+    std::vector<Entry> entries_;
+    std::atomic<size_t> count_{ 0 };
+    bool enabled_ = false;
+    unsigned long clock_ = 0;
+    size_t total_ = 0;
+    size_t max_bytes_ = (size_t)16 << 30;
+};
+inline RegCache& reg_cache()
+{
+    static RegCache c;
+    return c;
+}
+// pinned already, or page-locked in place by the registration cache
+inline bool direct_copy_ok(const void* h, size_t bytes) { return is_pinned(h) || reg_cache().note(h, bytes); }
+
 struct Ring
 {
     void* buf[RING] = {};
@@ -147,21 +326,11 @@ inline Ring& ring()
     return r;
 }
 
-inline bool is_pinned(const void* p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
-    {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-}
 
 // `r`: the pinned staging ring to use (one per host thread that copies; the default ring belongs to the caller's thread)
 inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t st)
 {
-    if (bytes < SMALL || is_pinned(h)) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+    if (bytes < SMALL || direct_copy_ok(h, bytes)) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
     BBG_CHECK(r.init());
     size_t off = 0;
     while (off < bytes)
@@ -179,10 +348,9 @@ inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t 
 inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st) { return h2d_ring(ring(), d, h, bytes, st); }
 
 // returns with the data in h (synchronous for pageable destinations, like cudaMemcpy)
-inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st)
+inline int d2h_ring(Ring& r, void* h, const void* d, size_t bytes, cudaStream_t st)
 {
-    if (bytes < SMALL || is_pinned(h)) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
-    Ring& r = ring();
+    if (bytes < SMALL || direct_copy_ok(h, bytes)) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
     BBG_CHECK(r.init());
     const size_t chunks = (bytes + CHUNK - 1) / CHUNK;
     for (size_t k = 0; k < chunks + (RING - 1); ++k)
@@ -191,6 +359,9 @@ inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st)
         {
             const int i = (int)(k % RING);
             const size_t off = k * CHUNK, len = bytes - off < CHUNK ? bytes - off : CHUNK;
+            // the slot may still hold an upload queued by an earlier h2d on another stream (an MSM launched beside the
+            // transforms): wait until it is off the wire before overwriting it
+            if (k < (size_t)RING) BBG_CHECK(cudaEventSynchronize(r.ev[i]));
             BBG_CHECK(cudaMemcpyAsync(r.buf[i], (const char*)d + off, len, cudaMemcpyDeviceToHost, st));
             BBG_CHECK(cudaEventRecord(r.ev[i], st));
         }
@@ -205,11 +376,23 @@ inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st)
     }
     return 0;
 }
+inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st) { return d2h_ring(ring(), h, d, bytes, st); }
 } // namespace bbg_hostcopy
 #else
 namespace bbg_hostcopy
 {
 inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st) { return bbg_rt::h2d(d, h, bytes, st); }
 inline int d2h(void* h, const void* d, size_t bytes, cudaStream_t st) { return bbg_rt::d2h(h, d, bytes, st); }
+struct RegCache
+{
+    void enable(bool) {}
+    void forget(const void*) {}
+    void release() {}
+};
+inline RegCache& reg_cache()
+{
+    static RegCache c;
+    return c;
+}
 } // namespace bbg_hostcopy
 #endif

@@ -42,7 +42,21 @@ int msm_device_batched(const void* const* d_scalars, size_t batch, const void* d
 // msm_finish waits for that MSM and folds its windows on the host (up to 6 tickets may be pending)
 int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const void* d_table, size_t n, cudaStream_t stream, int* ticket_out);
 int msm_finish(int ticket, void* out_xyzz_host);
+// msm_launch with the scalars either on the primary device or — host_scalars — still in the caller's host buffers: the
+// primary's point range is uploaded into `staging` (batch * n * 32 bytes of primary-device memory) behind `stream`, and
+// in a multi-GPU instance every other device uploads its own range over its own PCIe link
+int msm_launch_any(int workspace, const void* const* scalars, bool host_scalars, void* staging, size_t batch, const void* d_table, size_t n,
+                   cudaStream_t stream, int* ticket_out);
+bool msm_ticket_pending(int ticket);
 int msm_release_workspace();
+// Multi-GPU (one process, several devices): devices[0] = the primary device the library was initialised on; the others
+// get a worker thread each.  Registered point tables are replicated to every device; msm_launch then fans an MSM over
+// such a table out by contiguous point range (scalar_multiplication.cpp:703-728) and msm_finish adds the per-device sums.
+int msm_multi_init(const int* devices, int count);
+int msm_multi_device_count();
+int msm_multi_replicate(const void* d_table_primary, size_t bytes, cudaStream_t stream);
+int msm_multi_drop_replica(const void* d_table_primary);
+int msm_multi_quiesce();
 size_t msm_launch_count();
 // d_points[i] = (start + i * step) * G (affine, canonical), i < n; start / step: Fr Montgomery limbs (host)
 int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* step_mont, void* d_points, size_t n, cudaStream_t stream);

@@ -28,10 +28,20 @@
 // written + read, 64 MiB sorted entries, ~1 GiB of 64-byte point gathers mostly served from L2.
 #include "bbg_internal.h"
 #include "bbg_host_g1.h"
+#include "bbg_hostcopy.h"
 
+#include <atomic>
 #include <chrono>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
+#ifndef BBG_EMULATE
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#endif
 
 namespace bbg
 {
@@ -539,7 +549,7 @@ __global__ void __launch_bounds__(64) g1_progression_kernel(fe a0, fe d, fe* poi
 namespace
 {
 using namespace msmk;
-size_t g_msm_launches = 0;
+std::atomic<size_t> g_msm_launches{ 0 };
 
 struct Workspace
 {
@@ -555,14 +565,22 @@ struct Workspace
         if (e == 0) bytes = need;
         return e;
     }
-} g_ws_pool[2];
+    void release()
+    {
+        if (p) bbg_rt::dev_free(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
 
-// An MSM in flight: everything the host finish needs once the kernels are done.  msm_launch() queues the kernels and the
-// copy of the per-window reductions into a pinned host slot and returns a ticket; msm_finish() waits for that copy and folds
+// An MSM in flight: everything the host finish needs once the kernels are done.  launch queues the kernels and the
+// copy of the per-window reductions into a pinned host slot and returns a ticket; finish waits for that copy and folds
 // the windows.  Two workspaces let MSMs on two streams overlap (the latency-bound tail kernels of one under the accumulate
 // pass of the next); several tickets may be pending per workspace because the copy is ordered behind the kernels on the
 // launching stream.
 constexpr int MSM_TICKETS = 6;
+constexpr int MAX_DEVICES = 16;
+struct PeerJob;
 struct MsmTicket
 {
     bool pending = false;
@@ -573,10 +591,23 @@ struct MsmTicket
     size_t red_count = 0;
     void* host_red = nullptr;
     size_t host_bytes = 0;
+    // multi-GPU: the shards of this MSM that run on the other devices (primary context only)
+    PeerJob* peer_jobs[MAX_DEVICES] = {};
+    int peer_count = 0;
 #ifndef BBG_EMULATE
     cudaEvent_t done = nullptr;
+    cudaEvent_t scalars_ready = nullptr; // recorded on the launching stream before the peers read the scalars
 #endif
-} g_tickets[MSM_TICKETS];
+};
+
+// Everything one device needs to run MSMs: the primary device owns g_primary, every other device of a multi-GPU
+// library instance has its own inside its worker (below).
+struct MsmContext
+{
+    Workspace ws[2];
+    MsmTicket tickets[MSM_TICKETS];
+};
+MsmContext g_primary;
 
 int ticket_host_buffer(MsmTicket& t, size_t bytes)
 {
@@ -595,6 +626,26 @@ int ticket_host_buffer(MsmTicket& t, size_t bytes)
     return 0;
 }
 
+void context_release(MsmContext& ctx)
+{
+    for (Workspace& w : ctx.ws) w.release();
+    for (MsmTicket& t : ctx.tickets)
+    {
+#ifndef BBG_EMULATE
+        if (t.host_red) cudaFreeHost(t.host_red);
+        if (t.done) cudaEventDestroy(t.done);
+        if (t.scalars_ready) cudaEventDestroy(t.scalars_ready);
+        t.done = nullptr;
+        t.scalars_ready = nullptr;
+#else
+        free(t.host_red);
+#endif
+        t.host_red = nullptr;
+        t.host_bytes = 0;
+        t.pending = false;
+    }
+}
+
 // Window plan.  Cost model in units of one mixed addition, fitted to B200 measurements (r01, 2^17 .. 2^26 points):
 //   per entry  1.13  (accumulate 0.16 ns + histogram / scatter atomics), + 0.15 when there are fewer than 2^16 buckets
 //              in total (few distinct counters: the L2 atomic units serialise);
@@ -611,6 +662,11 @@ void pick_windows(size_t n, int& c_out, int& W_out)
     if (c_lo > 22) c_lo = 22;
     int c_hi = target + 3 > 22 ? 22 : target + 3;
     if (c_hi < c_lo) c_hi = c_lo; // tiny n: the range collapses to the smallest window
+    if (const char* e = getenv("BBG_MSM_WINDOW")) // development override
+    {
+        const int v = atoi(e);
+        if (v >= 2 && v <= 22) c_lo = c_hi = v;
+    }
     double best = -1;
     c_out = c_lo;
     W_out = (128 + c_lo - 1) / c_lo;
@@ -675,55 +731,22 @@ Plan make_plan(size_t n)
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-} // namespace
 
-size_t msm_launch_count() { return g_msm_launches; }
-int msm_release_workspace()
+// `batch` MSMs of the same size over the same point table in ONE pipeline on the current device: MSM b's windows become
+// the virtual windows b * W .. b * W + W - 1 of a single sort / accumulate / reduce pass, so the latency-bound tail
+// kernels (scan, fix-up, chunk, reduce) and the host round trip are paid once per batch (the prover commits 3 + 1 + 3 + 2
+// polynomials per proof against the same SRS, prover.cpp:65-124, :640-652).
+int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_scalars, size_t batch, const void* d_table, size_t n, cudaStream_t st)
 {
-    for (Workspace& w : g_ws_pool)
-    {
-        if (w.p) bbg_rt::dev_free(w.p);
-        w.p = nullptr;
-        w.bytes = 0;
-    }
-    for (MsmTicket& t : g_tickets)
-    {
-#ifndef BBG_EMULATE
-        if (t.host_red) cudaFreeHost(t.host_red);
-        if (t.done) cudaEventDestroy(t.done);
-        t.done = nullptr;
-#else
-        free(t.host_red);
-#endif
-        t.host_red = nullptr;
-        t.host_bytes = 0;
-        t.pending = false;
-    }
-    return 0;
-}
-
-// `batch` MSMs of the same size over the same point table in ONE pipeline: MSM b's windows become the virtual windows
-// b * W .. b * W + W - 1 of a single sort / accumulate / reduce pass, so the latency-bound tail kernels (scan, fix-up,
-// chunk, reduce) and the host round trip are paid once per batch (the prover commits 3 + 1 + 3 + 2 polynomials per
-// proof against the same SRS, prover.cpp:65-124, :640-652).
-// out_xyzz_host: HOST buffer of batch x 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sums
-int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const void* d_table, size_t n, cudaStream_t st, int* ticket_out)
-{
-    if (workspace < 0 || workspace > 1 || ticket_out == nullptr || batch == 0) return 1007;
-    int id = -1;
-    for (int i = 0; i < MSM_TICKETS && id < 0; ++i)
-        if (!g_tickets[i].pending) id = i;
-    if (id < 0) return 1007; // too many MSMs in flight
-    MsmTicket& tk = g_tickets[id];
+    MsmTicket& tk = ctx.tickets[id];
     tk.batch = batch;
     tk.zero = (n == 0);
     if (n == 0)
     {
         tk.pending = true;
-        *ticket_out = id;
         return 0;
     }
-    Workspace& g_ws = g_ws_pool[workspace];
+    Workspace& g_ws = ctx.ws[workspace];
     if (2 * n > ((size_t)1 << 28)) return 1008;
     const Plan single = make_plan(n);
     if (single.c < 2 || single.c > 22 || single.W < 1 || single.W > 64 || (single.W - 1) * single.c >= 127 || single.W * single.c < 128)
@@ -825,21 +848,18 @@ int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const 
     tk.pl = pl;
     tk.red_count = red_count;
     tk.pending = true;
-    *ticket_out = id;
     return 0;
 }
 
 // ---- 7. host finish: waits for the ticket's kernels, folds the windows of every MSM of the batch ---------------------
-int msm_finish(int ticket, void* out_xyzz_host)
+int context_finish(MsmContext& ctx, int ticket, hostg1::hxyzz* out)
 {
-    if (ticket < 0 || ticket >= MSM_TICKETS || !g_tickets[ticket].pending) return 1007;
-    MsmTicket& tk = g_tickets[ticket];
+    MsmTicket& tk = ctx.tickets[ticket];
     tk.pending = false;
     const size_t batch = tk.batch;
     if (tk.zero)
     {
-        const hostg1::hxyzz inf = hostg1::infinity();
-        for (size_t b = 0; b < batch; ++b) memcpy((char*)out_xyzz_host + b * sizeof inf, &inf, sizeof inf);
+        for (size_t b = 0; b < batch; ++b) out[b] = hostg1::infinity();
         return 0;
     }
 #ifndef BBG_EMULATE
@@ -852,27 +872,526 @@ int msm_finish(int ticket, void* out_xyzz_host)
     const int bits = pl.reduce_outputs - 2;
     for (size_t b = 0; b < batch; ++b)
     {
-    hostg1::hxyzz result = hostg1::infinity();
-    for (int w = single.W - 1; w >= 0; --w)
-    {
-        const hostg1::hxyzz* rw = r_data + (b * (size_t)single.W + (size_t)w) * pl.reduce_outputs;
-        // sum_t t * A_t = sum_r 2^r T_r   (Horner from the top bit)
-        hostg1::hxyzz tsum = hostg1::infinity();
-        for (int b = bits - 1; b >= 0; --b)
+        hostg1::hxyzz result = hostg1::infinity();
+        for (int w = single.W - 1; w >= 0; --w)
         {
-            tsum = hostg1::dbl(tsum);
-            tsum = hostg1::add(tsum, rw[b]);
+            const hostg1::hxyzz* rw = r_data + (b * (size_t)single.W + (size_t)w) * pl.reduce_outputs;
+            // sum_t t * A_t = sum_r 2^r T_r   (Horner from the top bit)
+            hostg1::hxyzz tsum = hostg1::infinity();
+            for (int r = bits - 1; r >= 0; --r)
+            {
+                tsum = hostg1::dbl(tsum);
+                tsum = hostg1::add(tsum, rw[r]);
+            }
+            for (int i = 0; i < pl.chunk_log; ++i) tsum = hostg1::dbl(tsum); // * chunk size
+            // bucket value = t * chunk + v + 1
+            hostg1::hxyzz sw = hostg1::add(hostg1::add(tsum, rw[bits]), rw[bits + 1]);
+            // result = 2^c * result + S_w   (reference :619-639, here with plain c-bit windows)
+            for (int i = 0; i < pl.c; ++i) result = hostg1::dbl(result);
+            result = hostg1::add(result, sw);
         }
-        for (int i = 0; i < pl.chunk_log; ++i) tsum = hostg1::dbl(tsum); // * chunk size
-        // bucket value = t * chunk + v + 1
-        hostg1::hxyzz sw = hostg1::add(hostg1::add(tsum, rw[bits]), rw[bits + 1]);
-        // result = 2^c * result + S_w   (reference :619-639, here with plain c-bit windows)
-        for (int i = 0; i < pl.c; ++i) result = hostg1::dbl(result);
-        result = hostg1::add(result, sw);
-    }
-    memcpy((char*)out_xyzz_host + b * sizeof result, &result, sizeof result);
+        out[b] = result;
     }
     bbg_prof::add_host_ms(bbg_prof::MSM_HOST_FINISH, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+    return 0;
+}
+
+// ================================================================================================
+// Multi-GPU: point ranges fanned out over the devices of one box
+// ================================================================================================
+// The reference splits an MSM into contiguous point ranges inside batched_scalar_multiplications, one per OpenMP thread
+// (scalar_multiplication.cpp:703-728), and folds the partial sums on the calling thread (:750-765).  The same split here,
+// one range per GPU: the primary device (the one every other entry point of the library runs on) keeps range 0, each other
+// device has a worker thread with its own stream, MSM context and replica of the registered point tables; a worker pulls
+// its slice of the scalars (peer copy over NVLink from the primary's HBM, or its own PCIe upload from the caller's host
+// buffer), runs the same single-device pipeline and folds its windows; the launching thread adds the per-device sums.
+// No collective: the only exchange is 128 bytes per device and MSM, handed over in host memory.
+#ifndef BBG_EMULATE
+constexpr int PEER_INFLIGHT = 4;
+struct PeerJob
+{
+    const void* src[4] = {};
+    size_t batch = 0;
+    size_t lo = 0, count = 0; // scalar index range of this shard
+    bool host_src = false;
+    int src_device = 0;
+    cudaEvent_t ready = nullptr; // scalars valid on the source device (device sources only)
+    const void* d_table = nullptr; // this device's replica, already offset to the shard
+    hostg1::hxyzz out[4];
+    int err = 0;
+    std::atomic<int> done{ 0 };
+};
+
+struct Replica
+{
+    const char* base0;
+    size_t bytes;
+    void* peer[MAX_DEVICES];
+};
+
+class PeerWorker
+{
+  public:
+    PeerWorker(int device, int primary) : device_(device), primary_(primary), th_([this]() { run(); }) {}
+    ~PeerWorker()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    int device() const { return device_; }
+    void submit(PeerJob* j)
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            q_.push_back(j);
+            ++outstanding_;
+        }
+        cv_.notify_one();
+    }
+    void quiesce()
+    {
+        std::unique_lock<std::mutex> lock(m_);
+        idle_.wait(lock, [this]() { return outstanding_ == 0; });
+    }
+    int init_error()
+    {
+        std::unique_lock<std::mutex> lock(m_);
+        idle_.wait(lock, [this]() { return started_; });
+        return init_err_;
+    }
+
+  private:
+    struct Inflight
+    {
+        PeerJob* job;
+        int ticket;
+    };
+    int launch(PeerJob* j, unsigned seq, int* ticket)
+    {
+        const size_t bytes = j->count * 32;
+        Workspace& buf = scalars_[seq % PEER_INFLIGHT];
+        BBG_CHECK(buf.ensure(j->batch * bytes));
+        const void* ptrs[4];
+        if (!j->host_src) BBG_CHECK(cudaStreamWaitEvent(stream_, j->ready, 0));
+        for (size_t b = 0; b < j->batch; ++b)
+        {
+            char* dst = (char*)buf.p + b * bytes;
+            const char* src = (const char*)j->src[b] + j->lo * 32;
+            if (j->host_src) BBG_CHECK(bbg_hostcopy::h2d_ring(ring_, dst, src, bytes, stream_));
+            else BBG_CHECK(cudaMemcpyPeerAsync(dst, device_, src, j->src_device, bytes, stream_));
+            ptrs[b] = dst;
+        }
+        int id = -1;
+        for (int i = 0; i < MSM_TICKETS && id < 0; ++i)
+            if (!ctx_.tickets[i].pending) id = i;
+        if (id < 0) return 1007;
+        BBG_CHECK(context_launch(ctx_, id, (int)(seq & 1), ptrs, j->batch, j->d_table, j->count, stream_));
+        *ticket = id;
+        return 0;
+    }
+    void complete(PeerJob* j, int err)
+    {
+        j->err = err;
+        j->done.store(1, std::memory_order_release);
+        std::lock_guard<std::mutex> lock(m_);
+        if (--outstanding_ == 0) idle_.notify_all();
+    }
+    void run()
+    {
+        bbg_prof::thread_muted() = true;
+        int e = (int)cudaSetDevice(device_);
+        if (e == 0) e = (int)cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
+        if (e == 0)
+        {
+            // peer copies go straight over NVLink when the devices can address each other (staged by the driver otherwise)
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, device_, primary_) == cudaSuccess && can) cudaDeviceEnablePeerAccess(primary_, 0);
+            cudaGetLastError();
+        }
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            init_err_ = e;
+            started_ = true;
+        }
+        idle_.notify_all();
+        if (e != 0) return drain();
+        std::vector<Inflight> inflight;
+        unsigned seq = 0;
+        for (;;)
+        {
+            PeerJob* j = nullptr;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                if (inflight.empty()) cv_.wait(lock, [this]() { return stop_ || !q_.empty(); });
+                if (!q_.empty() && inflight.size() < (size_t)PEER_INFLIGHT)
+                {
+                    j = q_.front();
+                    q_.pop_front();
+                }
+                else if (stop_ && inflight.empty())
+                    break;
+            }
+            if (j != nullptr)
+            {
+                int ticket = -1;
+                const int err = launch(j, seq++, &ticket);
+                if (err != 0)
+                {
+                    cudaGetLastError();
+                    complete(j, err);
+                }
+                else
+                    inflight.push_back({ j, ticket });
+                // keep queueing while the launching thread keeps submitting (a prover queues its three wire
+                // commitments back to back); finish the oldest once nothing is waiting
+                std::lock_guard<std::mutex> lock(m_);
+                if (!q_.empty() && inflight.size() < (size_t)PEER_INFLIGHT) continue;
+            }
+            if (!inflight.empty())
+            {
+                Inflight f = inflight.front();
+                inflight.erase(inflight.begin());
+                const int err = context_finish(ctx_, f.ticket, f.job->out);
+                complete(f.job, err);
+            }
+        }
+        cudaStreamSynchronize(stream_);
+        context_release(ctx_);
+        for (Workspace& w : scalars_) w.release();
+        ring_.release();
+        cudaStreamDestroy(stream_);
+    }
+    void drain() // initialisation failed: fail every job handed to us
+    {
+        for (;;)
+        {
+            PeerJob* j = nullptr;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [this]() { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = q_.front();
+                q_.pop_front();
+            }
+            complete(j, init_err_);
+        }
+    }
+    int device_, primary_;
+    std::mutex m_;
+    std::condition_variable cv_, idle_;
+    std::deque<PeerJob*> q_;
+    bool stop_ = false, started_ = false;
+    int init_err_ = 0;
+    int outstanding_ = 0;
+    cudaStream_t stream_ = nullptr;
+    MsmContext ctx_;
+    Workspace scalars_[PEER_INFLIGHT];
+    bbg_hostcopy::Ring ring_;
+    std::thread th_; // last: started once everything above exists
+};
+
+struct MultiState
+{
+    int primary = 0;
+    std::vector<std::unique_ptr<PeerWorker>> peers; // devices 1 .. G-1 of the instance
+    std::vector<Replica> replicas;
+    size_t min_points = (size_t)1 << 15;       // below this one device is faster than the hand-over
+    size_t min_shard = (size_t)1 << 13;
+    double primary_share = 1.0;                // the primary's range relative to an equal split (it also runs the NTTs)
+    std::vector<PeerJob*> free_jobs;
+} g_multi;
+
+PeerJob* job_alloc()
+{
+    if (!g_multi.free_jobs.empty())
+    {
+        PeerJob* j = g_multi.free_jobs.back();
+        g_multi.free_jobs.pop_back();
+        j->done.store(0, std::memory_order_relaxed);
+        j->err = 0;
+        return j;
+    }
+    return new PeerJob();
+}
+void job_free(PeerJob* j) { g_multi.free_jobs.push_back(j); }
+
+const Replica* find_replica(const void* d_table, size_t bytes)
+{
+    for (const Replica& r : g_multi.replicas)
+        if ((const char*)d_table >= r.base0 && (const char*)d_table + bytes <= r.base0 + r.bytes) return &r;
+    return nullptr;
+}
+#endif // !BBG_EMULATE
+} // namespace
+
+size_t msm_launch_count() { return g_msm_launches.load(); }
+
+int msm_multi_device_count()
+{
+#ifndef BBG_EMULATE
+    return 1 + (int)g_multi.peers.size();
+#else
+    return 1;
+#endif
+}
+
+int msm_multi_quiesce()
+{
+#ifndef BBG_EMULATE
+    for (auto& p : g_multi.peers) p->quiesce();
+#endif
+    return 0;
+}
+
+// devices[0] must be the device the library was initialised on (current on the calling thread)
+int msm_multi_init(const int* devices, int count)
+{
+#ifndef BBG_EMULATE
+    if (count < 1 || count > MAX_DEVICES || devices == nullptr) return 1007;
+    if (!g_multi.peers.empty())
+    {
+        // idempotent for the same device list
+        if ((int)g_multi.peers.size() + 1 != count || g_multi.primary != devices[0]) return 1007;
+        for (int i = 1; i < count; ++i)
+            if (g_multi.peers[(size_t)i - 1]->device() != devices[i]) return 1007;
+        return 0;
+    }
+    g_multi.primary = devices[0];
+    if (const char* e = getenv("BBG_MULTI_MIN_POINTS")) g_multi.min_points = (size_t)atol(e) > 0 ? (size_t)atol(e) : 1;
+    if (const char* e = getenv("BBG_MULTI_MIN_SHARD")) g_multi.min_shard = (size_t)atol(e) > 0 ? (size_t)atol(e) : 1;
+    if (const char* e = getenv("BBG_MULTI_PRIMARY_SHARE"))
+    {
+        const double v = atof(e);
+        if (v > 0.0 && v <= 4.0) g_multi.primary_share = v;
+    }
+    for (int i = 1; i < count; ++i)
+    {
+        if (devices[i] == devices[0]) return 1007;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[0], devices[i]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devices[i], 0);
+        cudaGetLastError();
+        g_multi.peers.emplace_back(new PeerWorker(devices[i], devices[0]));
+    }
+    for (auto& p : g_multi.peers)
+    {
+        const int e = p->init_error();
+        if (e != 0)
+        {
+            g_multi.peers.clear();
+            return e;
+        }
+    }
+    return 0;
+#else
+    (void)devices;
+    return count == 1 ? 0 : 1007;
+#endif
+}
+
+// Every device of the instance gets its own copy of a registered point table (8 GB at 2^26 points: HBM is 180 GB), so any
+// sub-range of it can be sharded; copied device to device from the primary's, behind `st`.
+int msm_multi_replicate(const void* d_base0, size_t bytes, cudaStream_t st)
+{
+#ifndef BBG_EMULATE
+    if (g_multi.peers.empty()) return 0;
+    Replica r;
+    r.base0 = (const char*)d_base0;
+    r.bytes = bytes;
+    for (void*& p : r.peer) p = nullptr;
+    int e = 0;
+    for (size_t i = 0; i < g_multi.peers.size() && e == 0; ++i)
+    {
+        const int dev = g_multi.peers[i]->device();
+        e = (int)cudaSetDevice(dev);
+        if (e == 0) e = (int)cudaMalloc(&r.peer[i], bytes ? bytes : 256);
+        cudaSetDevice(g_multi.primary);
+        if (e == 0) e = (int)cudaMemcpyPeerAsync(r.peer[i], dev, d_base0, g_multi.primary, bytes, st);
+    }
+    if (e == 0) e = bbg_rt::sync(st);
+    if (e != 0)
+    {
+        for (size_t i = 0; i < g_multi.peers.size(); ++i)
+        {
+            if (r.peer[i] == nullptr) continue;
+            cudaSetDevice(g_multi.peers[i]->device());
+            cudaFree(r.peer[i]);
+        }
+        cudaSetDevice(g_multi.primary);
+        cudaGetLastError();
+        return e;
+    }
+    g_multi.replicas.push_back(r);
+#else
+    (void)d_base0;
+    (void)bytes;
+    (void)st;
+#endif
+    return 0;
+}
+
+int msm_multi_drop_replica(const void* d_base0)
+{
+#ifndef BBG_EMULATE
+    for (size_t k = 0; k < g_multi.replicas.size(); ++k)
+    {
+        if (g_multi.replicas[k].base0 != (const char*)d_base0) continue;
+        msm_multi_quiesce();
+        for (size_t i = 0; i < g_multi.peers.size(); ++i)
+        {
+            if (g_multi.replicas[k].peer[i] == nullptr) continue;
+            cudaSetDevice(g_multi.peers[i]->device());
+            cudaFree(g_multi.replicas[k].peer[i]);
+        }
+        cudaSetDevice(g_multi.primary);
+        g_multi.replicas.erase(g_multi.replicas.begin() + (long)k);
+        return 0;
+    }
+#else
+    (void)d_base0;
+#endif
+    return 0;
+}
+
+int msm_release_workspace()
+{
+#ifndef BBG_EMULATE
+    msm_multi_quiesce();
+    for (size_t k = 0; k < g_multi.replicas.size(); ++k)
+    {
+        for (size_t i = 0; i < g_multi.peers.size(); ++i)
+        {
+            if (g_multi.replicas[k].peer[i] == nullptr) continue;
+            cudaSetDevice(g_multi.peers[i]->device());
+            cudaFree(g_multi.replicas[k].peer[i]);
+        }
+    }
+    if (!g_multi.peers.empty()) cudaSetDevice(g_multi.primary);
+    g_multi.replicas.clear();
+    g_multi.peers.clear(); // joins the workers, which free their own device memory
+    for (PeerJob* j : g_multi.free_jobs) delete j;
+    g_multi.free_jobs.clear();
+#endif
+    context_release(g_primary);
+    return 0;
+}
+
+bool msm_ticket_pending(int ticket) { return ticket >= 0 && ticket < MSM_TICKETS && g_primary.tickets[ticket].pending; }
+
+// Queue `batch` same-size MSMs on the primary device's stream `st` (and, when the library drives several GPUs and the table
+// is a replicated one, the other point ranges on the other devices); hands back a ticket for msm_finish.
+//   d_scalars   device pointers on the primary device, or — host_scalars — the caller's host buffers: then each device
+//               uploads its own range over its own PCIe link (the primary's copy goes through `staging`, batch * n * 32
+//               bytes of primary-device memory owned by the caller)
+int msm_launch_any(int workspace, const void* const* scalars, bool host_scalars, void* staging, size_t batch, const void* d_table, size_t n,
+                   cudaStream_t st, int* ticket_out)
+{
+    if (workspace < 0 || workspace > 1 || ticket_out == nullptr || batch == 0 || batch > 4) return 1007;
+    int id = -1;
+    for (int i = 0; i < MSM_TICKETS && id < 0; ++i)
+        if (!g_primary.tickets[i].pending) id = i;
+    if (id < 0) return 1007; // too many MSMs in flight
+    MsmTicket& tk = g_primary.tickets[id];
+    tk.peer_count = 0;
+    size_t n0 = n;
+#ifndef BBG_EMULATE
+    const Replica* rep = nullptr;
+    size_t devices = 1;
+    if (!g_multi.peers.empty() && n >= g_multi.min_points && (rep = find_replica(d_table, n * 128)) != nullptr)
+    {
+        devices = 1 + g_multi.peers.size();
+        while (devices > 1 && n / devices < g_multi.min_shard) --devices;
+    }
+    if (devices > 1)
+    {
+        // contiguous ranges; the primary's is scaled by primary_share, the others share the rest equally
+        double share0 = g_multi.primary_share / ((double)(devices - 1) + g_multi.primary_share);
+        n0 = (size_t)((double)n * share0);
+        if (n0 > n) n0 = n;
+        const size_t rest = n - n0;
+        if (!host_scalars)
+        {
+            if (tk.scalars_ready == nullptr) BBG_CHECK(cudaEventCreateWithFlags(&tk.scalars_ready, cudaEventDisableTiming));
+            BBG_CHECK(cudaEventRecord(tk.scalars_ready, st));
+        }
+        const size_t table_off = (size_t)((const char*)d_table - rep->base0);
+        for (size_t g = 1; g < devices; ++g)
+        {
+            const size_t lo = n0 + rest * (g - 1) / (devices - 1), hi = n0 + rest * g / (devices - 1);
+            if (hi == lo) continue;
+            PeerJob* j = job_alloc();
+            for (size_t b = 0; b < batch; ++b) j->src[b] = scalars[b];
+            j->batch = batch;
+            j->lo = lo;
+            j->count = hi - lo;
+            j->host_src = host_scalars;
+            j->src_device = g_multi.primary;
+            j->ready = tk.scalars_ready;
+            j->d_table = (const char*)rep->peer[g - 1] + table_off + lo * 128;
+            tk.peer_jobs[tk.peer_count++] = j;
+            g_multi.peers[g - 1]->submit(j);
+        }
+    }
+#endif
+    const void* dev_ptrs[4];
+    for (size_t b = 0; b < batch; ++b)
+    {
+        if (host_scalars)
+        {
+            char* dst = (char*)staging + b * n0 * 32;
+            if (n0 > 0) BBG_CHECK(bbg_hostcopy::h2d(dst, scalars[b], n0 * 32, st));
+            dev_ptrs[b] = dst;
+        }
+        else
+            dev_ptrs[b] = scalars[b];
+    }
+    const int e = context_launch(g_primary, id, workspace, dev_ptrs, batch, d_table, n0, st);
+    if (e != 0)
+    {
+#ifndef BBG_EMULATE
+        // the peers' shards are already queued: let them finish before reporting the failure
+        for (int k = 0; k < tk.peer_count; ++k)
+        {
+            while (!tk.peer_jobs[k]->done.load(std::memory_order_acquire)) std::this_thread::yield();
+            job_free(tk.peer_jobs[k]);
+        }
+        tk.peer_count = 0;
+#endif
+        return e;
+    }
+    *ticket_out = id;
+    return 0;
+}
+
+int msm_launch(int workspace, const void* const* d_scalars, size_t batch, const void* d_table, size_t n, cudaStream_t st, int* ticket_out)
+{
+    return msm_launch_any(workspace, d_scalars, false, nullptr, batch, d_table, n, st, ticket_out);
+}
+
+// out_xyzz_host: HOST buffer of batch x 16 uint64 (X, Y, ZZ, ZZZ), un-normalised sums
+int msm_finish(int ticket, void* out_xyzz_host)
+{
+    if (ticket < 0 || ticket >= MSM_TICKETS || !g_primary.tickets[ticket].pending) return 1007;
+    MsmTicket& tk = g_primary.tickets[ticket];
+    hostg1::hxyzz sums[4];
+    int e = context_finish(g_primary, ticket, sums);
+#ifndef BBG_EMULATE
+    for (int k = 0; k < tk.peer_count; ++k)
+    {
+        PeerJob* j = tk.peer_jobs[k];
+        while (!j->done.load(std::memory_order_acquire)) std::this_thread::yield();
+        if (e == 0) e = j->err;
+        if (e == 0)
+            for (size_t b = 0; b < tk.batch; ++b) sums[b] = hostg1::add(sums[b], j->out[b]); // scalar_multiplication.cpp:750-765
+        job_free(j);
+    }
+    tk.peer_count = 0;
+#endif
+    if (e != 0) return e;
+    for (size_t b = 0; b < tk.batch; ++b) memcpy((char*)out_xyzz_host + b * sizeof(hostg1::hxyzz), &sums[b], sizeof(hostg1::hxyzz));
     return 0;
 }
 
@@ -901,7 +1420,7 @@ int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* s
     const fe a0 = load_fe(start_mont), d = load_fe(step_mont);
     const size_t runs = (n + GEN_RUN - 1) / GEN_RUN;
     BBG_LAUNCH_NOSYNC(g1_progression_kernel, dim3((unsigned)((runs + 63) / 64)), dim3(64), st, a0, d, (fe*)d_points, n);
-    ++g_msm_launches;
+    g_msm_launches += 1;
     return bbg_rt::last_error();
 }
 
@@ -909,7 +1428,7 @@ int g1_table_from_transcript_device(const void* d_g1_bytes, void* d_table, size_
 {
     if (n == 0) return 0;
     BBG_LAUNCH_NOSYNC(srs_from_transcript_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const uint8_t*)d_g1_bytes, (fe*)d_table, n);
-    ++g_msm_launches;
+    g_msm_launches += 1;
     return bbg_rt::last_error();
 }
 
@@ -917,7 +1436,7 @@ int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cu
 {
     if (n == 0) return 0;
     BBG_LAUNCH_NOSYNC(endo_table_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_points, (fe*)d_table, n);
-    ++g_msm_launches;
+    g_msm_launches += 1;
     return bbg_rt::last_error();
 }
 } // namespace bbg

@@ -116,6 +116,13 @@ inline State& state()
     static State s;
     return s;
 }
+// The stopwatch belongs to the thread that drives the primary device; the per-device worker threads of the multi-GPU MSM
+// (bbg_msm.cu) mute it for themselves.
+inline bool& thread_muted()
+{
+    static thread_local bool muted = false;
+    return muted;
+}
 inline void collect()
 {
 #ifndef BBG_EMULATE
@@ -151,7 +158,7 @@ struct Scope
     cudaStream_t st_;
     cudaEvent_t a_ = nullptr, b_ = nullptr;
     bool live_;
-    Scope(int i, cudaStream_t st) : id_(i), st_(st), live_(state().on)
+    Scope(int i, cudaStream_t st) : id_(i), st_(st), live_(state().on && !thread_muted())
     {
         if (!live_) return;
         cudaEventCreate(&a_);
@@ -170,7 +177,7 @@ struct Scope
 };
 inline void add_host_ms(int i, double ms)
 {
-    if (!state().on) return;
+    if (!state().on || thread_muted()) return;
     state().total_ms[i] += ms;
     state().count[i] += 1;
 }

@@ -21,16 +21,7 @@ namespace barretenberg
 {
 void evaluation_domain::compute_lookup_table()
 {
-    static bool ready = false;
-    int e = 0;
-    if (!ready)
-    {
-        const char* dev = getenv("BBG_DEVICE");
-        e = bbg_init(dev ? atoi(dev) : 0);
-        if (e == 0) bbg_set_auto_srs_cache(1);
-        if (e == 0) bbg_shim::stats().after_init();
-        ready = (e == 0);
-    }
+    int e = bbg_shim::ensure_library();
     bbg_shim::Timer timer("compute_lookup_table");
     roots = (fr::field_t*)(aligned_alloc(32, sizeof(fr::field_t) * size * 2));
     if (e == 0) e = bbg_fr_domain_lookup_table((uint64_t*)roots, (unsigned)log2_size);

@@ -28,16 +28,7 @@ namespace
 void run(barretenberg::fr::field_t* coeffs, const barretenberg::evaluation_domain& domain, int op, const barretenberg::fr::field_t* constant,
          const char* what)
 {
-    static bool ready = false;
-    int e = 0;
-    if (!ready)
-    {
-        const char* dev = getenv("BBG_DEVICE");
-        e = bbg_init(dev ? atoi(dev) : 0);
-        if (e == 0) bbg_set_auto_srs_cache(1);
-        if (e == 0) bbg_shim::stats().after_init();
-        ready = (e == 0);
-    }
+    int e = bbg_shim::ensure_library();
     bbg_shim::Timer timer(what);
     if (e == 0) e = bbg_ntt_fr((uint64_t*)coeffs, (unsigned)domain.log2_size, op, (const uint64_t*)constant);
     if (e != 0)
@@ -73,18 +64,7 @@ void coset_ifft(fr::field_t* coeffs, const evaluation_domain& domain) { run(coef
 // Build the reference file with -Dcompute_lagrange_polynomial_fft=cpu_reference_compute_lagrange_polynomial_fft as well.
 void compute_lagrange_polynomial_fft(fr::field_t* l_1_coefficients, const evaluation_domain& src_domain, const evaluation_domain& target_domain)
 {
-    fr::field_t probe; // run() initialises the library; reuse it through a no-op sized call guard
-    (void)probe;
-    static bool ready = false;
-    int e = 0;
-    if (!ready)
-    {
-        const char* dev = getenv("BBG_DEVICE");
-        e = bbg_init(dev ? atoi(dev) : 0);
-        if (e == 0) bbg_set_auto_srs_cache(1);
-        if (e == 0) bbg_shim::stats().after_init();
-        ready = (e == 0);
-    }
+    int e = bbg_shim::ensure_library();
     bbg_shim::Timer timer("compute_lagrange_polynomial_fft");
     if (e == 0) e = bbg_compute_lagrange_polynomial_fft((uint64_t*)l_1_coefficients, (unsigned)src_domain.log2_size, (unsigned)target_domain.log2_size);
     if (e != 0)
@@ -101,17 +81,7 @@ void compute_lagrange_polynomial_fft(fr::field_t* l_1_coefficients, const evalua
 //   -Dcompute_kate_opening_coefficients=cpu_reference_compute_kate_opening_coefficients
 namespace
 {
-int ensure_library()
-{
-    static bool ready = false;
-    if (ready) return 0;
-    const char* dev = getenv("BBG_DEVICE");
-    int e = bbg_init(dev ? atoi(dev) : 0);
-    if (e == 0) bbg_set_auto_srs_cache(1);
-    if (e == 0) bbg_shim::stats().after_init();
-    ready = (e == 0);
-    return e;
-}
+int ensure_library() { return bbg_shim::ensure_library(); }
 void die(const char* what, int e)
 {
     fprintf(stderr, "bbgpu shim: %s failed: %s (no CPU fallback)\n", what, bbg_error_string(e));

@@ -59,13 +59,7 @@ template <typename Fn> int timed(const char* name, Fn fn)
 
 void init_library()
 {
-    static bool ready = false;
-    if (ready) return;
-    const char* dev = getenv("BBG_DEVICE");
-    check(bbg_init(dev ? atoi(dev) : 0), "bbg_init");
-    bbg_set_auto_srs_cache(1);
-    bbg_shim::stats().after_init();
-    ready = true;
+    check(bbg_shim::ensure_library(), "bbg_init");
 }
 
 // one device-side prover per circuit size, kept for the life of the process (2.9 GB of HBM at n = 2^20)

@@ -29,16 +29,7 @@ ReferenceString::ReferenceString(const size_t num_points)
         precomputed_g2_lines = nullptr;
         return;
     }
-    static bool ready = false;
-    int e = 0;
-    if (!ready)
-    {
-        const char* dev = getenv("BBG_DEVICE");
-        e = bbg_init(dev ? atoi(dev) : 0);
-        if (e == 0) bbg_set_auto_srs_cache(1);
-        if (e == 0) bbg_shim::stats().after_init();
-        ready = (e == 0);
-    }
+    int e = bbg_shim::ensure_library();
     bbg_shim::Timer timer("ReferenceString(n)");
     monomials = (barretenberg::g1::affine_element*)(aligned_alloc(64, sizeof(barretenberg::g1::affine_element) * (2 * degree + 2)));
     precomputed_g2_lines = (barretenberg::pairing::miller_lines*)(aligned_alloc(64, sizeof(barretenberg::pairing::miller_lines) * 2));

@@ -8,8 +8,9 @@
 //   -Dpippenger=cpu_reference_pippenger -Dbatched_scalar_multiplications=cpu_reference_batched_scalar_multiplications
 //   -Dgenerate_pippenger_point_table=cpu_reference_generate_pippenger_point_table
 //   -Dalt_pippenger=cpu_reference_alt_pippenger -Dpippenger_low_memory=cpu_reference_pippenger_low_memory
-// so its other helper symbols (compute_wnaf_state, pippenger_internal, pippenger_precomputed, ...) keep their reference
-// CPU bodies, and add this file for the five names above.  Replace pippenger and
+//   -Dpippenger_precomputed=cpu_reference_pippenger_precomputed
+// (or the objcopy --redefine-sym form of INTEGRATION.md) so its other helper symbols (compute_wnaf_state, pippenger_internal,
+// generate_pippenger_precompute_table, ...) keep their reference CPU bodies, and add this file for the six names above.  Replace pippenger and
 // batched_scalar_multiplications TOGETHER (the reference's batched version calls pippenger from inside an OpenMP
 // region with sub-range pointers, scalar_multiplication.cpp:731-738).
 //
@@ -34,14 +35,8 @@ namespace
 }
 void ensure_init()
 {
-    static bool done = false;
-    if (done) return;
-    const char* dev = getenv("BBG_DEVICE");
-    int e = bbg_init(dev ? atoi(dev) : 0);
+    const int e = bbg_shim::ensure_library();
     if (e != 0) die("bbg_init", e);
-    bbg_set_auto_srs_cache(1);
-    bbg_shim::stats().after_init();
-    done = true;
 }
 static_assert(sizeof(barretenberg::fr::field_t) == 32, "field_t layout");
 static_assert(sizeof(barretenberg::g1::affine_element) == 64, "affine_element layout");
@@ -83,16 +78,38 @@ g1::element pippenger(fr::field_t* scalars, g1::affine_element* points, size_t n
     return out;
 }
 
-// scalar_multiplication.cpp:317-455 (bucket-ordered prototype) and :142-263 (in-place, scalar-mutating variant): the same
-// group element as pippenger, called only by the reference's benchmarks (bench_barretenberg.cpp:487-498).  Forwarded to
-// the same GPU MSM; unlike the reference's pippenger_low_memory the scalars are NOT overwritten.
+// scalar_multiplication.cpp:317-455 (bucket-ordered prototype over the same 2n-entry table): the same group element as
+// pippenger; called by the reference's tests and benchmarks (test_scalar_multiplication.cpp:197-230,
+// bench_barretenberg.cpp:487-498).
 g1::element alt_pippenger(fr::field_t* scalars, g1::affine_element* points, size_t num_initial_points, size_t forced_bucket_width)
 {
     return pippenger(scalars, points, num_initial_points, forced_bucket_width);
 }
+// scalar_multiplication.cpp:142-263: `points` are the n PLAIN points (no endomorphism entries — the reference applies
+// beta on the fly, :222-225), test_scalar_multiplication.cpp:164-195.  Unlike the reference the scalars are NOT overwritten
+// with their non-Montgomery endomorphism halves (:144-147, :171).
 g1::element pippenger_low_memory(fr::field_t* scalars, g1::affine_element* points, size_t num_points)
 {
-    return pippenger(scalars, points, num_points, 0);
+    ensure_init();
+    bbg_shim::Timer timer("pippenger_low_memory");
+    g1::element out;
+    int e = bbg_msm_g1_points((const uint64_t*)scalars, (const uint64_t*)points, num_points, (uint64_t*)&out);
+    if (e != 0) die("pippenger_low_memory", e);
+    return out;
+}
+// scalar_multiplication.cpp:478-488: round_points[r] = 2^((bits + 1)(num_rounds - 1 - r)) P, the last entry being the n
+// plain points themselves (:120-124).  The sum does not depend on how the windows are laid out, so the GPU MSM runs on
+// that last entry; the pre-doubled tables of generate_pippenger_precompute_table (kept as the reference's CPU body) are
+// a CPU-side device to save doublings and are not read.
+g1::element pippenger_precomputed(fr::field_t* scalars, const std::vector<g1::affine_element*>& round_points, const size_t num_initial_points)
+{
+    ensure_init();
+    bbg_shim::Timer timer("pippenger_precomputed");
+    g1::element out;
+    if (round_points.empty()) die("pippenger_precomputed (no round points)", BBG_E_BAD_ARGUMENT);
+    int e = bbg_msm_g1_points((const uint64_t*)scalars, (const uint64_t*)round_points.back(), num_initial_points, (uint64_t*)&out);
+    if (e != 0) die("pippenger_precomputed", e);
+    return out;
 }
 
 // scalar_multiplication.cpp:650-772: writes only mul_state[i].output, normalised

@@ -77,6 +77,32 @@ inline Stats& stats()
     static Stats s;
     return s;
 }
+// One place where every shim brings the library up (0 on success, the bbgpu error otherwise; idempotent):
+//   BBG_DEVICE=d          primary CUDA device (default 0)
+//   BBG_NUM_GPUS=g        drive g GPUs of the box, devices d .. d+g-1: MSMs over the SRS are cut into point ranges, one per
+//                         device (bbg_init_multi; the reference's callers get all cores the same way)
+//   BBG_HOST_REGISTER=0   do not page-lock long-lived caller buffers in place (on by default in the shims; a prover
+//                         linked with -Wl,--wrap=free gets host_buffer_free_wrap.cpp's release hook)
+inline int ensure_library()
+{
+    static int state = -1; // -1 not tried
+    if (state == 0) return 0;
+    const char* dev = getenv("BBG_DEVICE");
+    const char* gpus = getenv("BBG_NUM_GPUS");
+    const int first = dev ? atoi(dev) : 0;
+    int count = gpus ? atoi(gpus) : 1;
+    if (count < 1) count = 1;
+    if (count > 16) count = 16;
+    int list[16];
+    for (int i = 0; i < count; ++i) list[i] = first + i;
+    int e = count > 1 ? bbg_init_multi(list, count) : bbg_init(first);
+    if (e == 0) e = bbg_set_auto_srs_cache(1);
+    const char* reg = getenv("BBG_HOST_REGISTER");
+    if (e == 0 && !(reg != nullptr && reg[0] == '0')) e = bbg_set_host_register_cache(1);
+    if (e == 0) stats().after_init();
+    state = e;
+    return e;
+}
 struct Timer
 {
     const char* name_;

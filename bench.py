@@ -6,13 +6,20 @@ Workload ("step"), synthetic and seeded:
     configs[1]  the NTT batch of 8 prover polynomials: fft and ifft at n = 2^20 and coset_fft at 4n = 2^22
                 (low n coefficients non-zero, the prover's pattern — prover.cpp:418-425).
 `value` = milliseconds per step with every input resident in HBM (time-like: lower is better);
-`e2e`   = the same step through the host-buffer C ABI the reference's signatures map to (pinned host buffers,
-          H2D/D2H inside the timed region, SRS points registered once like ReferenceString does).
+`e2e`   = the same step through the calls the reference's signatures really make (polynomial_arithmetic.hpp:28-39,
+          scalar_multiplication.hpp:60-61): ONE blocking bbg_msm_g1 and 24 single-polynomial bbg_ntt_fr calls on plain
+          aligned_alloc (pageable) host memory, H2D/D2H inside the timed region, SRS points registered once like
+          ReferenceString does, long-lived buffers page-locked in place by the library on their second sighting
+          (bbg_set_host_register_cache, what the shims switch on);
+`e2e_pinned` = the batched / launched form on caller-pinned buffers (bbg_msm_g1_launch + 3 x bbg_ntt_fr_batched), an API
+          extension the reference's signatures do not reach — reported next to it, not as the headline.
+`msm_2p26` = BASELINE configs[3]: one MSM of 2^26 synthetic points sharded by point range over the N ranks.
 With --gpus N (torchrun) the MSM is sharded by point range and the NTT batch by polynomial (configs[2]): total work
 fixed => "scaling": "strong"; per-rank device time, max over ranks.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified sources compiled
-by oracle/Makefile; multithreaded x86-asm path) on the same workload on the box's host cores.
+by oracle/Makefile; multithreaded x86-asm path) on the same workload — all 8 polynomials of every transform — on the
+box's host cores (every core the process may run on, whatever OMP_NUM_THREADS a launcher exported).
 """
 import argparse
 import json
@@ -102,7 +109,7 @@ def workload_config(args, world):
         "msm_points": 1 << args.log_n,
         "ntt_batch": BATCH,
         "ntt_sizes": [1 << args.log_n, 1 << args.log_n, 1 << (args.log_n + 2)],
-        "streams": "the MSM runs on a second stream beside the NTT batch (device-resident step and e2e: bbg_msm_g1_launch / _finish around the three bbg_ntt_fr_batched calls)",
+        "streams": "device-resident step: the MSM runs on a second stream beside the NTT batch; e2e: sequential blocking calls, as the reference's signatures are",
         "sharding": "msm by point range, ntt batch by polynomial (no data-path collective; %d-rank gather of 128-byte partials)" % world,
         "untimed_steps": "warm-up W + 10 more while the clock sampler spins up",
         "l2": "inputs larger than L2 (polynomial batch %d MiB, point table %d MiB), no flush" % (
@@ -139,9 +146,14 @@ class ReferenceCpu:
         self.kind = "reference"
         if self.r is None:
             raise RuntimeError("oracle/_ref/libbb_ref.so is not built (run __graft_entry__.build() where /root/reference exists)")
-        cores = os.cpu_count() or 1
+        # every core this process may run on — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its ranks,
+        # which left the round-1 reference arm on one thread at N = 2, 4, 8
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
         t = 1
-        while t * 2 <= min(cores, self.r.ref_omp_threads() if self.r.ref_omp_threads() > 0 else cores):
+        while t * 2 <= cores:
             t *= 2
         # evaluation_domain silently needs a power-of-two thread count (SURVEY.md §5 hazard)
         self.r.ref_set_omp_threads(t)
@@ -167,16 +179,21 @@ class ReferenceCpu:
         # same point family as the GPU arm; built with the reference's own group code
         r.ref_g1_arith_progression(H.ptr(S.to_limbs(S.mont(0x1234567))), H.ptr(S.to_limbs(S.mont(0x89ABC))), H.ptr(pts), n)
         r.ref_generate_pippenger_point_table(H.ptr(pts), H.ptr(t.reshape(2 * n, 8)), n)
-        self.p_ptr, p = self._alloc(32 * n)
-        p.reshape(n, 4)[:] = S.random_field(2001, n)
-        self.q_ptr, q = self._alloc(32 * 4 * n)
-        q[:] = 0
-        q.reshape(4 * n, 4)[:n] = S.random_field(3001, n)
+        self.p_ptrs, self.q_ptrs = [], []
+        for j in range(BATCH):  # the same 8 + 8 polynomials as the GPU arm
+            ptr_, p = self._alloc(32 * n)
+            p.reshape(n, 4)[:] = S.random_field(2001 + j, n)
+            self.p_ptrs.append(ptr_)
+            ptr_, q = self._alloc(32 * 4 * n)
+            q[:] = 0
+            q.reshape(4 * n, 4)[:n] = S.random_field(3001 + j, n)
+            self.q_ptrs.append(ptr_)
         self.dom_n = r.ref_domain_new(n)
         self.dom_4n = r.ref_domain_new(4 * n)
 
     def step_sample(self):
-        """MSM in full; ONE of the 8 polynomials per NTT op, scaled by 8.  Returns (estimated ms per step, parts)."""
+        """The whole step, nothing extrapolated: the MSM and all 8 polynomials of every transform.
+        Returns (ms per step, parts)."""
         import ctypes as C
 
         r = self.r
@@ -185,22 +202,25 @@ class ReferenceCpu:
         t0 = time.perf_counter()
         r.ref_batched_scalar_multiplications(ptrs, self.t_ptr, self.n, 1, self.H.ptr(out))
         t1 = time.perf_counter()
-        r.ref_ntt(self.dom_n, 0, self.p_ptr, None)
+        for p in self.p_ptrs:
+            r.ref_ntt(self.dom_n, 0, p, None)
         t2 = time.perf_counter()
-        r.ref_ntt(self.dom_n, 1, self.p_ptr, None)
+        for p in self.p_ptrs:
+            r.ref_ntt(self.dom_n, 1, p, None)
         t3 = time.perf_counter()
-        r.ref_ntt(self.dom_4n, 2, self.q_ptr, None)
+        for q in self.q_ptrs:
+            r.ref_ntt(self.dom_4n, 2, q, None)
         t4 = time.perf_counter()
-        parts = {"msm_ms": (t1 - t0) * 1e3, "fft_ms": (t2 - t1) * 1e3, "ifft_ms": (t3 - t2) * 1e3, "coset_fft_4n_ms": (t4 - t3) * 1e3}
-        est = parts["msm_ms"] + BATCH * (parts["fft_ms"] + parts["ifft_ms"] + parts["coset_fft_4n_ms"])
-        return est, parts
+        parts = {"msm_ms": (t1 - t0) * 1e3, "fft_x%d_ms" % BATCH: (t2 - t1) * 1e3, "ifft_x%d_ms" % BATCH: (t3 - t2) * 1e3,
+                 "coset_fft_4n_x%d_ms" % BATCH: (t4 - t3) * 1e3}
+        return (t4 - t0) * 1e3, parts
 
     def describe(self):
-        return ("batched_scalar_multiplications(1 x 2^%d) in full + 1 of %d polynomials per NTT op (fft, ifft 2^%d; coset_fft 2^%d) "
-                "scaled x%d; OMP threads = %d" % (self.log_n, BATCH, self.log_n, self.log_n + 2, BATCH, self.threads))
+        return ("the whole step, measured: batched_scalar_multiplications(1 x 2^%d) + %d polynomials x (fft, ifft 2^%d; coset_fft 2^%d); "
+                "OMP threads = %d" % (self.log_n, BATCH, self.log_n, self.log_n + 2, self.threads))
 
 
-def prove_leg(log_gates, with_cpu):
+def prove_leg(log_gates, with_cpu, num_gpus=1):
     """BASELINE configs[4] next to the step metric: the reference's waffle StandardComposer prover, prebuilt by
     tests/cpp/Makefile (build/ travels to the GPU box), once with Prover::construct_proof on the GPU (HBM-resident rounds)
     and once all-CPU; proofs compared field for field.  Returns None when the binaries are not there."""
@@ -229,19 +249,88 @@ def prove_leg(log_gates, with_cpu):
             raise RuntimeError("%s failed: %s" % (binary, (out.stderr or out.stdout)[-300:]))
         return json.loads(out.stdout.strip().splitlines()[-1])
 
-    gpu = run("prover_gpu", 5)
-    cold = run("prover_gpu", 3, {"BBG_PLONK_KEY_CACHE": "0"})
+    multi = {"BBG_NUM_GPUS": str(num_gpus)} if num_gpus > 1 else {}
+    gpu = run("prover_gpu", 5, multi)
+    cold = run("prover_gpu", 3, dict(multi, BBG_PLONK_KEY_CACHE="0"))
     res = {"workload": "configs[4]: waffle StandardComposer prove, n = 2^%d (bench_plonk.cpp:25-37 circuit, seeded witnesses, synthetic SRS)" % log_gates,
-           "gpu_prove_ms": gpu["prove_ms_best"], "gpu_prove_ms_cold_key": cold["prove_ms_best"], "gpu_prove_ms_first": gpu["prove_ms_first"],
-           "gpu_verified": gpu["verified"] and cold["verified"],
-           "note": "gpu_prove_ms: circuit constants (permutation, selectors) found unchanged on the device by their fingerprint, witness uploaded; "
-                   "cold_key: constants uploaded and transformed every proof, as the reference does",
+           "gpu_prove_ms": cold["prove_ms_best"], "gpu_prove_ms_warm_key": gpu["prove_ms_best"], "gpu_prove_ms_first": gpu["prove_ms_first"],
+           "gpus": num_gpus, "gpu_verified": gpu["verified"] and cold["verified"],
+           "note": "gpu_prove_ms (the headline): circuit constants (permutation, selectors) uploaded and transformed every proof, the work the "
+                   "reference does per proof; warm_key: constants found unchanged on the device by their fingerprint, only the witness "
+                   "uploaded; first: first proof of the process (tables, workspaces, SRS upload); gpus > 1: commitments cut into point "
+                   "ranges over the devices inside libbbgpu.so (BBG_NUM_GPUS -> bbg_init_multi)",
            "path": "Prover::construct_proof -> shim/prover_gpu.cpp -> bbg_plonk_* (witness, mappings and selectors uploaded from pageable host memory every proof)"}
     if with_cpu:
         cpu = run("prover_cpu", 1)
         res.update({"cpu_reference_prove_ms": cpu["prove_ms_best"], "cpu_threads": threads, "cpu_verified": cpu["verified"],
-                    "proofs_identical": all(cpu["proof"][k] == gpu["proof"][k] for k in cpu["proof"])})
+                    "proofs_identical": all(cpu["proof"][k] == gpu["proof"][k] and cpu["proof"][k] == cold["proof"][k] for k in cpu["proof"])})
+    else:
+        res["proofs_identical_warm_vs_cold"] = all(gpu["proof"][k] == cold["proof"][k] for k in gpu["proof"])
     return res
+
+
+def msm_large_leg(lib, parallel, S, rank, world, log_big, barrier, max_over_ranks, fold, steps=3, warmup=1):
+    """BASELINE configs[3]: one MSM of 2^log_big synthetic points ((a0 + i d) G, generated on the device), each rank a
+    contiguous point range, partial sums gathered (128 bytes per rank) and folded on the host.  Scalars: independent seeded
+    blocks of 2^20.  Gate: the result must equal [(sum_i k_i (a0 + i d)) mod r] G computed as a 1-point MSM; every rank adds
+    up its own range's share of that dot product."""
+    n = 1 << log_big
+    lo, hi = parallel.shard_range(n, rank, world)
+    n_loc = hi - lo
+    a0, d = 0x7654321, 0xABCDE
+    BLK = 1 << 20
+    t_setup = time.perf_counter()
+    d_points = lib.dev_alloc(max(n_loc, 1) * 64)
+    d_table = lib.dev_alloc(max(n_loc, 1) * 128)
+    lib.generate_multiples_dev(S.to_limbs(S.mont(a0 + lo * d)), S.to_limbs(S.mont(d)), d_points, n_loc)
+    lib.generate_pippenger_point_table_dev(d_points, d_table, n_loc)
+    lib.sync()
+    lib.dev_free(d_points)
+    d_scalars = lib.dev_alloc(max(n_loc, 1) * 32)
+    share = 0
+    pos = lo
+    while pos < hi:  # block by block: never more than 32 MiB of scalars on the host
+        blk = pos // BLK
+        chunk = S.random_field(7000 + blk, min(BLK, n))
+        s_, e_ = pos - blk * BLK, min(hi - blk * BLK, chunk.shape[0])
+        piece = np.ascontiguousarray(chunk[s_:e_])
+        lib.h2d(d_scalars + (pos - lo) * 32, piece)
+        share = (share + S.dot_mod_r(piece, a0 + pos * d, d)) % S.FR_MODULUS
+        pos += e_ - s_
+    setup_s = time.perf_counter() - t_setup
+
+    def run():
+        return fold(lib.msm_partial_dev(d_scalars, d_table, n_loc))
+
+    res = None
+    for _ in range(warmup):
+        res = run()
+    times = []
+    for _ in range(steps):
+        barrier()
+        t0 = time.perf_counter()
+        res = run()
+        times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+    # closed form: gather every rank's share of the dot product (as an Fr element through the same partial gather)
+    share_limbs = np.zeros(16, dtype=np.uint64)
+    share_limbs[:4] = S.to_limbs(share)
+    shares = parallel.gather_partials(share_limbs, world, device="cuda" if world > 1 else None)
+    ok = None
+    if rank == 0:
+        total = sum(S.from_limbs(shares[r][:4]) for r in range(world)) % S.FR_MODULUS
+        d_g, d_gt, d_s1 = lib.dev_alloc(64), lib.dev_alloc(128), lib.dev_alloc(32)
+        lib.generate_multiples_dev(S.to_limbs(S.mont(1)), S.to_limbs(0), d_g, 1)
+        lib.generate_pippenger_point_table_dev(d_g, d_gt, 1)
+        lib.h2d(d_s1, S.to_limbs(S.mont(total)).reshape(1, 4))
+        expect = lib.msm_dev(d_s1, d_gt, 1)
+        ok = bool((res == expect).all())
+        for p_ in (d_g, d_gt, d_s1):
+            lib.dev_free(p_)
+    lib.dev_free(d_scalars)
+    lib.dev_free(d_table)
+    return {"workload": "configs[3]: MSM 2^%d synthetic points (a0 + i d) G, uniform scalars, point ranges over %d rank(s)" % (log_big, world),
+            "ms": min(times), "ms_all": times, "n_gpus": world, "points_per_rank": n_loc, "closed_form_ok": ok, "setup_s": setup_s,
+            "timing": "wall clock around launch + host fold + gather, barrier before, max over ranks, best of %d after %d warm-up" % (steps, warmup)}
 
 
 def run_reference(args, rank, world):
@@ -252,7 +341,7 @@ def run_reference(args, rank, world):
     except Exception as e:  # oracle/_ref missing
         print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0]}))
         return
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         ref.step_sample()
     vals, parts = [], None
     for _ in range(args.steps):
@@ -261,7 +350,7 @@ def run_reference(args, rank, world):
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": "ms_per_step_msm2p%d_plus_ntt_batch" % args.log_n, "value": value, "unit": "ms", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": value, "higher_is_better": False, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64x4 Montgomery (x86-64 MULX/ADX asm)", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": "ms", "cores": ref.threads, "kind": ref.kind, "sample": ref.describe(), "parts_ms": parts},
@@ -288,6 +377,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = bb.Library(device=local_rank)
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
 
     def barrier():
         lib.sync()
@@ -339,6 +429,31 @@ def run_b200(args, rank, local_rank, world):
     lib.h2d(d_poly_n, h_poly_n)
     lib.h2d(d_poly_4n, h_poly_4n)
 
+    # ---- the same inputs in plain aligned_alloc memory: what the reference's callers hand over ---------------------------
+    import ctypes as C
+
+    libc = C.CDLL(None)
+    libc.aligned_alloc.restype = C.c_void_p
+    libc.aligned_alloc.argtypes = [C.c_size_t, C.c_size_t]
+
+    def pageable(shape):
+        nbytes = int(np.prod(shape)) * 8
+        ptr_ = libc.aligned_alloc(64, (nbytes + 63) // 64 * 64)
+        if not ptr_:
+            raise MemoryError("aligned_alloc(%d)" % nbytes)
+        return np.ctypeslib.as_array((C.c_uint64 * (nbytes // 8)).from_address(ptr_)).reshape(shape)
+
+    pg_scalars = pageable((max(n_loc, 1), 4))
+    pg_scalars[:n_loc] = scalars_all[lo:hi]
+    pg_table = pageable((2 * max(n_loc, 1), 8))
+    pg_table[:] = h_table
+    lib.srs_register(pg_table)  # ReferenceString::monomials: uploaded once, like the shim does
+    pg_poly_n = [pageable((n, 4)) for _ in range(P)]
+    pg_poly_4n = [pageable((4 * n, 4)) for _ in range(P)]
+    for j in range(P):
+        pg_poly_n[j][:] = h_poly_n[j]
+        pg_poly_4n[j][:] = h_poly_4n[j]
+
     def fold(partial16):
         """Tiny NCCL all-gather of the 128-byte partials over NVLink, then the host-side fold."""
         return lib.fold_partials(parallel.gather_partials(partial16, world, device="cuda"))
@@ -362,7 +477,22 @@ def run_b200(args, rank, local_rank, world):
         return fold(part)
 
     def step_host():
-        """The call a user of the reference signatures makes: host buffers in, host buffers out."""
+        """The calls the reference's signatures make (pippenger: scalar_multiplication.hpp:60-61; fft / ifft / coset_fft:
+        polynomial_arithmetic.hpp:28-39): blocking, one polynomial per call, pageable buffers in and out."""
+        if n_loc:
+            part = parallel.normalized_to_partial(lib.msm(pg_scalars[:n_loc], pg_table, n_loc))  # bbg_msm_g1
+        else:
+            part = np.zeros(16, dtype=np.uint64)
+        for j in range(P):
+            lib.ntt("fft", pg_poly_n[j])  # bbg_ntt_fr
+        for j in range(P):
+            lib.ntt("ifft", pg_poly_n[j])
+        for j in range(P):
+            lib.ntt("coset_fft", pg_poly_4n[j])
+        return fold(part)
+
+    def step_host_pinned():
+        """API extension beyond the reference's signatures: caller-pinned buffers, batched transforms, launched MSM."""
         ticket = lib.msm_launch(h_scalars[:n_loc], h_table, n_loc) if n_loc else None  # bbg_msm_g1_launch: beside the NTT copies
         if P:
             lib.ntt("fft", h_poly_n[:P])
@@ -440,6 +570,13 @@ def run_b200(args, rank, local_rank, world):
         lib.msm_partial_dev(d_scalars, d_table, n_loc)
 
     ops_ms = {"msm_2p%d" % log_n: time_op(msm_only, host_finish=True)}
+    if n_loc >= 1024:
+        # degenerate digit distribution (constant polynomials do occur in a prover): every scalar equal, so each window's
+        # entries fall into one bucket — the block-reduction fix-up path
+        d_const = lib.dev_alloc(n_loc * 32)
+        lib.h2d(d_const, np.ascontiguousarray(np.broadcast_to(scalars_all[lo], (n_loc, 4))))
+        ops_ms["msm_2p%d_constant_scalars" % log_n] = time_op(lambda: lib.msm_partial_dev(d_const, d_table, n_loc), host_finish=True)
+        lib.dev_free(d_const)
     if P:
         ops_ms["fft_2p%d_per_poly" % log_n] = time_op(lambda: lib.ntt_dev("fft", d_poly_n, log_n, batch=P)) / P
         ops_ms["ifft_2p%d_per_poly" % log_n] = time_op(lambda: lib.ntt_dev("ifft", d_poly_n, log_n, batch=P)) / P
@@ -455,18 +592,38 @@ def run_b200(args, rank, local_rank, world):
         return
 
     # ---- e2e through the host-buffer ABI ----------------------------------------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        step_host()
-    barrier()
-    lib.timer_start()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        step_host()
-    ev_ms = lib.timer_stop()
-    e2e_ms = max_over_ranks(max(ev_ms, (time.perf_counter() - t0) * 1e3)) / e2e_steps
+    def time_host(step, warm):
+        for _ in range(warm):
+            step()
+        barrier()
+        lib.timer_start()
+        t0 = time.perf_counter()
+        steps = max(1, min(args.steps, 5))
+        for _ in range(steps):
+            step()
+        ev_ms = lib.timer_stop()
+        return max_over_ranks(max(ev_ms, (time.perf_counter() - t0) * 1e3)) / steps
+
+    # the reference-signature calls: first on cold buffers (every call staged through the pinned ring: what a caller whose
+    # buffers never repeat would see), then with the registration cache on (second sighting page-locks a buffer in place,
+    # so three warm-up steps: stage, register, steady state)
+    e2e_staged_ms = time_host(step_host, 1)
+    lib.set_host_register_cache(True)
+    e2e_ms = time_host(step_host, max(3, min(args.warmup, 5)))
+    for a in [pg_scalars] + pg_poly_n + pg_poly_4n:
+        lib.host_buffer_forget(a)
+    lib.set_host_register_cache(False)
+    e2e_pinned_ms = time_host(step_host_pinned, min(args.warmup, 2))
     h2d_bytes = n_loc * 32 + P * (2 * n * 32 + 4 * n * 32)
     d2h_bytes = 96 + P * (2 * n * 32 + 4 * n * 32)
+    # the pageable polynomials went through fft then ifft every step: still the inputs
+    if P and not (pg_poly_n[0] == S.random_field(2001 + polys[0], n)).all():
+        raise SystemExit("bench.py: e2e parity gate failed (ifft(fft(x)) != x through the pageable host path)")
+
+    # ---- BASELINE configs[3]: MSM 2^26 synthetic points, sharded by point range over the ranks ---------------------------
+    msm_big = None
+    if not args.no_msm26:
+        msm_big = msm_large_leg(lib, parallel, S, rank, world, args.log_big, barrier, max_over_ranks, fold)
 
     # ---- kernel attribution (separate untimed pass) + measured integer-pipe peak ------------------------------
     lib.profile_enable(True)
@@ -535,20 +692,39 @@ def run_b200(args, rank, local_rank, world):
             "dtype": "u32x8 Montgomery (bn254 Fq/Fr)", "data": "synthetic", "config": workload_config(args, world),
             "components_ms": ops_ms, "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                    "note": "host-buffer C ABI (bbg_msm_g1_launch / _finish on a registered SRS around 3 x bbg_ntt_fr_batched), pinned host memory"},
+                    "note": "the reference-signature calls: 1 x bbg_msm_g1 (blocking, registered SRS) + %d x single-polynomial bbg_ntt_fr on "
+                            "aligned_alloc (pageable) buffers; long-lived buffers page-locked in place by the library on their second "
+                            "sighting (bbg_set_host_register_cache, as the shims do)" % (3 * P),
+                    "staged_first_sighting_ms": e2e_staged_ms},
+            "e2e_pinned": {"value": e2e_pinned_ms, "unit": "ms", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                           "note": "API extension, not the reference's call: caller-pinned buffers, bbg_msm_g1_launch / _finish around 3 x bbg_ntt_fr_batched"},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kern, "imad_peaks": peaks,
             "algorithmic_gmac": {k: v / 1e9 for k, v in macs.items()},
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        if world == 1 and not args.no_prove:
+        if msm_big is not None:
+            msm_big["frac_of_imad_peak"] = (algorithmic_macs(args.log_big)["msm"] / (msm_big["ms"] * 1e-3)) / (mac_peak * world) if msm_big.get("ms") else None
+            line["msm_2p%d" % args.log_big] = msm_big
+        if not args.no_prove:
+            # configs[4].  N = 1: one GPU behind the shim (+ the all-CPU reference prover beside it).  N > 1 (torchrun): rank 0
+            # runs the same binary with BBG_NUM_GPUS = N — one process driving N devices through bbg_init_multi — while the
+            # other ranks idle at the barrier below.
             try:
-                prove = prove_leg(log_n, with_cpu=not args.no_cpu_baseline)
+                prove = prove_leg(log_n, with_cpu=(world == 1 and not args.no_cpu_baseline), num_gpus=world)
             except Exception as e:  # noqa: BLE001
                 prove = {"unavailable": str(e).splitlines()[0][:200]}
             if prove is not None:
                 line["prove"] = prove
         print(json.dumps(line))
+        if store is not None:
+            store.set("bbg_bench_rank0_done", "1")
+    elif store is not None:
+        # wait on the rendezvous store, not in an NCCL barrier: a collective would keep a spinning kernel on this GPU while
+        # rank 0's prover leg drives it through bbg_init_multi
+        import datetime
+
+        store.wait(["bbg_bench_rank0_done"], datetime.timedelta(minutes=30))
     barrier()
     if world > 1:
         dist.destroy_process_group()
@@ -563,6 +739,8 @@ def main():
     ap.add_argument("--log-n", type=int, default=LOG_N, help="log2 of the MSM / NTT size (BASELINE: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prove", action="store_true", help="skip the full-prover leg (BASELINE configs[4])")
+    ap.add_argument("--no-msm26", action="store_true", help="skip the 2^26-point MSM leg (BASELINE configs[3])")
+    ap.add_argument("--log-big", type=int, default=26, help="log2 of the large synthetic MSM (BASELINE configs[3]: 26)")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e, microbench and CPU-baseline legs (short runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -56,6 +56,17 @@ enum bbg_ntt_op
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int bbg_init(int device);            /* select device, create the work stream; idempotent */
+/* One process, several GPUs of one box (the reference splits an MSM into point ranges inside
+ * batched_scalar_multiplications, scalar_multiplication.cpp:688-761, so its caller gets every core without asking).
+ * devices[0] becomes the primary device — everything bbg_init(devices[0]) gives, every NTT, every device pointer of this
+ * API lives there — and each further device gets a worker thread, a stream and its own copy of every registered point
+ * table.  From then on an MSM of >= 2^15 points over a registered / cached table (bbg_msm_g1, _batched, _launch, the
+ * *_dev forms when d_table points into such a table, and the commitments of the resident prover) is cut into contiguous
+ * point ranges, one per device, exactly as :703-728 cuts it per thread; the per-device sums are added on the calling
+ * thread (:750-765).  Results are the same group elements, hence bit-identical outputs.  May be called after bbg_init on
+ * the same primary device; idempotent for the same list.  BBG_MULTI_MIN_POINTS / BBG_MULTI_PRIMARY_SHARE tune the split. */
+int bbg_init_multi(const int* devices, int count);
+int bbg_device_count(void);          /* devices driven by this instance (1 after bbg_init) */
 int bbg_shutdown(void);              /* free tables, caches, workspace */
 int bbg_set_stream(void* cuda_stream); /* run on a caller-owned cudaStream_t (e.g. torch's current stream) */
 const char* bbg_error_string(int code);
@@ -91,6 +102,10 @@ int bbg_srs_unregister(const uint64_t* table_2n);
 int bbg_set_auto_srs_cache(int enable);
 /* sum_i scalars[i] * P_i over table entries points_table[0 .. 2n); out_xyz = 12 limbs, normalised */
 int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, uint64_t out_xyz[12]);
+/* the same sum over n PLAIN affine points (64 bytes each, no endomorphism entries): what pippenger_low_memory and
+ * pippenger_precomputed are handed (scalar_multiplication.hpp:52, :79-81; .cpp:142-263, :478-573 apply the endomorphism on
+ * the fly); the 2n-entry table is built on the device.  Unlike pippenger_low_memory the scalars are not overwritten. */
+int bbg_msm_g1_points(const uint64_t* scalars, const uint64_t* points_n, size_t n, uint64_t out_xyz[12]);
 /* `batches` MSMs of the same size n (multiplication_state[], scalar_multiplication.hpp:88-94) */
 int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* points_tables, size_t n, size_t batches,
                        uint64_t* out_xyz /* batches x 12 */);
@@ -212,6 +227,30 @@ int bbg_plonk_round_linearise(bbg_plonk_prover* p, const uint64_t* scalars, cons
  * out = PI_Z, PI_Z_OMEGA (2 x 12) */
 int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, const uint64_t beta_inv[4], const uint64_t zeta[4],
                              const uint64_t zeta_omega[4], const uint64_t* wire_shift_terms, const uint64_t* selector_terms, uint64_t* out_xyz);
+
+/* ---- caller-owned host buffers -------------------------------------------------------------------
+ * The reference's callers pass pageable memory (aligned_alloc, types.hpp:25) and reuse the same long-lived buffers call
+ * after call (barretenberg::polynomial members, ReferenceString::monomials).  With the cache on, a pageable buffer of
+ * >= 1 MiB seen a second time behind the same address and size is page-locked in place (cudaHostRegister) and from then on
+ * copied at the pinned rate, without the staging memcpy.  Contract: hand a buffer to bbg_host_buffer_forget BEFORE
+ * freeing it (the driver keeps DMA mappings of the physical pages; an address range unmapped and mapped again would be
+ * read through the old ones).  shim/host_buffer_free_wrap.cpp does that for a prover linked with -Wl,--wrap=free.
+ * Off by default; BBG_HOST_REGISTER_MAX_MB caps the page-locked total (default 16384). */
+int bbg_set_host_register_cache(int enable);
+int bbg_host_buffer_forget(const void* host_ptr); /* any pointer into the buffer; unknown pointers are ignored; thread-safe */
+
+/* ---- device self test (tests only; bbg_selftest.cu) --------------------------------------------------
+ * Element-wise field / group primitives on the device, host buffers in and out, for limb-for-limb comparison with the
+ * reference's known-answer vectors (test/test_fq.cpp:51-133, test_fr.cpp:51-88, test_g1.cpp:41-122) and the oracle.
+ * field: 0 = Fq, 1 = Fr.  op: 0 mul (coarse: (ab + Mp) / 2^256), 1 sqr (coarse), 2 mul by a constant (canonical),
+ * 3 add (coarse), 4 sub (coarse), 5 reduce_once, 6 neg (lazy range), 7 to_montgomery_form, 8 from_montgomery_form,
+ * 9 invert, 10 a - b + 2p uncorrected, 11 mul (canonical), 12 mul by a constant (raw, must lie in [0, 2p)).
+ * b may be NULL for the unary ops. */
+int bbg_field_selftest(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count);
+/* p, q, out: affine points (64 bytes).  op: 0 mixed add P + Q, 1 2P + 2Q through the general addition, 2 4P through two
+ * doublings, 3 ((inf + P) + Q) + P by mixed additions, 4 general addition P + Q, 5 the endomorphism table entry
+ * (beta x, -y), 6 2P from the affine image. */
+int bbg_g1_selftest(int op, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t count);
 
 /* ---- device memory helpers (tests, bench, device-resident callers) ---------------------------- */
 int bbg_dev_alloc(void** d_ptr, size_t bytes);

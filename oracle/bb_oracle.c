@@ -242,6 +242,43 @@ void orc_mul_n(int w, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t 
 {
     for (size_t i = 0; i < n; ++i) f_mul(&FP[w], a + 4 * i, b + 4 * i, r + 4 * i);
 }
+/* Element-wise batches for the device self test (tests/test_field_selftest.py); op codes = bbg_field_selftest's
+ * (include/bbgpu.h).  Ops whose device result is only defined as a residue (2, 6, 12) are returned canonical here. */
+void orc_field_op_n(int w, int op, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n)
+{
+    const field_params* f = &FP[w];
+    for (size_t i = 0; i < n; ++i)
+    {
+        const uint64_t* x = a + 4 * i;
+        const uint64_t* y = b ? b + 4 * i : NULL;
+        uint64_t* o = r + 4 * i;
+        uint64_t t[4];
+        switch (op)
+        {
+        case 0: f_mul_coarse(f, x, y, o); break;
+        case 1: f_sqr_coarse(f, x, o); break;
+        case 2: case 11: case 12: f_mul(f, x, y, o); break;
+        case 3: f_add_coarse(f, x, y, o); break;
+        case 4: f_sub_coarse(f, x, y, o); break;
+        case 5: f_reduce_once(f, x, o); break;
+        case 6: f_reduce_once(f, x, t); memset(o, 0, 32); f_sub(f, o, t, o); break; /* -x mod p, canonical, 0 -> 0 */
+        case 7: f_to_mont(f, x, o); break;
+        case 8: f_from_mont(f, x, o); break;
+        case 9: f_invert(f, x, o); break;
+        case 10: raw_add(x, f->p2, t); { /* x + 2p - y as a 256-bit integer, no correction */
+            unsigned __int128 bw = 0;
+            for (int k = 0; k < 4; ++k)
+            {
+                unsigned __int128 d = (unsigned __int128)t[k] - y[k] - (uint64_t)bw;
+                o[k] = (uint64_t)d;
+                bw = (d >> 64) & 1;
+            }
+        } break;
+        default: memset(o, 0, 32);
+        }
+    }
+}
+
 void orc_constant(int which, uint64_t* r)
 {
     const uint64_t* src = NULL;
@@ -533,6 +570,45 @@ void orc_g1_batch_normalize(uint64_t* pts, size_t n)
         memcpy(p + 8, FQ->one, 32);
     }
     free(tmp);
+}
+
+/* Affine in, affine out (normalised; infinity = flag) for the device self test; op codes = bbg_g1_selftest's. */
+static void aff_to_jac(const uint64_t* a, uint64_t* j)
+{
+    memcpy(j, a, 64);
+    memcpy(j + 8, FQ->one, 32);
+    if (a[7] >> 63) pt_set_inf(j);
+}
+void orc_g1_op_n(int op, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n)
+{
+    for (size_t i = 0; i < n; ++i)
+    {
+        uint64_t P[12], Q[12], t[12], u[12], r[12];
+        aff_to_jac(p + 8 * i, P);
+        aff_to_jac(q + 8 * i, Q);
+        switch (op)
+        {
+        case 0: if (q[8 * i + 7] >> 63) memcpy(r, P, 96); else orc_g1_mixed_add(P, q + 8 * i, r); break;
+        case 1: orc_g1_dbl(P, t); orc_g1_dbl(Q, u); orc_g1_add(t, u, r); break;
+        case 2: orc_g1_dbl(P, t); orc_g1_dbl(t, r); break;
+        case 3: orc_g1_add(P, Q, t); orc_g1_add(t, P, r); break;
+        case 4: orc_g1_add(P, Q, r); break;
+        case 5: {
+            uint64_t tab[16];
+            orc_generate_pippenger_point_table(p + 8 * i, tab, 1);
+            aff_to_jac(tab + 8, r);
+        } break;
+        case 6: orc_g1_dbl(P, r); break;
+        default: memcpy(r, P, 96); pt_set_inf(r);
+        }
+        orc_g1_normalize(r, t);
+        memcpy(out + 8 * i, t, 64);
+        if (pt_is_inf(t))
+        {
+            memset(out + 8 * i, 0, 64);
+            out[8 * i + 7] = (uint64_t)1 << 63;
+        }
+    }
 }
 
 /* group.hpp:536-552: y^2 == x^3 + b, compared out of Montgomery form */

@@ -45,6 +45,9 @@ void orc_invert(int field, const uint64_t a[4], uint64_t r[4]);        /* field.
 void orc_pow_small(int field, const uint64_t a[4], uint64_t e, uint64_t r[4]); /* field.hpp:290-332 */
 void orc_constant(int which, uint64_t r[4]);                           /* same numbering as ref_constant() */
 void orc_mul_n(int field, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n);
+/* element-wise batches, op codes of bbg_field_selftest / bbg_g1_selftest (include/bbgpu.h); residue-only ops canonical */
+void orc_field_op_n(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n);
+void orc_g1_op_n(int op, const uint64_t* p_affine, const uint64_t* q_affine, uint64_t* out_affine, size_t n);
 
 /* ---- scalar decomposition: field.hpp:413-485, groups/wnaf.hpp:15-55 ----------------------- */
 void orc_split_endo(const uint64_t k[4], uint64_t out[4]); /* out[0..1]=k1, out[2..3]=k2 (aliased form, scalar_multiplication.cpp:292) */

@@ -74,6 +74,27 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def require_ref():
+    """For `-m gpu` tests: the compiled reference is a prebuilt artefact that travels to the GPU box (oracle/_ref is
+    git-ignored, not gpurun-ignored).  Its absence there is a broken checkout, not a reason to skip: fail loudly, so a
+    green run can never mean "the reference comparisons were silently left out"."""
+    if not have_ref():
+        import pytest
+
+        pytest.fail("oracle/_ref/libbb_ref.so is missing: build it where /root/reference exists "
+                    "(python -c 'import __graft_entry__ as g; g.build()') — GPU parity tests do not skip")
+    return ref()
+
+
+def require_built(*names):
+    """Same rule for the prebuilt harness binaries under build/ (tests/cpp/Makefile)."""
+    missing = [n for n in names if not os.path.exists(os.path.join(ROOT, "build", n))]
+    if missing:
+        import pytest
+
+        pytest.fail("build/%s missing: run make -C tests/cpp where /root/reference exists — GPU tests do not skip" % ", build/".join(missing))
+
+
 def ref():
     """The compiled reference (None when oracle/_ref was never built)."""
     global _ref

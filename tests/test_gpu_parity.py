@@ -66,9 +66,9 @@ def test_ntt_golden_reference_vectors(lib):
             assert (b == g["ntt_" + name]).all(), name
 
 
-@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
 @pytest.mark.parametrize("log_n", [17, 18, 19, 20, 21, 22])
 def test_ntt_large_vs_compiled_reference(lib, log_n):
+    H.require_ref()  # -m gpu: a missing compiled reference fails, it does not skip
     ref_threads_pow2()
     n = 1 << log_n
     x = H.random_scalars_mont(log_n, n)
@@ -79,9 +79,9 @@ def test_ntt_large_vs_compiled_reference(lib, log_n):
         assert (got == ref_ntt(H.NTT_OPS[name], x, k)).all(), (log_n, name)
 
 
-@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
 @pytest.mark.parametrize("log_n,ops", [(23, list(H.NTT_OPS)), (24, ["fft", "ifft", "coset_fft", "coset_ifft"]), (25, ["coset_fft", "ifft"])])
 def test_ntt_three_pass_sizes_vs_compiled_reference(lib, log_n, ops):
+    H.require_ref()  # -m gpu: a missing compiled reference fails, it does not skip
     """n > 2^22 (up to the field's 2^28 two-adicity): outer split + two-pass blocks, three HBM passes.  A circuit of
     2^21 .. 2^23 gates needs these for its 4n domain."""
     ref_threads_pow2()
@@ -206,18 +206,14 @@ def test_msm_edge_cases(lib):
 @pytest.mark.parametrize("distinct", [1, 3, 1000])
 def test_msm_repetitive_scalars_giant_buckets(lib, distinct):
     """Constant / highly repetitive scalar vectors (they occur in the prover) give buckets spanning thousands of
-    slices: exercises the block-reduction fix-up path and must stay fast."""
-    import time
+    slices: exercises the block-reduction fix-up path (its cost is a bench.py figure, `degenerate_msm_ms`, not an
+    assertion here)."""
     n = 1 << 18
     table, a0, d = H.generator_multiples_table(13, n)
     vals = H.random_scalars_mont(97, distinct)
     sc = np.ascontiguousarray(vals[np.arange(n) % distinct])
-    lib.msm(sc, table)
-    t0 = time.perf_counter()
     got = lib.msm(sc, table)
-    ms = (time.perf_counter() - t0) * 1e3
     assert (got == H.closed_form_msm(sc, a0, d)).all()
-    assert ms < 100, "degenerate digit distribution took %.1f ms" % ms
 
 
 def test_batched_msm_and_srs_cache(lib):
@@ -248,7 +244,7 @@ def test_msm_full_size_closed_form_and_reference(lib, log_n):
     got = lib.msm(sc, table)
     assert (got == H.closed_form_msm(sc, a0, d)).all()
     # bench recipe scalars: powers of one element (bench_barretenberg.cpp:196-206)
-    if H.have_ref():
+    if H.require_ref() is not None:  # fails (never skips) when the compiled reference is missing
         r = H.ref()
         out = np.zeros((1, 12), dtype=np.uint64)
         sbuf = r.ref_aligned_alloc(32 * n)
@@ -327,7 +323,7 @@ def test_compute_lagrange_polynomial_fft(lib, log_src, log_tgt):
         exp = np.zeros_like(got)
         H.oracle().orc_compute_lagrange_polynomial_fft(ptr(exp), log_src, log_tgt)
         assert (got == exp).all()
-    if H.have_ref():
+    if H.require_ref() is not None:  # fails (never skips) when the compiled reference is missing
         r = H.ref()
         ref_threads_pow2()
         p = r.ref_aligned_alloc(32 * t)
@@ -443,9 +439,9 @@ def test_poly_evaluate(lib, n):
     assert (lib.evaluate(c, z) == _canonical(want.reshape(1, 4))[0]).all()
 
 
-@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
 @pytest.mark.parametrize("log_src,log_target", [(3, 5), (12, 13), (16, 18), (20, 21), (20, 22)])
 def test_divide_by_pseudo_vanishing_polynomial(lib, log_src, log_target):
+    H.require_ref()  # -m gpu: a missing compiled reference fails, it does not skip
     lib = lib
     T = 1 << log_target
     x = H.random_scalars_mont(80 + log_target, T)
@@ -460,9 +456,9 @@ def test_divide_by_pseudo_vanishing_polynomial(lib, log_src, log_target):
     assert (got == want).all()
 
 
-@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not present")
 @pytest.mark.parametrize("n", [1, 33, 5000, 1 << 16, (1 << 20) - 3, 1 << 20])
 def test_compute_kate_opening_coefficients(lib, n):
+    H.require_ref()  # -m gpu: a missing compiled reference fails, it does not skip
     """dest = (F(X) - F(z)) / (X - z): the reference's serial recurrence vs the suffix scan, as values; F(z) limb-equal"""
     lib = lib
     import ctypes as C
@@ -479,3 +475,86 @@ def test_compute_kate_opening_coefficients(lib, n):
     got, f = lib.compute_kate_opening_coefficients(src, z)
     assert (f == f_ref).all()
     assert (got == _canonical(want)).all()
+
+
+# ---- round 2: host-buffer hazards named by the round-1 review ---------------------------------------------------------
+def test_msm_launched_beside_large_pageable_transforms(lib):
+    """bbg_msm_g1_launch with >= 1 MiB of pageable scalars (the staging-ring path) followed by pageable transforms of
+    >= 1 MiB on the work stream: the download ring must not reuse a slot whose MSM upload has not run yet, and an
+    unregistered table must reach the MSM stream before its kernels and must not be overwritten by the next launch."""
+    n = 1 << 16
+    tables = [H.generator_multiples_table(61 + 2 * i, n) for i in range(2)]
+    scs = [H.random_scalars_mont(80 + i, n) for i in range(2)]  # 2 MiB each, pageable numpy memory
+    x = H.random_scalars_mont(12, 1 << 18)  # 8 MiB pageable
+    for _ in range(2):  # second round: the same buffers again (registration cache hit when it is on)
+        tickets = [lib.msm_launch(scs[i], tables[i][0], n) for i in range(2)]  # two different unregistered tables in flight
+        y = lib.ntt("fft", x.copy())
+        assert (lib.ntt("ifft", y) == x).all()
+        for i in (1, 0):
+            got = lib.msm_finish(tickets[i])
+            assert (got == H.closed_form_msm(scs[i], tables[i][1], tables[i][2])).all(), i
+
+
+def test_host_register_cache(lib):
+    """Pageable buffers seen twice are page-locked in place: results unchanged on first, second and later sightings, after
+    the caller rewrites the buffer, and after it tells the library to forget it."""
+    lib.set_host_register_cache(True)
+    try:
+        n = 1 << 17  # 4 MiB
+        x = H.random_scalars_mont(15, n)
+        od = None
+        buf = x.copy()
+        expect = None
+        for it in range(4):
+            buf[:] = x
+            lib.ntt("coset_fft", buf)
+            if expect is None:
+                expect = buf.copy()
+                if H.have_ref():
+                    assert (expect == ref_ntt(H.NTT_OPS["coset_fft"], x)).all()
+            assert (buf == expect).all(), it
+        # new contents behind the same (now page-locked) address
+        x2 = H.random_scalars_mont(16, n)
+        buf[:] = x2
+        lib.ntt("coset_ifft", lib.ntt("coset_fft", buf))
+        assert (buf == x2).all()
+        lib.host_buffer_forget(buf)
+        buf[:] = x
+        lib.ntt("coset_fft", buf)
+        assert (buf == expect).all()
+        # MSM scalars through the cache as well
+        m = 1 << 16
+        table, a0, d = H.generator_multiples_table(91, m)
+        sc = H.random_scalars_mont(92, m)
+        for _ in range(3):
+            assert (lib.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+        lib.host_buffer_forget(sc)
+        lib.host_buffer_forget(table)
+    finally:
+        lib.set_host_register_cache(False)
+
+
+def test_msm_plain_points_entry(lib):
+    """bbg_msm_g1_points (behind pippenger_low_memory / pippenger_precomputed): n plain points, table built on the device"""
+    import ctypes as C
+
+    lib.lib.bbg_msm_g1_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    for n in (1, 2, 999, 5000):
+        table, a0, d = H.generator_multiples_table(33 + n, n)
+        plain = np.ascontiguousarray(table[0::2])
+        sc = H.random_scalars_mont(5 + n, n)
+        out = np.zeros(12, dtype=np.uint64)
+        lib.check(lib.lib.bbg_msm_g1_points(sc.ctypes.data_as(C.c_void_p), plain.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)))
+        assert (out == H.oracle_msm(sc, table)).all(), n
+
+
+def test_multi_device_instance():
+    """bbg_init_multi over every GPU of the box in a process of its own (tests/multi_device_check.py): host, device,
+    batched and launched MSMs over registered tables fanned out by point range must equal the single-device results and the
+    closed form.  With one GPU the script still runs (a one-device list) and checks the same identities."""
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "tests", "multi_device_check.py")], cwd=H.ROOT, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "multi-device check ok" in out.stdout

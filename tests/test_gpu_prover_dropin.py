@@ -21,8 +21,7 @@ def have_binaries():
 
 @pytest.fixture(scope="module")
 def srs():
-    if not have_binaries():
-        pytest.skip("build/prover_{cpu,gpu} not built (needs the reference tree: make -C tests/cpp)")
+    H.require_built("make_srs", "prover_cpu", "prover_gpu")  # -m gpu: missing prebuilt binaries fail, they do not skip
     path = os.path.join(B, "srs", "transcript.dat")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     need = 64 * 16383 + 28 + 256 + 64
@@ -69,8 +68,7 @@ def test_resident_prover_other_widget_mixes(srs, log_gates, composer):
 @pytest.mark.parametrize("log_gates", [5, 12])
 def test_prover_classic_round_structure_matches_cpu_reference(srs, log_gates, binary, env):
     """the ten-entry-point drop-in alone (reference round structure), also reachable from the resident build"""
-    if not os.path.exists(os.path.join(B, binary)):
-        pytest.skip(binary + " not built")
+    H.require_built(binary)
     cpu = run("prover_cpu", log_gates)
     gpu = run(binary, log_gates, repeat=2, env=env)
     assert cpu["verified"] and gpu["verified"]
