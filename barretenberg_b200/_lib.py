@@ -97,6 +97,11 @@ class Library:
     def set_host_register_cache(self, on=True):
         self.check(self.lib.bbg_set_host_register_cache(1 if on else 0))
 
+    def host_register_stats(self):
+        ms, b, c = C.c_double(), C.c_uint64(), C.c_uint64()
+        self.check(self.lib.bbg_host_register_stats(C.byref(ms), C.byref(b), C.byref(c)))
+        return {"register_ms": ms.value, "registered_bytes": int(b.value), "registrations": int(c.value)}
+
     def host_buffer_forget(self, array_or_ptr):
         p = array_or_ptr.ctypes.data if isinstance(array_or_ptr, np.ndarray) else int(array_or_ptr)
         self.check(self.lib.bbg_host_buffer_forget(C.c_void_p(p)))

@@ -234,7 +234,7 @@ int msm_host_batched(const uint64_t* const* scalars, size_t batch, const uint64_
 #ifndef BBG_EMULATE
     // the other devices' workers copy straight out of the caller's buffers: page-lock them here, once, as a whole
     if (msm_multi_device_count() > 1)
-        for (size_t b = 0; b < batch; ++b) (void)bbg_hostcopy::direct_copy_ok(scalars[b], n * 32);
+        for (size_t b = 0; b < batch; ++b) (void)bbg_hostcopy::reg_cache().classify(scalars[b], n * 32);
 #endif
     int ticket = -1;
     BBG_CHECK(msm_launch_any(0, (const void* const*)scalars, true, g_stage_scalars.p, batch, d_table, n, g_stream, &ticket));
@@ -272,6 +272,7 @@ int bbg_init(int device)
     BBG_CHECK(cudaStreamCreateWithFlags(&g_copy_out, cudaStreamNonBlocking));
     BBG_CHECK(cudaStreamCreateWithFlags(&g_msm_stream, cudaStreamNonBlocking));
     BBG_CHECK(cudaEventCreateWithFlags(&g_msm_fence, cudaEventDisableTiming));
+    bbg_hostcopy::reg_cache().set_quiesce([]() { quiesce_all(); });
 #else
     (void)device;
 #endif
@@ -411,7 +412,7 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
     }
 #ifndef BBG_EMULATE
     bool all_pinned = batch > 1;
-    for (size_t i = 0; i < batch && all_pinned; ++i) all_pinned = bbg_hostcopy::is_pinned(coeffs[i]);
+    for (size_t i = 0; i < batch && all_pinned; ++i) all_pinned = bbg_hostcopy::caller_pinned_whole(coeffs[i], bytes);
     if (all_pinned)
     {
         // three-stage pipeline over polynomials: upload i+1 | transform i | download i-1 (PCIe is full duplex)
@@ -646,7 +647,14 @@ int bbg_msm_g1_launch(const uint64_t* scalars, const uint64_t* points_table, siz
 #endif
     BBG_CHECK(slot->scalars.ensure(n * 32));
 #ifndef BBG_EMULATE
+    // a buffer the registration cache page-locked is still "pageable" to its owner: theirs again when this call returns
+    const bool wait_copy = bbg_hostcopy::copy_is_async(scalars, n * 32) && !bbg_hostcopy::caller_pinned_whole(scalars, n * 32);
     BBG_CHECK(bbg_hostcopy::h2d_ring(g_msm_ring, slot->scalars.p, scalars, n * 32, st));
+    if (wait_copy)
+    {
+        BBG_CHECK(cudaEventRecord(g_msm_fence, st));
+        BBG_CHECK(cudaEventSynchronize(g_msm_fence));
+    }
 #else
     BBG_CHECK(bbg_hostcopy::h2d(slot->scalars.p, scalars, n * 32, st));
 #endif
@@ -976,6 +984,15 @@ int bbg_set_host_register_cache(int enable)
     BBG_CHECK(ensure_ready());
     if (!enable) quiesce_all();
     bbg_hostcopy::reg_cache().enable(enable != 0);
+    return 0;
+}
+int bbg_host_register_stats(double* register_ms, uint64_t* registered_bytes, uint64_t* registrations)
+{
+    if (register_ms == nullptr || registered_bytes == nullptr || registrations == nullptr) return BBG_E_BAD_ARGUMENT;
+    unsigned long long b = 0, c = 0;
+    bbg_hostcopy::reg_cache().stats(register_ms, &b, &c);
+    *registered_bytes = b;
+    *registrations = c;
     return 0;
 }
 int bbg_host_buffer_forget(const void* host_ptr)

@@ -20,6 +20,7 @@
 
 #ifndef BBG_EMULATE
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -122,6 +123,15 @@ inline bool is_pinned(const void* p)
 }
 
 // ---- cudaHostRegister cache for caller-owned pageable buffers -----------------------------------------------------------
+// Only the WHOLE pages inside a buffer are page-locked: heap blocks share their first and last page with their neighbours,
+// and a page can be registered once.  A copy of a registered buffer is therefore three copies — a head and a tail of less
+// than a page each through the driver's own pageable path, the page-locked middle directly.
+struct PinnedSpan
+{
+    size_t head = 0; // bytes before the page-locked middle
+    size_t mid = 0;  // page-locked bytes (0: nothing usable)
+    bool whole = false; // the caller pinned the whole buffer itself (cudaHostAlloc / cudaHostRegister)
+};
 class RegCache
 {
   public:
@@ -134,40 +144,88 @@ class RegCache
             const long v = atol(e);
             if (v >= 0) max_bytes_ = (size_t)v << 20;
         }
+        if (const char* e = getenv("BBG_HOST_REGISTER_AFTER"))
+        {
+            const long v = atol(e);
+            if (v >= 1) register_after_ = (unsigned)v;
+        }
         if (!on) drop_all_locked();
     }
     bool enabled() const { return enabled_; }
-    // Called for a pageable buffer about to be copied.  Returns true when [p, p + bytes) is page-locked now (registered
-    // by an earlier call or by this one: second sighting of the same address and size).
-    bool note(const void* p, size_t bytes)
+    // Called for a buffer about to be copied: which part of [p, p + bytes) is page-locked.  Counts sightings (one per
+    // copy: an in-place transform is two); the register_after_-th sighting of the same address and size page-locks the
+    // buffer's whole pages in place.  Page-locking costs about as much as ten staged copies of the same buffer (measured on
+    // the B200 box: cudaHostRegister runs at 1-2 GB/s, the staging ring at ~12 GB/s, a pinned copy at ~50 GB/s), so only
+    // buffers that keep coming back are worth it; temporaries freed after one proof never get there.
+    PinnedSpan classify(const void* p, size_t bytes)
     {
-        if (!enabled_) return false;
+        PinnedSpan r;
+        const char* lo = (const char*)p;
+        const char* hi = lo + bytes;
+        if (!enabled_ || count_.load(std::memory_order_acquire) == 0)
+        {
+            if (caller_pinned(lo, hi))
+            {
+                r.whole = true;
+                return r;
+            }
+            if (!enabled_) return r;
+        }
         std::lock_guard<std::mutex> lock(m_);
         ++clock_;
+        bool overlap = false;
         for (Entry& e : entries_)
         {
-            if ((const char*)p >= e.base && (const char*)p + bytes <= e.base + e.bytes && e.registered)
+            if (!e.registered) continue;
+            if (lo >= e.base && hi <= e.base + e.bytes)
             {
                 e.used = clock_;
-                return true;
+                return span_of(e, lo, hi);
             }
+            if (lo < e.reg_base + e.reg_bytes && hi > e.reg_base) overlap = true;
+        }
+        if (!overlap && caller_pinned(lo, hi))
+        {
+            r.whole = true;
+            return r;
         }
         for (Entry& e : entries_)
         {
-            if (e.base == (const char*)p && e.bytes == bytes)
+            if (e.base == lo && e.bytes == bytes)
             {
                 e.used = clock_;
-                return try_register_locked(e);
+                if (++e.sightings >= register_after_ && try_register_locked(e)) return span_of(e, lo, hi);
+                return r;
             }
         }
         if (entries_.size() >= MAX_ENTRIES) evict_locked(/*registered_only=*/false);
         Entry n;
-        n.base = (const char*)p;
+        n.base = lo;
         n.bytes = bytes;
         n.used = clock_;
+        n.sightings = 1;
         entries_.push_back(n);
         count_.store(entries_.size(), std::memory_order_release);
-        return false;
+        return r;
+    }
+    // the same answer without counting a sighting or registering anything
+    PinnedSpan peek(const void* p, size_t bytes)
+    {
+        PinnedSpan r;
+        const char* lo = (const char*)p;
+        const char* hi = lo + bytes;
+        if (enabled_ && count_.load(std::memory_order_acquire) != 0)
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            for (Entry& e : entries_)
+            {
+                if (!e.registered) continue;
+                if (lo >= e.base && hi <= e.base + e.bytes) return span_of(e, lo, hi);
+                if (lo < e.reg_base + e.reg_bytes && hi > e.reg_base) return r; // partly ours: not the caller's pinning
+            }
+        }
+        r.whole = caller_pinned(lo, hi);
+        return r;
     }
     // the caller is about to free (or has remapped) the buffer that starts at / contains p
     void forget(const void* p)
@@ -193,6 +251,14 @@ class RegCache
         drop_all_locked();
     }
     size_t registered_bytes() const { return total_; }
+    void stats(double* ms, unsigned long long* bytes, unsigned long long* count) const
+    {
+        *ms = stat_ms_;
+        *bytes = stat_bytes_;
+        *count = stat_count_;
+    }
+    // hook for "nothing of this library is still in flight on any device" (set by the C-ABI layer; default: this device)
+    void set_quiesce(void (*fn)()) { quiesce_ = fn; }
 
   private:
     struct Entry
@@ -200,33 +266,60 @@ class RegCache
         const char* base = nullptr;
         size_t bytes = 0;
         unsigned long used = 0;
+        unsigned sightings = 0;
         bool registered = false;
         bool failed = false;
-        char* reg_base = nullptr; // page-rounded range actually registered
+        char* reg_base = nullptr; // the whole pages inside [base, base + bytes)
         size_t reg_bytes = 0;
     };
     static constexpr size_t MAX_ENTRIES = 96;
+    static constexpr size_t PAGE = 4096;
+    static bool caller_pinned(const char* lo, const char* hi) { return hi > lo && is_pinned(lo) && is_pinned(hi - 1); }
+    static PinnedSpan span_of(const Entry& e, const char* lo, const char* hi)
+    {
+        PinnedSpan r;
+        const char* a = lo > e.reg_base ? lo : e.reg_base;
+        const char* b = hi < e.reg_base + e.reg_bytes ? hi : e.reg_base + e.reg_bytes;
+        if (b > a)
+        {
+            r.head = (size_t)(a - lo);
+            r.mid = (size_t)(b - a);
+        }
+        return r;
+    }
     bool try_register_locked(Entry& e)
     {
         if (e.failed) return false;
-        const size_t page = 4096;
-        char* lo = (char*)((uintptr_t)e.base & ~(uintptr_t)(page - 1));
-        char* hi = (char*)(((uintptr_t)e.base + e.bytes + page - 1) & ~(uintptr_t)(page - 1));
+        char* lo = (char*)(((uintptr_t)e.base + PAGE - 1) & ~(uintptr_t)(PAGE - 1));
+        char* hi = (char*)(((uintptr_t)e.base + e.bytes) & ~(uintptr_t)(PAGE - 1));
+        if (hi <= lo + 16 * PAGE)
+        {
+            e.failed = true;
+            return false;
+        }
         const size_t len = (size_t)(hi - lo);
-        while (total_ + len > max_bytes_ && evict_locked(/*registered_only=*/true)) {}
+        // a different buffer registered earlier behind overlapping addresses is gone (freed without a forget, or this is
+        // the same allocation seen with another size): its registration makes way.  Entries stay in the table (no
+        // references move); an unregistered one ages out.
+        for (Entry& o : entries_)
+            if (&o != &e && o.registered && lo < o.reg_base + o.reg_bytes && hi > o.reg_base) unregister_locked(o);
+        while (total_ + len > max_bytes_ && evict_other_locked(e)) {}
         if (total_ + len > max_bytes_)
         {
             e.failed = true;
             return false;
         }
+        const auto t0 = std::chrono::steady_clock::now();
         const cudaError_t err = cudaHostRegister(lo, len, cudaHostRegisterPortable);
         if (err != cudaSuccess)
         {
             cudaGetLastError();
             e.failed = true;
-            // neighbouring heap blocks may share our first / last page with an earlier registration
-            return is_pinned(e.base) && is_pinned(e.base + e.bytes - 1) && err == cudaErrorHostMemoryAlreadyRegistered;
+            return false;
         }
+        stat_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stat_bytes_ += len;
+        stat_count_ += 1;
         e.registered = true;
         e.reg_base = lo;
         e.reg_bytes = len;
@@ -236,11 +329,25 @@ class RegCache
     void unregister_locked(Entry& e)
     {
         if (!e.registered) return;
-        cudaDeviceSynchronize(); // nothing may still be on the wire from / to these pages
+        if (quiesce_) quiesce_(); // nothing may still be on the wire from / to these pages
+        else cudaDeviceSynchronize();
         cudaHostUnregister(e.reg_base);
         cudaGetLastError();
         total_ -= e.reg_bytes;
         e.registered = false;
+    }
+    bool evict_other_locked(const Entry& keep)
+    {
+        long best = -1;
+        for (size_t i = 0; i < entries_.size(); ++i)
+        {
+            if (!entries_[i].registered || &entries_[i] == &keep) continue;
+            if (best < 0 || entries_[i].used < entries_[(size_t)best].used) best = (long)i;
+        }
+        if (best < 0) return false;
+        unregister_locked(entries_[(size_t)best]); // stays in the table, unregistered: erasing would move `keep`
+        entries_[(size_t)best].failed = false;
+        return true;
     }
     bool evict_locked(bool registered_only)
     {
@@ -269,14 +376,16 @@ class RegCache
     unsigned long clock_ = 0;
     size_t total_ = 0;
     size_t max_bytes_ = (size_t)16 << 30;
+    unsigned register_after_ = 6;
+    double stat_ms_ = 0;
+    unsigned long long stat_bytes_ = 0, stat_count_ = 0;
+    void (*quiesce_)() = nullptr;
 };
 inline RegCache& reg_cache()
 {
     static RegCache c;
     return c;
 }
-// pinned already, or page-locked in place by the registration cache
-inline bool direct_copy_ok(const void* h, size_t bytes) { return is_pinned(h) || reg_cache().note(h, bytes); }
 
 struct Ring
 {
@@ -327,10 +436,34 @@ inline Ring& ring()
 }
 
 
+// one buffer, up to three copies: pageable head (< 1 page), page-locked middle, pageable tail
+inline int copy_spans(void* d, const void* h, size_t bytes, const PinnedSpan& sp, bool to_device, cudaStream_t st)
+{
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    auto part = [&](size_t off, size_t len) -> int {
+        if (len == 0) return 0;
+        return to_device ? (int)cudaMemcpyAsync((char*)d + off, (const char*)h + off, len, kind, st)
+                         : (int)cudaMemcpyAsync((char*)const_cast<void*>(h) + off, (const char*)d + off, len, kind, st);
+    };
+    if (to_device)
+    {
+        // the two fragments first (the driver stages them and returns), then the asynchronous middle
+        BBG_CHECK(part(0, sp.head));
+        BBG_CHECK(part(sp.head + sp.mid, bytes - sp.head - sp.mid));
+        return part(sp.head, sp.mid);
+    }
+    BBG_CHECK(part(sp.head, sp.mid));
+    BBG_CHECK(part(0, sp.head)); // pageable destination: returns once everything queued before it, and itself, has landed
+    return part(sp.head + sp.mid, bytes - sp.head - sp.mid);
+}
+
 // `r`: the pinned staging ring to use (one per host thread that copies; the default ring belongs to the caller's thread)
 inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t st)
 {
-    if (bytes < SMALL || direct_copy_ok(h, bytes)) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+    if (bytes < SMALL) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+    const PinnedSpan sp = reg_cache().classify(h, bytes);
+    if (sp.whole) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+    if (sp.mid > 0) return copy_spans(d, h, bytes, sp, true, st);
     BBG_CHECK(r.init());
     size_t off = 0;
     while (off < bytes)
@@ -346,11 +479,23 @@ inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t 
     return 0;
 }
 inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st) { return h2d_ring(ring(), d, h, bytes, st); }
+// true when a copy from h queued by h2d may still be reading h after h2d returned (the caller pinned it, or the
+// registration cache did): callers that promise "the buffer is yours again on return" wait for the copy in that case
+inline bool copy_is_async(const void* h, size_t bytes)
+{
+    if (bytes < SMALL) return is_pinned(h);
+    const PinnedSpan sp = reg_cache().peek(h, bytes);
+    return sp.whole || sp.mid > 0;
+}
+inline bool caller_pinned_whole(const void* h, size_t bytes) { return reg_cache().peek(h, bytes).whole; }
 
 // returns with the data in h (synchronous for pageable destinations, like cudaMemcpy)
 inline int d2h_ring(Ring& r, void* h, const void* d, size_t bytes, cudaStream_t st)
 {
-    if (bytes < SMALL || direct_copy_ok(h, bytes)) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+    if (bytes < SMALL) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+    const PinnedSpan sp = reg_cache().classify(h, bytes);
+    if (sp.whole) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+    if (sp.mid > 0) return copy_spans(const_cast<void*>(d), h, bytes, sp, false, st);
     BBG_CHECK(r.init());
     const size_t chunks = (bytes + CHUNK - 1) / CHUNK;
     for (size_t k = 0; k < chunks + (RING - 1); ++k)
@@ -388,6 +533,8 @@ struct RegCache
     void enable(bool) {}
     void forget(const void*) {}
     void release() {}
+    void set_quiesce(void (*)()) {}
+    void stats(double* ms, unsigned long long* bytes, unsigned long long* count) const { *ms = 0; *bytes = 0; *count = 0; }
 };
 inline RegCache& reg_cache()
 {

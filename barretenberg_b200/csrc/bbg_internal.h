@@ -3,11 +3,20 @@
 #include "bbg_rt.h"
 #include "bbg_g1.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+// BBG_DEBUG=1: name the failing call on stderr (development aid; the error code is returned either way)
+inline int bbg_trace_error(int e, const char* expr, const char* file, int line)
+{
+    static const bool on = getenv("BBG_DEBUG") != nullptr;
+    if (on) fprintf(stderr, "bbgpu: error %d from %s at %s:%d\n", e, expr, file, line);
+    return e;
+}
 #define BBG_CHECK(expr)                                                                            \
     do                                                                                             \
     {                                                                                              \
         int bbg_err_ = (int)(expr);                                                                \
-        if (bbg_err_ != 0) return bbg_err_;                                                        \
+        if (bbg_err_ != 0) return bbg_trace_error(bbg_err_, #expr, __FILE__, __LINE__);            \
     } while (0)
 
 namespace bbg

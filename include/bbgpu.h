@@ -231,13 +231,16 @@ int bbg_plonk_round_openings(bbg_plonk_prover* p, const uint64_t* nu_powers, con
 /* ---- caller-owned host buffers -------------------------------------------------------------------
  * The reference's callers pass pageable memory (aligned_alloc, types.hpp:25) and reuse the same long-lived buffers call
  * after call (barretenberg::polynomial members, ReferenceString::monomials).  With the cache on, a pageable buffer of
- * >= 1 MiB seen a second time behind the same address and size is page-locked in place (cudaHostRegister) and from then on
- * copied at the pinned rate, without the staging memcpy.  Contract: hand a buffer to bbg_host_buffer_forget BEFORE
+ * >= 1 MiB that keeps coming back behind the same address and size (6th copy; BBG_HOST_REGISTER_AFTER) is page-locked in
+ * place (cudaHostRegister) and from then on copied at the pinned rate, without the staging memcpy; page-locking costs
+ * about ten staged copies, so one-proof temporaries are left alone.  Contract: hand a buffer to bbg_host_buffer_forget BEFORE
  * freeing it (the driver keeps DMA mappings of the physical pages; an address range unmapped and mapped again would be
  * read through the old ones).  shim/host_buffer_free_wrap.cpp does that for a prover linked with -Wl,--wrap=free.
  * Off by default; BBG_HOST_REGISTER_MAX_MB caps the page-locked total (default 16384). */
 int bbg_set_host_register_cache(int enable);
 int bbg_host_buffer_forget(const void* host_ptr); /* any pointer into the buffer; unknown pointers are ignored; thread-safe */
+/* what page-locking has cost so far: wall milliseconds inside cudaHostRegister, bytes and buffers registered */
+int bbg_host_register_stats(double* register_ms, uint64_t* registered_bytes, uint64_t* registrations);
 
 /* ---- device self test (tests only; bbg_selftest.cu) --------------------------------------------------
  * Element-wise field / group primitives on the device, host buffers in and out, for limb-for-limb comparison with the

@@ -505,7 +505,7 @@ def test_host_register_cache(lib):
         od = None
         buf = x.copy()
         expect = None
-        for it in range(4):
+        for it in range(6):  # page-locked in place at the 6th copy (two per in-place transform)
             buf[:] = x
             lib.ntt("coset_fft", buf)
             if expect is None:
@@ -526,8 +526,9 @@ def test_host_register_cache(lib):
         m = 1 << 16
         table, a0, d = H.generator_multiples_table(91, m)
         sc = H.random_scalars_mont(92, m)
-        for _ in range(3):
+        for _ in range(8):
             assert (lib.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+        assert lib.host_register_stats()["registrations"] >= 2
         lib.host_buffer_forget(sc)
         lib.host_buffer_forget(table)
     finally:
