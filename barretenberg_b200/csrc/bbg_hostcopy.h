@@ -131,27 +131,38 @@ struct PinnedSpan
     size_t head = 0; // bytes before the page-locked middle
     size_t mid = 0;  // page-locked bytes (0: nothing usable)
     bool whole = false; // the caller pinned the whole buffer itself (cudaHostAlloc / cudaHostRegister)
+    bool mixed = false; // touches more than one registration: only a host memcpy through the staging ring is safe
 };
 class RegCache
 {
   public:
     void enable(bool on)
     {
-        std::lock_guard<std::mutex> lock(m_);
-        enabled_ = on;
-        if (const char* e = getenv("BBG_HOST_REGISTER_MAX_MB"))
         {
-            const long v = atol(e);
-            if (v >= 0) max_bytes_ = (size_t)v << 20;
+            std::lock_guard<std::mutex> lock(m_);
+            enabled_ = on;
+            if (const char* e = getenv("BBG_HOST_REGISTER_MAX_MB"))
+            {
+                const long v = atol(e);
+                if (v >= 0) max_bytes_ = (size_t)v << 20;
+            }
+            if (const char* e = getenv("BBG_HOST_REGISTER_AFTER"))
+            {
+                const long v = atol(e);
+                if (v >= 1) register_after_ = (unsigned)v;
+            }
+            if (!on) drop_all_locked();
         }
-        if (const char* e = getenv("BBG_HOST_REGISTER_AFTER"))
-        {
-            const long v = atol(e);
-            if (v >= 1) register_after_ = (unsigned)v;
-        }
-        if (!on) drop_all_locked();
+        flush_retired();
     }
     bool enabled() const { return enabled_; }
+    // threads that must never wait for the library to go idle (the per-device MSM workers: they ARE the library's work)
+    // only look registrations up
+    static bool& lookup_only_thread()
+    {
+        static thread_local bool v = false;
+        return v;
+    }
     // Called for a buffer about to be copied: which part of [p, p + bytes) is page-locked.  Counts sightings (one per
     // copy: an in-place transform is two); the register_after_-th sighting of the same address and size page-locks the
     // buffer's whole pages in place.  Page-locking costs about as much as ten staged copies of the same buffer (measured on
@@ -159,53 +170,53 @@ class RegCache
     // buffers that keep coming back are worth it; temporaries freed after one proof never get there.
     PinnedSpan classify(const void* p, size_t bytes)
     {
+        if (lookup_only_thread()) return peek(p, bytes);
         PinnedSpan r;
         const char* lo = (const char*)p;
         const char* hi = lo + bytes;
-        if (!enabled_ || count_.load(std::memory_order_acquire) == 0)
+        if (!enabled_)
         {
+            r.whole = caller_pinned(lo, hi);
+            return r;
+        }
+        bool retired = false;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            ++clock_;
+            if (touching_locked(lo, hi, &r)) return r;
             if (caller_pinned(lo, hi))
             {
                 r.whole = true;
                 return r;
             }
-            if (!enabled_) return r;
-        }
-        std::lock_guard<std::mutex> lock(m_);
-        ++clock_;
-        bool overlap = false;
-        for (Entry& e : entries_)
-        {
-            if (!e.registered) continue;
-            if (lo >= e.base && hi <= e.base + e.bytes)
+            Entry* e = nullptr;
+            for (Entry& x : entries_)
+                if (x.base == lo && x.bytes == bytes) e = &x;
+            if (e == nullptr)
             {
-                e.used = clock_;
-                return span_of(e, lo, hi);
+                if (entries_.size() >= MAX_ENTRIES) retired = evict_locked(/*registered_only=*/false) || retired;
+                Entry n;
+                n.base = lo;
+                n.bytes = bytes;
+                n.used = clock_;
+                n.sightings = 1;
+                entries_.push_back(n);
+                count_.store(entries_.size(), std::memory_order_release);
             }
-            if (lo < e.reg_base + e.reg_bytes && hi > e.reg_base) overlap = true;
-        }
-        if (!overlap && caller_pinned(lo, hi))
-        {
-            r.whole = true;
-            return r;
-        }
-        for (Entry& e : entries_)
-        {
-            if (e.base == lo && e.bytes == bytes)
+            else
             {
-                e.used = clock_;
-                if (++e.sightings >= register_after_ && try_register_locked(e)) return span_of(e, lo, hi);
-                return r;
+                e->used = clock_;
+                if (++e->sightings >= register_after_ && !e->failed)
+                {
+                    // make room first: an older registration behind overlapping addresses is gone (freed without a forget,
+                    // or the same allocation seen with another size), and the page-locked total has a cap.  Retired
+                    // registrations are released outside the lock (below); this buffer registers at its next sighting.
+                    if (make_room_locked(*e)) retired = true;
+                    else if (register_locked(*e)) r = span_of(*e, lo, hi);
+                }
             }
         }
-        if (entries_.size() >= MAX_ENTRIES) evict_locked(/*registered_only=*/false);
-        Entry n;
-        n.base = lo;
-        n.bytes = bytes;
-        n.used = clock_;
-        n.sightings = 1;
-        entries_.push_back(n);
-        count_.store(entries_.size(), std::memory_order_release);
+        if (retired) flush_retired();
         return r;
     }
     // the same answer without counting a sighting or registering anything
@@ -217,12 +228,7 @@ class RegCache
         if (enabled_ && count_.load(std::memory_order_acquire) != 0)
         {
             std::lock_guard<std::mutex> lock(m_);
-            for (Entry& e : entries_)
-            {
-                if (!e.registered) continue;
-                if (lo >= e.base && hi <= e.base + e.bytes) return span_of(e, lo, hi);
-                if (lo < e.reg_base + e.reg_bytes && hi > e.reg_base) return r; // partly ours: not the caller's pinning
-            }
+            if (touching_locked(lo, hi, &r)) return r;
         }
         r.whole = caller_pinned(lo, hi);
         return r;
@@ -231,24 +237,31 @@ class RegCache
     void forget(const void* p)
     {
         if (count_.load(std::memory_order_acquire) == 0) return; // fast path: free() wrappers call this for every block
-        std::lock_guard<std::mutex> lock(m_);
-        for (size_t i = 0; i < entries_.size();)
+        bool retired = false;
         {
-            Entry& e = entries_[i];
-            if ((const char*)p >= e.base && (const char*)p < e.base + e.bytes)
+            std::lock_guard<std::mutex> lock(m_);
+            for (size_t i = 0; i < entries_.size();)
             {
-                unregister_locked(e);
-                entries_.erase(entries_.begin() + (long)i);
+                Entry& e = entries_[i];
+                if ((const char*)p >= e.base && (const char*)p < e.base + e.bytes)
+                {
+                    retired = retire_locked(e) || retired;
+                    entries_.erase(entries_.begin() + (long)i);
+                }
+                else
+                    ++i;
             }
-            else
-                ++i;
+            count_.store(entries_.size(), std::memory_order_release);
         }
-        count_.store(entries_.size(), std::memory_order_release);
+        if (retired) flush_retired();
     }
     void release()
     {
-        std::lock_guard<std::mutex> lock(m_);
-        drop_all_locked();
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            drop_all_locked();
+        }
+        flush_retired();
     }
     size_t registered_bytes() const { return total_; }
     void stats(double* ms, unsigned long long* bytes, unsigned long long* count) const
@@ -287,34 +300,76 @@ class RegCache
         }
         return r;
     }
-    bool try_register_locked(Entry& e)
+    // Any range that touches page-locked pages of ours is copied in pieces: one cudaMemcpyAsync must never span
+    // page-locked and pageable memory, and a sub-range of a registered buffer (a device's share of the scalars, the low n
+    // coefficients of a 4n polynomial) usually starts in the buffer's unregistered first page.
+    bool touching_locked(const char* lo, const char* hi, PinnedSpan* out)
     {
-        if (e.failed) return false;
-        char* lo = (char*)(((uintptr_t)e.base + PAGE - 1) & ~(uintptr_t)(PAGE - 1));
-        char* hi = (char*)(((uintptr_t)e.base + e.bytes) & ~(uintptr_t)(PAGE - 1));
+        int touching = 0;
+        Entry* hit = nullptr;
+        for (Entry& e : entries_)
+        {
+            if (e.registered && lo < e.reg_base + e.reg_bytes && hi > e.reg_base)
+            {
+                ++touching;
+                hit = &e;
+            }
+        }
+        if (touching == 0) return false;
+        if (touching == 1)
+        {
+            hit->used = clock_;
+            *out = span_of(*hit, lo, hi);
+        }
+        else
+            out->mixed = true;
+        return true;
+    }
+    static void inner_pages(const Entry& e, char** lo, char** hi)
+    {
+        *lo = (char*)(((uintptr_t)e.base + PAGE - 1) & ~(uintptr_t)(PAGE - 1));
+        *hi = (char*)(((uintptr_t)e.base + e.bytes) & ~(uintptr_t)(PAGE - 1));
+    }
+    // true when something had to be retired (then nothing is registered now: the caller flushes and tries again later)
+    bool make_room_locked(Entry& e)
+    {
+        char *lo, *hi;
+        inner_pages(e, &lo, &hi);
         if (hi <= lo + 16 * PAGE)
         {
             e.failed = true;
             return false;
         }
         const size_t len = (size_t)(hi - lo);
-        // a different buffer registered earlier behind overlapping addresses is gone (freed without a forget, or this is
-        // the same allocation seen with another size): its registration makes way.  Entries stay in the table (no
-        // references move); an unregistered one ages out.
+        bool retired = false;
         for (Entry& o : entries_)
-            if (&o != &e && o.registered && lo < o.reg_base + o.reg_bytes && hi > o.reg_base) unregister_locked(o);
-        while (total_ + len > max_bytes_ && evict_other_locked(e)) {}
-        if (total_ + len > max_bytes_)
+            if (&o != &e && o.registered && lo < o.reg_base + o.reg_bytes && hi > o.reg_base) retired = retire_locked(o) || retired;
+        while (total_ + len > max_bytes_)
         {
-            e.failed = true;
-            return false;
+            Entry* oldest = nullptr;
+            for (Entry& o : entries_)
+                if (&o != &e && o.registered && (oldest == nullptr || o.used < oldest->used)) oldest = &o;
+            if (oldest == nullptr)
+            {
+                e.failed = true; // larger than the cap on its own
+                return retired;
+            }
+            retired = retire_locked(*oldest) || retired;
         }
+        return retired || !retired_.empty();
+    }
+    bool register_locked(Entry& e)
+    {
+        char *lo, *hi;
+        inner_pages(e, &lo, &hi);
+        const size_t len = (size_t)(hi - lo);
         const auto t0 = std::chrono::steady_clock::now();
         const cudaError_t err = cudaHostRegister(lo, len, cudaHostRegisterPortable);
         if (err != cudaSuccess)
         {
             cudaGetLastError();
-            e.failed = true;
+            // (pages still held by a registration that is being retired on another thread: try again next time)
+            if (err != cudaErrorHostMemoryAlreadyRegistered) e.failed = true;
             return false;
         }
         stat_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -326,28 +381,28 @@ class RegCache
         total_ += len;
         return true;
     }
-    void unregister_locked(Entry& e)
+    // no new copy will use e's pages from here on; the pages themselves are released by flush_retired(), outside the lock
+    bool retire_locked(Entry& e)
     {
-        if (!e.registered) return;
-        if (quiesce_) quiesce_(); // nothing may still be on the wire from / to these pages
-        else cudaDeviceSynchronize();
-        cudaHostUnregister(e.reg_base);
-        cudaGetLastError();
+        if (!e.registered) return false;
+        retired_.push_back(e.reg_base);
         total_ -= e.reg_bytes;
         e.registered = false;
-    }
-    bool evict_other_locked(const Entry& keep)
-    {
-        long best = -1;
-        for (size_t i = 0; i < entries_.size(); ++i)
-        {
-            if (!entries_[i].registered || &entries_[i] == &keep) continue;
-            if (best < 0 || entries_[i].used < entries_[(size_t)best].used) best = (long)i;
-        }
-        if (best < 0) return false;
-        unregister_locked(entries_[(size_t)best]); // stays in the table, unregistered: erasing would move `keep`
-        entries_[(size_t)best].failed = false;
+        e.sightings = 0;
         return true;
+    }
+    void flush_retired()
+    {
+        std::vector<char*> list;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            list.swap(retired_);
+        }
+        if (list.empty()) return;
+        if (quiesce_) quiesce_(); // nothing may still be on the wire from / to these pages
+        else cudaDeviceSynchronize();
+        for (char* p : list) cudaHostUnregister(p);
+        cudaGetLastError();
     }
     bool evict_locked(bool registered_only)
     {
@@ -358,19 +413,20 @@ class RegCache
             if (best < 0 || entries_[i].used < entries_[(size_t)best].used) best = (long)i;
         }
         if (best < 0) return false;
-        unregister_locked(entries_[(size_t)best]);
+        const bool retired = retire_locked(entries_[(size_t)best]);
         entries_.erase(entries_.begin() + best);
         count_.store(entries_.size(), std::memory_order_release);
-        return true;
+        return retired;
     }
     void drop_all_locked()
     {
-        for (Entry& e : entries_) unregister_locked(e);
+        for (Entry& e : entries_) retire_locked(e);
         entries_.clear();
         count_.store(0, std::memory_order_release);
     }
     std::mutex m_;
     std::vector<Entry> entries_;
+    std::vector<char*> retired_;
     std::atomic<size_t> count_{ 0 };
     bool enabled_ = false;
     unsigned long clock_ = 0;
@@ -460,10 +516,9 @@ inline int copy_spans(void* d, const void* h, size_t bytes, const PinnedSpan& sp
 // `r`: the pinned staging ring to use (one per host thread that copies; the default ring belongs to the caller's thread)
 inline int h2d_ring(Ring& r, void* d, const void* h, size_t bytes, cudaStream_t st)
 {
-    if (bytes < SMALL) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
-    const PinnedSpan sp = reg_cache().classify(h, bytes);
-    if (sp.whole) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+    const PinnedSpan sp = bytes < SMALL ? reg_cache().peek(h, bytes) : reg_cache().classify(h, bytes);
     if (sp.mid > 0) return copy_spans(d, h, bytes, sp, true, st);
+    if (sp.whole || (bytes < SMALL && !sp.mixed)) return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
     BBG_CHECK(r.init());
     size_t off = 0;
     while (off < bytes)
@@ -483,7 +538,6 @@ inline int h2d(void* d, const void* h, size_t bytes, cudaStream_t st) { return h
 // registration cache did): callers that promise "the buffer is yours again on return" wait for the copy in that case
 inline bool copy_is_async(const void* h, size_t bytes)
 {
-    if (bytes < SMALL) return is_pinned(h);
     const PinnedSpan sp = reg_cache().peek(h, bytes);
     return sp.whole || sp.mid > 0;
 }
@@ -492,10 +546,9 @@ inline bool caller_pinned_whole(const void* h, size_t bytes) { return reg_cache(
 // returns with the data in h (synchronous for pageable destinations, like cudaMemcpy)
 inline int d2h_ring(Ring& r, void* h, const void* d, size_t bytes, cudaStream_t st)
 {
-    if (bytes < SMALL) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
-    const PinnedSpan sp = reg_cache().classify(h, bytes);
-    if (sp.whole) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+    const PinnedSpan sp = bytes < SMALL ? reg_cache().peek(h, bytes) : reg_cache().classify(h, bytes);
     if (sp.mid > 0) return copy_spans(const_cast<void*>(d), h, bytes, sp, false, st);
+    if (sp.whole || (bytes < SMALL && !sp.mixed)) return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
     BBG_CHECK(r.init());
     const size_t chunks = (bytes + CHUNK - 1) / CHUNK;
     for (size_t k = 0; k < chunks + (RING - 1); ++k)

@@ -1003,6 +1003,7 @@ class PeerWorker
     void run()
     {
         bbg_prof::thread_muted() = true;
+        bbg_hostcopy::RegCache::lookup_only_thread() = true; // a worker never waits for the library to go idle: it IS its work
         int e = (int)cudaSetDevice(device_);
         if (e == 0) e = (int)cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
         if (e == 0)

@@ -518,6 +518,16 @@ def test_host_register_cache(lib):
         buf[:] = x2
         lib.ntt("coset_ifft", lib.ntt("coset_fft", buf))
         assert (buf == x2).all()
+        # sub-ranges of the page-locked buffer, small and large, starting in its unregistered first page and in the middle:
+        # a copy must never span page-locked and pageable memory in one piece
+        for start, log_m in ((0, 12), (0, 15), (3, 12), (1000, 15), (n - (1 << 12), 12)):
+            m = 1 << log_m
+            buf[:] = x
+            view = buf[start:start + m]
+            lib.ntt("fft", view)
+            ref_piece = x[start:start + m].copy()
+            assert (view == H.OracleDomain(m).ntt(H.NTT_OPS["fft"], ref_piece)).all(), (start, log_m)
+            assert (buf[:start] == x[:start]).all() and (buf[start + m:] == x[start + m:]).all()
         lib.host_buffer_forget(buf)
         buf[:] = x
         lib.ntt("coset_fft", buf)

@@ -30,8 +30,22 @@ def srs():
     return path
 
 
+def pow2_threads():
+    """evaluation_domain silently needs a power-of-two OpenMP team (SURVEY.md §5 hazard): with 24 host cores the all-CPU
+    reference prover produces a proof that does not verify"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    t = 1
+    while t * 2 <= cores:
+        t *= 2
+    return t
+
+
 def run(binary, log_gates, repeat=1, env=None, composer="standard"):
     e = dict(os.environ)
+    e["OMP_NUM_THREADS"] = str(pow2_threads())
     e.update(env or {})
     out = subprocess.run([os.path.join(B, binary), str(log_gates), str(repeat), composer], cwd=H.ROOT, capture_output=True, text=True, timeout=600,
                          env=e)
@@ -86,3 +100,27 @@ def test_resident_prover_is_reproducible_across_streams(srs, log_gates, repeat, 
     cpu = run("prover_cpu", log_gates, composer=composer)
     for k, v in cpu["proof"].items():
         assert gpu["proof"][k] == v, k
+
+
+@pytest.mark.parametrize("log_gates,composer", [(14, "standard"), (16, "standard"), (15, "mimc")])
+def test_resident_prover_on_every_gpu_of_the_box(srs, log_gates, composer):
+    """BBG_NUM_GPUS = all devices: the shim brings the library up with bbg_init_multi, the SRS is replicated and every
+    commitment of the resident rounds is cut into point ranges, one per device (scalar_multiplication.cpp:703-728 cuts per
+    thread).  The proof must stay identical to the all-CPU reference's, and reproducible.  On a one-GPU box this is the
+    single-device path (a one-device list), still checked."""
+    import torch
+
+    g = torch.cuda.device_count()
+    need = 64 * ((1 << log_gates) - 1) + 28 + 256 + 64
+    if os.path.getsize(srs) < need:
+        subprocess.check_call([os.path.join(B, "make_srs"), str(1 << log_gates), srs], cwd=H.ROOT)
+    env = {"BBG_NUM_GPUS": str(g), "BBG_MULTI_MIN_POINTS": "4096", "BBG_MULTI_MIN_SHARD": "512"}
+    cpu = run("prover_cpu", log_gates, composer=composer)
+    gpu = run("prover_gpu", log_gates, repeat=4, env=env, composer=composer)
+    assert cpu["verified"] and gpu["verified"] and gpu["repeat_mismatches"] == 0
+    for k, v in cpu["proof"].items():
+        assert gpu["proof"][k] == v, k
+    classic = run("prover_gpu_classic", log_gates, repeat=2, env=env, composer=composer)
+    assert classic["verified"]
+    for k, v in cpu["proof"].items():
+        assert classic["proof"][k] == v, k
