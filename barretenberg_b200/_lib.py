@@ -91,6 +91,17 @@ class Library:
                  "to_mont": 7, "from_mont": 8, "invert": 9, "sub_lazy": 10, "mul": 11, "mul_const_raw": 12}
     G1_OPS = {"mixed_add": 0, "add_doubled": 1, "dbl_dbl": 2, "accumulate": 3, "add": 4, "endo_entry": 5, "dbl_affine": 6}
 
+    def set_srs_precompute(self, on=True):
+        """Fixed-base windows for every registered / cached table from now on (and for those already registered)."""
+        self.check(self.lib.bbg_set_srs_precompute(1 if on else 0))
+
+    def srs_device_table(self, table):
+        """(device pointer, window bits, windows) of a registered host table; windows == 0: no fixed-base tables."""
+        d, c, w = C.c_void_p(), C.c_int(), C.c_int()
+        self.lib.bbg_srs_device_table.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.check(self.lib.bbg_srs_device_table(table.ctypes.data_as(C.c_void_p), C.byref(d), C.byref(c), C.byref(w)))
+        return d.value, c.value, w.value
+
     def device_count(self):
         return int(self.lib.bbg_device_count())
 

@@ -71,7 +71,32 @@ struct SrsEntry
 };
 std::vector<std::pair<const void*, const uint64_t*>> g_prover_srs; // prover -> host_base of the entry it pins
 std::vector<SrsEntry> g_srs;
+// point sets handed over WITHOUT their endomorphism entries (pippenger_low_memory, pippenger_precomputed): the 2n-entry
+// table is built on the device and kept under the caller's address like an auto-cached SRS (n x 64 host bytes behind it)
+struct PlainEntry
+{
+    const uint64_t* host_points;
+    size_t n;
+    void* d_table;
+    uint64_t fingerprint;
+};
+std::vector<PlainEntry> g_plain;
+uint64_t plain_fingerprint(const uint64_t* pts, size_t n)
+{
+    uint64_t h = 1469598103934665603ULL ^ (uint64_t)n;
+    for (size_t s = 0; s < 32; ++s)
+    {
+        const size_t idx = n <= 32 ? (s < n ? s : n - 1) : (s * (n - 1)) / 31;
+        for (int w = 0; w < 8; ++w)
+        {
+            h ^= pts[8 * idx + w];
+            h *= 1099511628211ULL;
+        }
+    }
+    return h;
+}
 bool g_auto_srs = false;
+bool g_srs_precompute = false; // build fixed-base windows for every registered / cached table (bbg_set_srs_precompute)
 constexpr size_t AUTO_SRS_MIN_POINTS = 1024; // below this an upload per call is cheaper than bookkeeping
 constexpr size_t AUTO_SRS_MAX_ENTRIES = 4;
 
@@ -131,6 +156,7 @@ void quiesce_all()
 void srs_drop(size_t i)
 {
     quiesce_all();
+    msm_fixed_base_drop(g_srs[i].d_table);
     msm_multi_drop_replica(g_srs[i].d_table);
     bbg_rt::dev_free(g_srs[i].d_table);
     for (size_t k = 0; k < g_prover_srs.size();)
@@ -151,10 +177,13 @@ int srs_add(const uint64_t* host_base, size_t n, void* d_table, bool automatic)
     s.automatic = automatic;
     s.pins = 0;
     s.fingerprint = table_fingerprint(host_base, n);
-    const int e = msm_multi_replicate(d_table, n * 128, g_stream); // no-op with one device
+    int e = msm_multi_replicate(d_table, n * 128, g_stream); // no-op with one device
+    if (e == 0 && g_srs_precompute) e = msm_fixed_base_build(d_table, n, g_stream);
     if (e != 0)
     {
         bbg_rt::sync(g_stream);
+        msm_fixed_base_drop(d_table);
+        msm_multi_drop_replica(d_table);
         bbg_rt::dev_free(d_table);
         return e;
     }
@@ -296,7 +325,12 @@ int bbg_init_multi(const int* devices, int count)
     if (count == 1) return 0;
     BBG_CHECK(msm_multi_init(devices, count));
     // tables registered before the other devices joined
-    for (const SrsEntry& s : g_srs) BBG_CHECK(msm_multi_replicate(s.d_table, s.n * 128, g_stream));
+    for (const SrsEntry& s : g_srs)
+    {
+        msm_fixed_base_drop(s.d_table); // (its window width depends on the number of devices)
+        BBG_CHECK(msm_multi_replicate(s.d_table, s.n * 128, g_stream));
+        if (g_srs_precompute) BBG_CHECK(msm_fixed_base_build(s.d_table, s.n, g_stream));
+    }
     return 0;
 }
 
@@ -320,6 +354,8 @@ int bbg_shutdown(void)
     g_stage_table.release();
     for (SrsEntry& s : g_srs) bbg_rt::dev_free(s.d_table);
     g_srs.clear();
+    for (PlainEntry& e : g_plain) bbg_rt::dev_free(e.d_table);
+    g_plain.clear();
     g_prover_srs.clear();
     bbg_hostcopy::reg_cache().release();
 #ifndef BBG_EMULATE
@@ -508,6 +544,40 @@ int bbg_set_auto_srs_cache(int enable)
     return 0;
 }
 
+int bbg_set_srs_precompute(int enable)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    g_srs_precompute = enable != 0;
+    quiesce_all();
+    for (const SrsEntry& s : g_srs)
+    {
+        if (g_srs_precompute) BBG_CHECK(msm_fixed_base_build(s.d_table, s.n, g_stream));
+        else msm_fixed_base_drop(s.d_table);
+    }
+    return 0;
+}
+
+int bbg_srs_device_table(const uint64_t* table_2n, void** d_table, int* window_bits, int* windows)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (table_2n == nullptr || d_table == nullptr) return BBG_E_BAD_ARGUMENT;
+    for (const SrsEntry& s : g_srs)
+    {
+        if (table_2n >= s.host_base && table_2n < s.host_base + 16 * s.n)
+        {
+            *d_table = (char*)s.d_table + ((const char*)table_2n - (const char*)s.host_base);
+            int c = 0, W = 0;
+            msm_fixed_base_info(s.d_table, &c, &W);
+            if (window_bits) *window_bits = c;
+            if (windows) *windows = W;
+            return 0;
+        }
+    }
+    return BBG_E_BAD_ARGUMENT;
+}
+
 int bbg_srs_unregister(const uint64_t* table_2n)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -533,7 +603,9 @@ int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, 
 }
 
 // pippenger_low_memory / pippenger_precomputed take the n plain points and apply the endomorphism on the fly
-// (scalar_multiplication.cpp:142-263, :478-573); here the 2n-entry table is built on the device next to the upload
+// (scalar_multiplication.cpp:142-263, :478-573); here the 2n-entry table is built on the device next to the upload, and —
+// with the auto cache on — kept (with its fixed-base windows when bbg_set_srs_precompute is on) for the next call that
+// names the same points
 int bbg_msm_g1_points(const uint64_t* scalars, const uint64_t* points_n, size_t n, uint64_t out_xyz[12])
 {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -543,17 +615,103 @@ int bbg_msm_g1_points(const uint64_t* scalars, const uint64_t* points_n, size_t 
     if (n > 0)
     {
         if (scalars == nullptr || points_n == nullptr) return BBG_E_BAD_ARGUMENT;
-        BBG_CHECK(g_stage_table.ensure(n * 192));
-        char* d_table = (char*)g_stage_table.p;
-        char* d_points = d_table + n * 128;
-        BBG_CHECK(bbg_hostcopy::h2d(d_points, points_n, n * 64, g_stream));
-        BBG_CHECK(g1_build_endo_table_device(d_points, d_table, n, g_stream));
+        const void* d_table = nullptr;
+        for (size_t i = 0; i < g_plain.size() && d_table == nullptr; ++i)
+        {
+            PlainEntry& e = g_plain[i];
+            if (e.host_points != points_n || e.n < n) continue;
+            if (plain_fingerprint(e.host_points, e.n) == e.fingerprint)
+            {
+                d_table = e.d_table;
+                break;
+            }
+            quiesce_all();
+            msm_fixed_base_drop(e.d_table);
+            msm_multi_drop_replica(e.d_table);
+            bbg_rt::dev_free(e.d_table);
+            g_plain.erase(g_plain.begin() + (long)i);
+            break;
+        }
+        if (d_table == nullptr)
+        {
+            const bool keep = g_auto_srs && n >= AUTO_SRS_MIN_POINTS;
+            void* d_tab = nullptr;
+            if (keep) BBG_CHECK(bbg_rt::dev_alloc(&d_tab, n * 128));
+            else
+            {
+                BBG_CHECK(g_stage_table.ensure(n * 192));
+                d_tab = g_stage_table.p;
+            }
+            // the plain points are staged behind the staging table (or, for a kept table, in the scalar staging buffer)
+            void* d_points = nullptr;
+            if (keep)
+            {
+                BBG_CHECK(g_stage_coeffs.ensure(n * 64));
+                d_points = g_stage_coeffs.p;
+            }
+            else
+                d_points = (char*)d_tab + n * 128;
+            int e = bbg_hostcopy::h2d(d_points, points_n, n * 64, g_stream);
+            if (e == 0) e = g1_build_endo_table_device(d_points, d_tab, n, g_stream);
+            if (e == 0 && keep)
+            {
+                if (g_plain.size() >= AUTO_SRS_MAX_ENTRIES)
+                {
+                    quiesce_all();
+                    msm_fixed_base_drop(g_plain[0].d_table);
+                    msm_multi_drop_replica(g_plain[0].d_table);
+                    bbg_rt::dev_free(g_plain[0].d_table);
+                    g_plain.erase(g_plain.begin());
+                }
+                e = bbg_rt::sync(g_stream);
+                if (e == 0) e = msm_multi_replicate(d_tab, n * 128, g_stream);
+                if (e == 0 && g_srs_precompute) e = msm_fixed_base_build(d_tab, n, g_stream);
+                if (e == 0) g_plain.push_back({ points_n, n, d_tab, plain_fingerprint(points_n, n) });
+            }
+            if (e != 0)
+            {
+                if (keep)
+                {
+                    bbg_rt::sync(g_stream);
+                    msm_fixed_base_drop(d_tab);
+                    msm_multi_drop_replica(d_tab);
+                    bbg_rt::dev_free(d_tab);
+                }
+                return e;
+            }
+            d_table = d_tab;
+        }
         BBG_CHECK(g_stage_scalars.ensure(n * 32));
-        BBG_CHECK(bbg_hostcopy::h2d(g_stage_scalars.p, scalars, n * 32, g_stream));
-        BBG_CHECK(msm_device(g_stage_scalars.p, d_table, n, &r, g_stream));
+        int ticket = -1;
+        const void* one[1] = { scalars };
+        BBG_CHECK(msm_launch_any(0, one, true, g_stage_scalars.p, 1, d_table, n, g_stream, &ticket));
+        BBG_CHECK(msm_finish(ticket, &r));
     }
     hostg1::to_normalized_jacobian(r, out_xyz);
     return 0;
+}
+
+// generate_pippenger_precompute_table (scalar_multiplication.cpp:90-129) on the device: table[i * n + j] =
+// 2^((bits_per_bucket + 1)(i + 1)) P_j for i < rounds - 1, rounds = WNAF_SIZE(bits_per_bucket + 1), canonical affine
+int bbg_generate_pippenger_precompute_table(const uint64_t* points_n, uint64_t* table, size_t n, unsigned bits_per_bucket)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    BBG_CHECK(ensure_ready());
+    if (n == 0) return 0;
+    if (points_n == nullptr || table == nullptr || bits_per_bucket < 1 || bits_per_bucket > 30) return BBG_E_BAD_ARGUMENT;
+    const int w = (int)bits_per_bucket + 1;
+    const int rounds = (127 + w) / w; // WNAF_SIZE (wnaf.hpp:5)
+    if (rounds < 2) return 0;
+    void *d_pts = nullptr, *d_out = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc(&d_pts, n * 64));
+    int e = bbg_rt::dev_alloc(&d_out, (size_t)(rounds - 1) * n * 64);
+    if (e == 0) e = bbg_hostcopy::h2d(d_pts, points_n, n * 64, g_stream);
+    if (e == 0) e = g1_precompute_plain_device(d_pts, d_out, n, w, rounds, g_stream);
+    if (e == 0) e = bbg_hostcopy::d2h(table, d_out, (size_t)(rounds - 1) * n * 64, g_stream);
+    if (e == 0) e = bbg_rt::sync(g_stream);
+    bbg_rt::dev_free(d_pts);
+    if (d_out) bbg_rt::dev_free(d_out);
+    return e;
 }
 
 int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* points_tables, size_t n, size_t batches, uint64_t* out_xyz)

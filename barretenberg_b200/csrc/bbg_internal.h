@@ -66,6 +66,12 @@ int msm_multi_device_count();
 int msm_multi_replicate(const void* d_table_primary, size_t bytes, cudaStream_t stream);
 int msm_multi_drop_replica(const void* d_table_primary);
 int msm_multi_quiesce();
+// Fixed-base form (generate_pippenger_precompute_table / pippenger_precomputed, scalar_multiplication.cpp:90-129,
+// :478-573): pre-doubled windows of a table on every device; MSMs that name the table (or a sub-range) then add the digits
+// of all windows into one bucket set.  Build after msm_multi_replicate, drop before msm_multi_drop_replica.
+int msm_fixed_base_build(const void* d_table_primary, size_t n_srs, cudaStream_t stream);
+int msm_fixed_base_drop(const void* d_table_primary);
+int msm_fixed_base_info(const void* d_table_primary, int* c, int* W);
 size_t msm_launch_count();
 // d_points[i] = (start + i * step) * G (affine, canonical), i < n; start / step: Fr Montgomery limbs (host)
 int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* step_mont, void* d_points, size_t n, cudaStream_t stream);
@@ -73,6 +79,8 @@ int g1_generate_progression_device(const uint64_t* start_mont, const uint64_t* s
 int g1_table_from_transcript_device(const void* d_g1_bytes, void* d_table, size_t n, cudaStream_t stream);
 // evaluation_domain::compute_lookup_table (evaluation_domain.cpp:33-54, :172-178): 2 * 2^log_size elements on the device
 int domain_lookup_table_device(void* d_roots, unsigned log_size, cudaStream_t stream);
+// out[i * n + j] = 2^(bits_per_window (i + 1)) P_j, i < rounds - 1 (generate_pippenger_precompute_table's layout)
+int g1_precompute_plain_device(const void* d_points, void* d_out, size_t n, int bits_per_window, int rounds, cudaStream_t stream);
 // table[2i] = P_i, table[2i+1] = (beta x_i, -y_i) on device (generate_pippenger_point_table layout)
 int g1_build_endo_table_device(const void* d_points, void* d_table, size_t n, cudaStream_t stream);
 } // namespace bbg

@@ -64,6 +64,10 @@ struct Plan
     int chunk_log;
     uint32_t chunks_per_window;
     int reduce_outputs; // per window: chunk bits + 2
+    // fixed-base form (a table of pre-doubled windows, below): every window's digits fall into ONE bucket set and entry
+    // (w, j) reads point j of window w's table, entry_stride entries further on
+    int sets;              // bucket sets per MSM: W, or 1 in the fixed-base form
+    uint32_t entry_stride; // 0, or the 2 * n_srs entries of one window's table
 };
 
 // little multi-word helpers for the endomorphism split (portable: host and device)
@@ -142,7 +146,9 @@ BBG_HD uint32_t window_bits(const uint32_t k[4], int pos, int c)
 
 // ---- 1. digits -------------------------------------------------------------------------------------
 // (the counting atomic returns the entry's rank inside its bucket: the scatter then needs no atomics of its own)
-__global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uint32_t NB, uint32_t* digits, uint32_t* ranks, uint32_t* counts)
+// set_stride: NB when every window has its own bucket set, 0 when all windows share one (fixed-base form)
+__global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uint32_t NB, uint32_t set_stride, uint32_t* digits, uint32_t* ranks,
+                                  uint32_t* counts)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -172,7 +178,7 @@ __global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uin
                 // same assumption, wnaf.hpp:11); clamp defensively so no bucket index is ever out of range
                 if (d > NB) d = NB;
                 packed[h] = (d - 1) | neg;
-                rank[h] = atomicAdd(&counts[(size_t)w * NB + (d - 1)], 1u);
+                rank[h] = atomicAdd(&counts[(size_t)w * set_stride + (d - 1)], 1u);
             }
             else
             {
@@ -270,16 +276,25 @@ __global__ void scan_apply_kernel(const uint32_t* in, uint32_t count, const uint
 }
 
 // ---- 3. scatter ------------------------------------------------------------------------------------
-__global__ void msm_scatter_kernel(const uint32_t* digits, const uint32_t* ranks, size_t num_points, int W, uint32_t NB, const uint32_t* offsets,
-                                   uint32_t* sorted)
+// W = windows of the whole (batched) pipeline, W1 = windows of one MSM.  Plain form: window w owns bucket set w and entry
+// j is table entry j.  Fixed-base form (entry_stride != 0): MSM w / W1 owns one bucket set and entry (w mod W1, j) is entry
+// j of that window's pre-doubled table.
+__global__ void msm_scatter_kernel(const uint32_t* digits, const uint32_t* ranks, size_t num_points, int W, int W1, uint32_t NB, uint32_t entry_stride,
+                                   const uint32_t* offsets, uint32_t* sorted)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= num_points * (size_t)W) return;
     const uint32_t d = digits[e];
     if (d == NO_DIGIT) return;
     const size_t w = e / num_points;
-    const uint32_t j = (uint32_t)(e - w * num_points);
-    const size_t b = w * NB + (d & 0x7fffffffu);
+    uint32_t j = (uint32_t)(e - w * num_points);
+    size_t set = w;
+    if (entry_stride != 0)
+    {
+        set = w / (size_t)W1;
+        j += (uint32_t)(w - set * (size_t)W1) * entry_stride;
+    }
+    const size_t b = set * NB + (d & 0x7fffffffu);
     const uint32_t pos = offsets[b] + ranks[e];
     sorted[pos] = j | (d & 0x80000000u);
 }
@@ -443,6 +458,48 @@ __global__ void endo_table_kernel(const fe* points, fe* table, size_t n)
     store_affine(table + 4 * i, p);
     store_affine(table + 4 * i + 2, G1::endo_table_entry(p));
 }
+// ---- fixed-base tables (generate_pippenger_precompute_table, scalar_multiplication.cpp:90-129) -------------------------
+// pre[w][j] = 2^(c w) * table[j] for w < W: with every window's point pre-doubled, the digits of ALL windows of a scalar
+// can be added into one bucket set (pippenger_precomputed, :478-573, does exactly that on the CPU) — no doublings between
+// windows, 1 / W of the buckets to reduce, and room for a wider window.  One thread per base point: c doublings per window,
+// one inversion per stored point; the odd (endomorphism) entries follow from the even ones, phi(2^k P) = 2^k phi(P).
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const fe* table, fe* pre, size_t n, int c, int W)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const affine_pt p = load_affine(table + 4 * i);
+    store_affine(pre + 4 * i, p);
+    store_affine(pre + 4 * i + 2, load_affine(table + 4 * i + 2));
+    xyzz_pt acc = G1::from_affine(p);
+    for (int w = 1; w < W; ++w)
+    {
+        for (int k = 0; k < c; ++k) acc = G1::dbl(acc);
+        const affine_pt a = G1::to_affine(acc);
+        fe* dst = pre + (size_t)w * 4 * n + 4 * i;
+        store_affine(dst, a);
+        store_affine(dst + 2, G1::endo_table_entry(a));
+        acc = G1::from_affine(a); // (keeps zz = 1: the next doublings start from the cheap form)
+    }
+}
+
+// generate_pippenger_precompute_table's own output layout (scalar_multiplication.cpp:90-129): n PLAIN points in,
+// table[i * n + j] = 2^((bits + 1)(i + 1)) * P_j for i < rounds - 1, canonical affine coordinates (the reference's
+// batch_normalize leaves x z^-2, y z^-3 fully reduced).
+__global__ void __launch_bounds__(128) precompute_plain_kernel(const fe* points, fe* out, size_t n, int bits_per_window, int rounds)
+{
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const affine_pt p = load_affine(points + 2 * j);
+    xyzz_pt acc = G1::affine_is_infinity(p) ? G1::infinity() : G1::from_affine(p);
+    for (int i = 0; i + 1 < rounds; ++i)
+    {
+        for (int k = 0; k < bits_per_window; ++k) acc = G1::dbl(acc);
+        const affine_pt a = G1::to_affine(acc);
+        store_affine(out + 2 * ((size_t)i * n + j), a);
+        if (!G1::affine_is_infinity(a)) acc = G1::from_affine(a);
+    }
+}
+
 // ---- SRS loader ------------------------------------------------------------------------------
 // io::read_transcript + read_g1_elements_from_buffer (io/io.hpp:76-98, :157-182) followed by
 // generate_pippenger_point_table (scalar_multiplication.cpp:131-140) in one pass over the raw transcript bytes:
@@ -602,10 +659,19 @@ struct MsmTicket
 
 // Everything one device needs to run MSMs: the primary device owns g_primary, every other device of a multi-GPU
 // library instance has its own inside its worker (below).
+// a point table of this device with its pre-doubled windows (fixed-base form)
+struct FixedBase
+{
+    const char* base;  // the plain 2 * n_srs-entry table the MSM calls name
+    size_t n_srs;
+    int c, W;
+    void* pre;         // W x 2 * n_srs entries
+};
 struct MsmContext
 {
     Workspace ws[2];
     MsmTicket tickets[MSM_TICKETS];
+    std::vector<FixedBase> fixed; // (touched by the thread that drives the device only)
 };
 MsmContext g_primary;
 
@@ -629,6 +695,8 @@ int ticket_host_buffer(MsmTicket& t, size_t bytes)
 void context_release(MsmContext& ctx)
 {
     for (Workspace& w : ctx.ws) w.release();
+    for (FixedBase& f : ctx.fixed) bbg_rt::dev_free(f.pre);
+    ctx.fixed.clear();
     for (MsmTicket& t : ctx.tickets)
     {
 #ifndef BBG_EMULATE
@@ -711,14 +779,50 @@ uint32_t pick_slice(size_t max_entries)
     return S;
 }
 
-Plan make_plan(size_t n)
+// Window width of a fixed-base table for MSMs of about n points: one bucket set of 2^(c-1) buckets whatever the number of
+// windows, so the per-bucket cost is paid once and c can grow (same cost constants as pick_windows).
+void pick_windows_fixed_base(size_t n, int& c_out, int& W_out)
+{
+    double best = -1;
+    c_out = 8;
+    W_out = 16;
+    for (int c = 8; c <= 22; ++c)
+    {
+        int W = (128 + c - 1) / c;
+        while ((W - 1) * c >= 127) --W;
+        if (W > 16) continue;
+        const int top_bits = 127 - (W - 1) * c;
+        const double buckets = (double)((size_t)1 << (c - 1));
+        const double avg = (double)W * 2.0 * (double)n / buckets;
+        double cost = (double)W * 2.0 * (double)n * 1.13 + buckets * (11.0 + 0.3 * avg / 64.0);
+        if (top_bits < 4) cost += 2.0 * (double)n * (4 - top_bits) / 8.0; // (a thin top window costs a table, not a bucket set)
+        if (best < 0 || cost < best)
+        {
+            best = cost;
+            c_out = c;
+            W_out = W;
+        }
+    }
+}
+
+// fixed_c != 0: the fixed-base form over a table pre-doubled for that window width
+Plan make_plan(size_t n, int fixed_c = 0, uint32_t entry_stride = 0)
 {
     Plan pl;
     pl.n = n;
     pl.num_points = 2 * n;
-    pick_windows(n, pl.c, pl.W);
+    if (fixed_c != 0)
+    {
+        pl.c = fixed_c;
+        pl.W = (128 + fixed_c - 1) / fixed_c;
+        while ((pl.W - 1) * pl.c >= 127) --pl.W;
+    }
+    else
+        pick_windows(n, pl.c, pl.W);
+    pl.sets = fixed_c != 0 ? 1 : pl.W;
+    pl.entry_stride = fixed_c != 0 ? entry_stride : 0;
     pl.NB = 1u << (pl.c - 1);
-    pl.total_buckets = pl.NB * (uint32_t)pl.W;
+    pl.total_buckets = pl.NB * (uint32_t)pl.sets;
     pl.max_entries = pl.num_points * (size_t)pl.W;
     pl.S = pick_slice(pl.max_entries);
     pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
@@ -748,12 +852,26 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     }
     Workspace& g_ws = ctx.ws[workspace];
     if (2 * n > ((size_t)1 << 28)) return 1008;
-    const Plan single = make_plan(n);
+    // a table registered with pre-doubled windows (msm_fixed_base_build) switches to the fixed-base form
+    int fixed_c = 0;
+    uint32_t entry_stride = 0;
+    for (const FixedBase& f : ctx.fixed)
+    {
+        if ((const char*)d_table >= f.base && (const char*)d_table + n * 128 <= f.base + f.n_srs * 128)
+        {
+            fixed_c = f.c;
+            entry_stride = (uint32_t)(2 * f.n_srs);
+            d_table = (const char*)f.pre + ((const char*)d_table - f.base);
+            break;
+        }
+    }
+    const Plan single = make_plan(n, fixed_c, entry_stride);
     if (single.c < 2 || single.c > 22 || single.W < 1 || single.W > 64 || (single.W - 1) * single.c >= 127 || single.W * single.c < 128)
         return 1009; // planner invariant
     if (single.max_entries * batch >= ((size_t)1 << 32) || (size_t)single.total_buckets * batch >= ((size_t)1 << 31)) return 1008;
     Plan pl = single; // the batch as one MSM with batch * W windows
     pl.W = single.W * (int)batch;
+    pl.sets = single.sets * (int)batch;
     pl.total_buckets = single.total_buckets * (uint32_t)batch;
     pl.max_entries = single.max_entries * batch;
     pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
@@ -773,10 +891,10 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     const size_t o_head = carve(pl.max_slices * 128);
     const size_t o_tail = carve(pl.max_slices * 128);
     const size_t o_work_list = carve((pl.max_slices / FIXUP_SERIAL_SPAN + 2) * 4);
-    const uint32_t total_chunks = pl.chunks_per_window * (uint32_t)pl.W;
+    const uint32_t total_chunks = pl.chunks_per_window * (uint32_t)pl.sets;
     const size_t o_A = carve((size_t)total_chunks * 128);
     const size_t o_V = carve((size_t)total_chunks * 128);
-    const size_t red_count = (size_t)pl.W * pl.reduce_outputs;
+    const size_t red_count = (size_t)pl.sets * pl.reduce_outputs;
     const size_t o_red = carve(red_count * 128);
     BBG_CHECK(g_ws.ensure(off));
     char* ws = (char*)g_ws.p;
@@ -801,7 +919,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
         bbg_prof::Scope prof(bbg_prof::MSM_DIGITS, st);
         for (size_t b = 0; b < batch; ++b)
             BBG_LAUNCH_NOSYNC(msm_digits_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_scalars[b], n, pl.c, single.W, pl.NB,
-                              digits + b * single.max_entries, ranks + b * single.max_entries, counts + b * single.total_buckets);
+                              pl.entry_stride != 0 ? 0u : pl.NB, digits + b * single.max_entries, ranks + b * single.max_entries, counts + b * single.total_buckets);
     }
     bbg_prof::Scope* prof_scan = new bbg_prof::Scope(bbg_prof::MSM_SCAN, st);
     BBG_LAUNCH(scan_block_sums_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, spine);
@@ -811,7 +929,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     {
         bbg_prof::Scope prof(bbg_prof::MSM_SCATTER, st);
         BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, (const uint32_t*)ranks,
-                          pl.num_points, pl.W, pl.NB, (const uint32_t*)offsets, sorted);
+                          pl.num_points, pl.W, single.W, pl.NB, pl.entry_stride, (const uint32_t*)offsets, sorted);
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_ACCUMULATE, st);
@@ -831,7 +949,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_REDUCE, st);
-        BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.W), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V,
+        BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.sets), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V,
                    pl.chunks_per_window, pl.reduce_outputs - 2, red);
     }
     g_msm_launches += 9 + batch;
@@ -849,6 +967,41 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     tk.red_count = red_count;
     tk.pending = true;
     return 0;
+}
+
+// Build the pre-doubled windows of a table on the current device and remember them in `ctx` (fixed-base form).
+int context_fixed_base_build(MsmContext& ctx, const void* d_table, size_t n_srs, int c, int W, cudaStream_t st)
+{
+    for (const FixedBase& f : ctx.fixed)
+        if (f.base == (const char*)d_table) return 0;
+    FixedBase f;
+    f.base = (const char*)d_table;
+    f.n_srs = n_srs;
+    f.c = c;
+    f.W = W;
+    f.pre = nullptr;
+    BBG_CHECK(bbg_rt::dev_alloc(&f.pre, (size_t)W * n_srs * 128));
+    BBG_LAUNCH_NOSYNC(msm_precompute_kernel, dim3((unsigned)((n_srs + 127) / 128)), dim3(128), st, (const fe*)d_table, (fe*)f.pre, n_srs, c, W);
+    g_msm_launches += 1;
+    int e = bbg_rt::last_error();
+    if (e == 0) e = bbg_rt::sync(st);
+    if (e != 0)
+    {
+        bbg_rt::dev_free(f.pre);
+        return e;
+    }
+    ctx.fixed.push_back(f);
+    return 0;
+}
+void context_fixed_base_drop(MsmContext& ctx, const void* d_table)
+{
+    for (size_t i = 0; i < ctx.fixed.size(); ++i)
+    {
+        if (ctx.fixed[i].base != (const char*)d_table) continue;
+        bbg_rt::dev_free(ctx.fixed[i].pre);
+        ctx.fixed.erase(ctx.fixed.begin() + (long)i);
+        return;
+    }
 }
 
 // ---- 7. host finish: waits for the ticket's kernels, folds the windows of every MSM of the batch ---------------------
@@ -873,9 +1026,9 @@ int context_finish(MsmContext& ctx, int ticket, hostg1::hxyzz* out)
     for (size_t b = 0; b < batch; ++b)
     {
         hostg1::hxyzz result = hostg1::infinity();
-        for (int w = single.W - 1; w >= 0; --w)
+        for (int w = single.sets - 1; w >= 0; --w) // (fixed-base form: one set, nothing to double)
         {
-            const hostg1::hxyzz* rw = r_data + (b * (size_t)single.W + (size_t)w) * pl.reduce_outputs;
+            const hostg1::hxyzz* rw = r_data + (b * (size_t)single.sets + (size_t)w) * pl.reduce_outputs;
             // sum_t t * A_t = sum_r 2^r T_r   (Horner from the top bit)
             hostg1::hxyzz tsum = hostg1::infinity();
             for (int r = bits - 1; r >= 0; --r)
@@ -887,7 +1040,8 @@ int context_finish(MsmContext& ctx, int ticket, hostg1::hxyzz* out)
             // bucket value = t * chunk + v + 1
             hostg1::hxyzz sw = hostg1::add(hostg1::add(tsum, rw[bits]), rw[bits + 1]);
             // result = 2^c * result + S_w   (reference :619-639, here with plain c-bit windows)
-            for (int i = 0; i < pl.c; ++i) result = hostg1::dbl(result);
+            if (w != single.sets - 1)
+                for (int i = 0; i < pl.c; ++i) result = hostg1::dbl(result);
             result = hostg1::add(result, sw);
         }
         out[b] = result;
@@ -910,6 +1064,7 @@ int context_finish(MsmContext& ctx, int ticket, hostg1::hxyzz* out)
 constexpr int PEER_INFLIGHT = 4;
 struct PeerJob
 {
+    int kind = 0; // 0: an MSM shard;  1: build the fixed-base windows of d_table (n_srs = count, c = batch, W = lo);  2: drop them
     const void* src[4] = {};
     size_t batch = 0;
     size_t lo = 0, count = 0; // scalar index range of this shard
@@ -1036,6 +1191,22 @@ class PeerWorker
                 else if (stop_ && inflight.empty())
                     break;
             }
+            if (j != nullptr && j->kind != 0)
+            {
+                // table maintenance: nothing of ours may be in flight on this device while tables come and go
+                while (!inflight.empty())
+                {
+                    Inflight f = inflight.front();
+                    inflight.erase(inflight.begin());
+                    complete(f.job, context_finish(ctx_, f.ticket, f.job->out));
+                }
+                int err = 0;
+                if (j->kind == 1) err = context_fixed_base_build(ctx_, j->d_table, j->count, (int)j->batch, (int)j->lo, stream_);
+                else context_fixed_base_drop(ctx_, j->d_table);
+                if (err != 0) cudaGetLastError();
+                complete(j, err);
+                continue;
+            }
             if (j != nullptr)
             {
                 int ticket = -1;
@@ -1114,6 +1285,7 @@ PeerJob* job_alloc()
         g_multi.free_jobs.pop_back();
         j->done.store(0, std::memory_order_relaxed);
         j->err = 0;
+        j->kind = 0;
         return j;
     }
     return new PeerJob();
@@ -1254,6 +1426,124 @@ int msm_multi_drop_replica(const void* d_base0)
 #else
     (void)d_base0;
 #endif
+    return 0;
+}
+
+// Fixed-base tables for a registered point table: pre-doubled windows on every device of the instance (each device works
+// on about n_srs / devices points per MSM, which sets the window width).  A no-op when the table would not fit the memory
+// budget (W x the table; BBG_SRS_PRECOMPUTE_MAX_MB, default a quarter of the free device memory).
+int msm_fixed_base_build(const void* d_table_primary, size_t n_srs, cudaStream_t st)
+{
+    if (n_srs < 1024) return 0;
+    size_t devices = 1;
+#ifndef BBG_EMULATE
+    devices += g_multi.peers.size();
+    if (n_srs < g_multi.min_points) devices = 1;
+    while (devices > 1 && n_srs / devices < g_multi.min_shard) --devices;
+#endif
+    int c = 0, W = 0;
+    pick_windows_fixed_base(n_srs / devices, c, W);
+    if (const char* e = getenv("BBG_MSM_FIXED_WINDOW")) // development override
+    {
+        const int v = atoi(e);
+        if (v >= 8 && v <= 22)
+        {
+            c = v;
+            W = (128 + c - 1) / c;
+            while ((W - 1) * c >= 127) --W;
+        }
+    }
+    const size_t bytes = (size_t)W * n_srs * 128;
+    if ((size_t)(W - 1) * 2 * n_srs + 2 * n_srs >= ((size_t)1 << 31)) return 0; // entry indices carry the sign in bit 31
+    size_t budget = 0;
+    if (const char* e = getenv("BBG_SRS_PRECOMPUTE_MAX_MB")) budget = (size_t)atol(e) << 20;
+#ifndef BBG_EMULATE
+    if (budget == 0)
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = free_b / 4;
+    }
+#else
+    if (budget == 0) budget = (size_t)1 << 30;
+#endif
+    if (bytes > budget) return 0;
+    BBG_CHECK(context_fixed_base_build(g_primary, d_table_primary, n_srs, c, W, st));
+#ifndef BBG_EMULATE
+    if (const Replica* rep = find_replica(d_table_primary, n_srs * 128))
+    {
+        if (rep->base0 == (const char*)d_table_primary)
+        {
+            std::vector<PeerJob*> jobs;
+            for (size_t i = 0; i < g_multi.peers.size(); ++i)
+            {
+                PeerJob* j = job_alloc();
+                j->kind = 1;
+                j->d_table = rep->peer[i];
+                j->count = n_srs;
+                j->batch = (size_t)c;
+                j->lo = (size_t)W;
+                jobs.push_back(j);
+                g_multi.peers[i]->submit(j);
+            }
+            int e = 0;
+            for (PeerJob* j : jobs)
+            {
+                while (!j->done.load(std::memory_order_acquire)) std::this_thread::yield();
+                if (e == 0) e = j->err;
+                job_free(j);
+            }
+            if (e != 0)
+            {
+                // all or nothing: a device without the windows would compute the same sums the slow way, which is fine, but
+                // an allocation failure is worth reporting
+                return e;
+            }
+        }
+    }
+#endif
+    return 0;
+}
+
+int msm_fixed_base_drop(const void* d_table_primary)
+{
+#ifndef BBG_EMULATE
+    if (const Replica* rep = find_replica(d_table_primary, 1))
+    {
+        if (rep->base0 == (const char*)d_table_primary)
+        {
+            std::vector<PeerJob*> jobs;
+            for (size_t i = 0; i < g_multi.peers.size(); ++i)
+            {
+                PeerJob* j = job_alloc();
+                j->kind = 2;
+                j->d_table = rep->peer[i];
+                jobs.push_back(j);
+                g_multi.peers[i]->submit(j);
+            }
+            for (PeerJob* j : jobs)
+            {
+                while (!j->done.load(std::memory_order_acquire)) std::this_thread::yield();
+                job_free(j);
+            }
+        }
+    }
+#endif
+    context_fixed_base_drop(g_primary, d_table_primary);
+    return 0;
+}
+
+// (c, W) of the fixed-base windows behind a primary-device table pointer; 0 when there are none
+int msm_fixed_base_info(const void* d_table_primary, int* c, int* W)
+{
+    for (const FixedBase& f : g_primary.fixed)
+    {
+        if ((const char*)d_table_primary >= f.base && (const char*)d_table_primary < f.base + f.n_srs * 128)
+        {
+            if (c) *c = f.c;
+            if (W) *W = f.W;
+            return 1;
+        }
+    }
     return 0;
 }
 
@@ -1429,6 +1719,14 @@ int g1_table_from_transcript_device(const void* d_g1_bytes, void* d_table, size_
 {
     if (n == 0) return 0;
     BBG_LAUNCH_NOSYNC(srs_from_transcript_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const uint8_t*)d_g1_bytes, (fe*)d_table, n);
+    g_msm_launches += 1;
+    return bbg_rt::last_error();
+}
+
+int g1_precompute_plain_device(const void* d_points, void* d_out, size_t n, int bits_per_window, int rounds, cudaStream_t st)
+{
+    if (n == 0 || rounds < 2) return 0;
+    BBG_LAUNCH_NOSYNC(precompute_plain_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), st, (const fe*)d_points, (fe*)d_out, n, bits_per_window, rounds);
     g_msm_launches += 1;
     return bbg_rt::last_error();
 }

@@ -9,8 +9,9 @@
 //   -Dgenerate_pippenger_point_table=cpu_reference_generate_pippenger_point_table
 //   -Dalt_pippenger=cpu_reference_alt_pippenger -Dpippenger_low_memory=cpu_reference_pippenger_low_memory
 //   -Dpippenger_precomputed=cpu_reference_pippenger_precomputed
+//   -Dgenerate_pippenger_precompute_table=cpu_reference_generate_pippenger_precompute_table
 // (or the objcopy --redefine-sym form of INTEGRATION.md) so its other helper symbols (compute_wnaf_state, pippenger_internal,
-// generate_pippenger_precompute_table, ...) keep their reference CPU bodies, and add this file for the six names above.  Replace pippenger and
+// ...) keep their reference CPU bodies, and add this file for the seven names above.  Replace pippenger and
 // batched_scalar_multiplications TOGETHER (the reference's batched version calls pippenger from inside an OpenMP
 // region with sub-range pointers, scalar_multiplication.cpp:731-738).
 //
@@ -97,10 +98,28 @@ g1::element pippenger_low_memory(fr::field_t* scalars, g1::affine_element* point
     if (e != 0) die("pippenger_low_memory", e);
     return out;
 }
+// scalar_multiplication.cpp:90-129: the caller-visible table of pre-doubled points, computed on the device and written in
+// the reference's layout (table[i * n + j] = 2^((bits + 1)(i + 1)) P_j, canonical affine — byte for byte the reference's
+// output), and the same vector of round pointers (:118-124).
+std::vector<g1::affine_element*> generate_pippenger_precompute_table(g1::affine_element* points, g1::affine_element* table, size_t num_points,
+                                                                     size_t bits_per_bucket)
+{
+    ensure_init();
+    bbg_shim::Timer timer("generate_pippenger_precompute_table");
+    const size_t num_rounds = (127 + bits_per_bucket + 1) / (bits_per_bucket + 1); // WNAF_SIZE(bits_per_bucket + 1)
+    int e = bbg_generate_pippenger_precompute_table((const uint64_t*)points, (uint64_t*)table, num_points, (unsigned)bits_per_bucket);
+    if (e != 0) die("generate_pippenger_precompute_table", e);
+    std::vector<g1::affine_element*> result(num_rounds);
+    result[num_rounds - 1] = points;
+    for (size_t i = 0; i + 1 < num_rounds; ++i) result[num_rounds - 2 - i] = &table[i * num_points];
+    return result;
+}
+
 // scalar_multiplication.cpp:478-488: round_points[r] = 2^((bits + 1)(num_rounds - 1 - r)) P, the last entry being the n
-// plain points themselves (:120-124).  The sum does not depend on how the windows are laid out, so the GPU MSM runs on
-// that last entry; the pre-doubled tables of generate_pippenger_precompute_table (kept as the reference's CPU body) are
-// a CPU-side device to save doublings and are not read.
+// plain points themselves (:120-124).  The sum does not depend on the window width, so the device runs its own fixed-base
+// form: the first call over a point set builds the 2n-entry table and the pre-doubled windows for the device's own width
+// in HBM and keeps them under the points' address (bbg_msm_g1_points; bbg_set_srs_precompute), later calls reuse them.
+// The caller's CPU-side tables (round_points[0 .. num_rounds - 2]) are not read.
 g1::element pippenger_precomputed(fr::field_t* scalars, const std::vector<g1::affine_element*>& round_points, const size_t num_initial_points)
 {
     ensure_init();

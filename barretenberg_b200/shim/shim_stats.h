@@ -81,6 +81,7 @@ inline Stats& stats()
 //   BBG_DEVICE=d          primary CUDA device (default 0)
 //   BBG_NUM_GPUS=g        drive g GPUs of the box, devices d .. d+g-1: MSMs over the SRS are cut into point ranges, one per
 //                         device (bbg_init_multi; the reference's callers get all cores the same way)
+//   BBG_SRS_PRECOMPUTE=0  plain Pippenger windows instead of the fixed-base tables built per ReferenceString
 //   BBG_HOST_REGISTER=0   do not page-lock long-lived caller buffers in place (on by default in the shims; a prover
 //                         linked with -Wl,--wrap=free gets host_buffer_free_wrap.cpp's release hook)
 inline int ensure_library()
@@ -97,6 +98,8 @@ inline int ensure_library()
     for (int i = 0; i < count; ++i) list[i] = first + i;
     int e = count > 1 ? bbg_init_multi(list, count) : bbg_init(first);
     if (e == 0) e = bbg_set_auto_srs_cache(1);
+    const char* pre = getenv("BBG_SRS_PRECOMPUTE");
+    if (e == 0 && !(pre != nullptr && pre[0] == '0')) e = bbg_set_srs_precompute(1);
     const char* reg = getenv("BBG_HOST_REGISTER");
     if (e == 0 && !(reg != nullptr && reg[0] == '0')) e = bbg_set_host_register_cache(1);
     if (e == 0) stats().after_init();

@@ -100,12 +100,30 @@ int bbg_srs_unregister(const uint64_t* table_2n);
  * the first time an MSM sees it; every hit re-checks a fingerprint of sampled host entries, so a buffer that was
  * freed and rewritten behind the same address is re-uploaded, never trusted. */
 int bbg_set_auto_srs_cache(int enable);
+/* Fixed-base form for registered / cached tables (the GPU side of generate_pippenger_precompute_table and
+ * pippenger_precomputed, scalar_multiplication.cpp:90-129, :478-573; reference test test_scalar_multiplication.cpp:233-269):
+ * with the switch on, every table that is registered (or auto-cached) also gets its pre-doubled windows
+ * pre[w][j] = 2^(c w) table[j] built on the device, W x the table's memory, on every device of the instance.  MSMs that
+ * name such a table, or a sub-range of it, then add the digits of ALL windows of a scalar into one bucket set — no
+ * doublings between windows, 1 / W of the buckets to reduce, a wider window — and give the same group element, hence
+ * the same normalised output.  The SRS of a prover is fixed, so this is built once per ReferenceString.  Off by default
+ * (the shims switch it on; BBG_SRS_PRECOMPUTE=0 keeps it off); skipped silently for a table whose windows would not fit
+ * BBG_SRS_PRECOMPUTE_MAX_MB (default: a quarter of the free device memory). */
+int bbg_set_srs_precompute(int enable);
+/* device copy of a registered table (or of the sub-range starting at the given entry), for device-resident callers of
+ * bbg_msm_g1_dev / _partial_dev*; window_bits / windows (may be NULL) = the fixed-base windows behind it, 0 when none */
+int bbg_srs_device_table(const uint64_t* table_2n, void** d_table, int* window_bits, int* windows);
 /* sum_i scalars[i] * P_i over table entries points_table[0 .. 2n); out_xyz = 12 limbs, normalised */
 int bbg_msm_g1(const uint64_t* scalars, const uint64_t* points_table, size_t n, uint64_t out_xyz[12]);
 /* the same sum over n PLAIN affine points (64 bytes each, no endomorphism entries): what pippenger_low_memory and
  * pippenger_precomputed are handed (scalar_multiplication.hpp:52, :79-81; .cpp:142-263, :478-573 apply the endomorphism on
  * the fly); the 2n-entry table is built on the device.  Unlike pippenger_low_memory the scalars are not overwritten. */
 int bbg_msm_g1_points(const uint64_t* scalars, const uint64_t* points_n, size_t n, uint64_t out_xyz[12]);
+/* generate_pippenger_precompute_table (scalar_multiplication.hpp:83-86, .cpp:90-129): from n plain points,
+ * table[i * n + j] = 2^((bits_per_bucket + 1)(i + 1)) P_j for i < WNAF_SIZE(bits_per_bucket + 1) - 1, canonical affine
+ * coordinates — byte for byte what the reference writes.  (The device keeps its own fixed-base windows for the MSM itself,
+ * bbg_set_srs_precompute; this call fills the caller-visible table.) */
+int bbg_generate_pippenger_precompute_table(const uint64_t* points_n, uint64_t* table, size_t n, unsigned bits_per_bucket);
 /* `batches` MSMs of the same size n (multiplication_state[], scalar_multiplication.hpp:88-94) */
 int bbg_msm_g1_batched(const uint64_t* const* scalars, const uint64_t* const* points_tables, size_t n, size_t batches,
                        uint64_t* out_xyz /* batches x 12 */);

@@ -26,6 +26,8 @@ g1::element cpu_reference_alt_pippenger(fr::field_t* scalars, g1::affine_element
 g1::element cpu_reference_pippenger_low_memory(fr::field_t* scalars, g1::affine_element* points, size_t num_points);
 g1::element cpu_reference_pippenger_precomputed(fr::field_t* scalars, const std::vector<g1::affine_element*>& round_points, const size_t num_initial_points);
 void cpu_reference_generate_pippenger_point_table(g1::affine_element* points, g1::affine_element* table, size_t num_points);
+std::vector<g1::affine_element*> cpu_reference_generate_pippenger_precompute_table(g1::affine_element* points, g1::affine_element* table,
+                                                                                   size_t num_points, size_t bits_per_bucket);
 void cpu_reference_batched_scalar_multiplications(multiplication_state* mul_state, size_t num_batches);
 } // namespace scalar_multiplication
 } // namespace barretenberg
@@ -113,12 +115,23 @@ int main(int argc, char** argv)
     {
         const size_t bits = scalar_multiplication::get_optimal_bucket_width(n);
         const size_t rounds = (127 + bits) / (bits + 1);
-        g1::affine_element* pre = (g1::affine_element*)aligned_alloc(32, sizeof(g1::affine_element) * n * (rounds - 1) + 64);
+        const size_t pre_bytes = sizeof(g1::affine_element) * n * (rounds - 1);
+        g1::affine_element* pre = (g1::affine_element*)aligned_alloc(32, pre_bytes + 64);
+        g1::affine_element* pre_cpu = (g1::affine_element*)aligned_alloc(32, pre_bytes + 64);
+        // the table itself: device-built vs the reference's CPU body, byte for byte, and the same round pointers
         std::vector<g1::affine_element*> round_points = scalar_multiplication::generate_pippenger_precompute_table(plain, pre, n, bits);
-        const g1::element got_pre = scalar_multiplication::pippenger_precomputed(scalars, round_points, n);
-        memcpy(scratch, scalars, sizeof(fr::field_t) * n);
-        ok_pre = same_point(got_pre, scalar_multiplication::cpu_reference_pippenger_precomputed(scratch, round_points, n)) && same_point(got_pre, expect);
+        std::vector<g1::affine_element*> round_cpu = scalar_multiplication::cpu_reference_generate_pippenger_precompute_table(plain, pre_cpu, n, bits);
+        ok_pre = round_points.size() == round_cpu.size() && round_points.size() == rounds && memcmp(pre, pre_cpu, pre_bytes) == 0;
+        for (size_t r = 0; ok_pre && r < rounds; ++r)
+            ok_pre = r + 1 == rounds ? (round_points[r] == plain && round_cpu[r] == plain) : (round_points[r] - pre == round_cpu[r] - pre_cpu);
+        for (int rep = 0; rep < 2; ++rep) // second call: the device's own fixed-base tables are cached behind `plain`
+        {
+            const g1::element got_pre = scalar_multiplication::pippenger_precomputed(scalars, round_points, n);
+            memcpy(scratch, scalars, sizeof(fr::field_t) * n);
+            ok_pre = ok_pre && same_point(got_pre, scalar_multiplication::cpu_reference_pippenger_precomputed(scratch, round_cpu, n)) && same_point(got_pre, expect);
+        }
         free(pre);
+        free(pre_cpu);
     }
 
     // batched_scalar_multiplications: 5 MSMs (test_scalar_multiplication.cpp:272-313), outputs already normalised

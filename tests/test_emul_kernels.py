@@ -338,3 +338,43 @@ def test_compute_kate_opening_coefficients(emu, n):
     got, f = lib.compute_kate_opening_coefficients(src, z)
     assert (f == f_ref).all()
     assert (got == _canonical(want)).all()
+
+
+@pytest.mark.parametrize("window", [0, 9, 13])
+def test_msm_fixed_base_windows(emu, window, monkeypatch):
+    """Fixed-base form (generate_pippenger_precompute_table / pippenger_precomputed, scalar_multiplication.cpp:90-129,
+    :478-573): tables registered while bbg_set_srs_precompute is on get pre-doubled windows, and every MSM over them — whole,
+    sub-range, batched, degenerate scalars — must equal the plain Pippenger result and the oracle.  window = 0: the
+    planner's own width; others force a width so that several window counts and top-window sizes are exercised."""
+    if window:
+        monkeypatch.setenv("BBG_MSM_FIXED_WINDOW", str(window))
+    n = 1300
+    table, a0, d = H.generator_multiples_table(55, n)
+    emu.set_srs_precompute(True)
+    try:
+        keep = emu.srs_register(table)
+        d_ptr, c, w = emu.srs_device_table(keep)
+        assert w >= 6 and c * w >= 128 and (not window or c == window)
+        sc = H.random_scalars_mont(56, n)
+        sc[1] = 0
+        sc[2] = sc[3]
+        sc[4] = H.to_limbs(H.from_limbs(sc[4]) + H.FR_MODULUS)
+        exp = H.oracle_msm(sc, table)
+        assert (emu.msm(sc, keep) == exp).all()
+        # sub-range of the registered table
+        off, m = 301, 700
+        assert (emu.msm(np.ascontiguousarray(sc[:m]), keep[2 * off:], m) == H.oracle_msm(np.ascontiguousarray(sc[:m]), np.ascontiguousarray(table[2 * off:2 * (off + m)]))).all()
+        # batched: one bucket set per MSM of the batch
+        scs = [H.random_scalars_mont(60 + i, n) for i in range(3)]
+        got = emu.msm_batched(scs, [keep] * 3)
+        for g_, s_ in zip(got, scs):
+            assert (g_ == H.oracle_msm(s_, table)).all()
+        # one digit value shared by every scalar, and all-zero scalars
+        same = np.tile(H.random_scalars_mont(99, 1)[0], (n, 1))
+        assert (emu.msm(same, keep) == H.closed_form_msm(same, a0, d)).all()
+        assert H.is_infinity(emu.msm(np.zeros((n, 4), dtype=np.uint64), keep))
+        emu.srs_unregister(keep)
+        # the same table, unregistered: plain Pippenger windows, same point
+        assert (emu.msm(sc, table) == exp).all()
+    finally:
+        emu.set_srs_precompute(False)
