@@ -6,7 +6,7 @@
 //                      barretenberg_b200/shim/*.cpp -> libbbgpu.so           (the drop-in under test)
 // Circuit: the one of test/benchmarks/bench_plonk.cpp:25-37, with SEEDED witnesses instead of getentropy so both
 // binaries prove the same statement; the prover draws no randomness, so the two proofs must be identical.
-//   usage: prover_harness <log2_gates> [repeat] [standard|bool|mimc|extended]
+//   usage: prover_harness <log2_gates> [repeat] [standard|bool|bool_degenerate|mimc|extended]
 // The three other composers exercise the bool / MiMC / sequential widgets with the circuits of the reference's own
 // composer tests (test/composer/test_{bool,mimc,extended}_composer.cpp), scaled to ~2^log2_gates gates and seeded.
 // prints one JSON line: sizes, timings, verify result and every proof element (hex limbs).
@@ -63,10 +63,27 @@ static void generate_test_plonk_circuit(waffle::StandardComposer& composer, size
 }
 
 // test_bool_composer.cpp:110-137, with seeded bits
-static void generate_bool_circuit(waffle::BoolComposer& composer, size_t num_gates)
+// full_size = false: the reference's own circuit (0 / 1 witnesses only).  Its quotient has degree < 2n, so T_HI is the point
+// at infinity, whose limbs the reference leaves unspecified (group.hpp:143-146) and hashes into the next challenge
+// (challenge.hpp:15-23): such proofs verify on both sides but are not comparable beyond that commitment ("bool_degenerate").
+static void generate_bool_circuit(waffle::BoolComposer& composer, size_t num_gates, bool full_size = true)
 {
     for (size_t i = 0; i + 5 <= num_gates - 2; i += 5)
     {
+        if (!full_size)
+        {
+            const uint64_t bits = splitmix();
+            fr::field_t a = (bits & 1) ? fr::one : fr::zero;
+            fr::field_t b = (bits & 2) ? fr::one : fr::zero;
+            uint32_t a_idx = composer.add_variable(a);
+            uint32_t b_idx = composer.add_variable(b);
+            uint32_t c_idx = composer.add_variable(fr::add(a, b));
+            composer.create_bool_gate(a_idx);
+            composer.create_bool_gate(b_idx);
+            composer.create_add_gate({ a_idx, b_idx, c_idx, fr::one, fr::one, fr::neg_one(), fr::zero });
+            i -= 2; // (three gates per turn instead of five)
+            continue;
+        }
         // two gates on full-size field elements keep every commitment of the proof away from the point at infinity
         // (the reference leaves the limbs of an infinity commitment unspecified, and they enter its transcript)
         fr::field_t d = seeded_element(), e = seeded_element();
@@ -241,6 +258,12 @@ int main(int argc, char** argv)
     {
         waffle::BoolComposer composer = waffle::BoolComposer();
         generate_bool_circuit(composer, num_gates);
+        return run(composer, log_gates, repeat, ms_since(t0), kind.c_str());
+    }
+    if (kind == "bool_degenerate")
+    {
+        waffle::BoolComposer composer = waffle::BoolComposer();
+        generate_bool_circuit(composer, num_gates, false);
         return run(composer, log_gates, repeat, ms_since(t0), kind.c_str());
     }
     if (kind == "mimc")
