@@ -80,6 +80,34 @@ __device__ __noinline__ fe fr_mul_shared(const fe a, const fe b) { return Fr::mu
 #else
 #define NTT_SYNC() __syncthreads()
 #endif
+// Exchange between two radix steps: a thread of the next step (owned field at tile-slot bit QB2) reads what the threads
+// that differ from it in thread bits [QB2, QB1) stored in this one (owned field at bit QB1 = QB2 + R).  Only those have to
+// meet: a warp when QB1 <= 5, otherwise the 2^(QB1 - max(QB2, 5)) warps that share the remaining warp-index bits
+// (named barriers 3..10; 1 and 2 are the whole-tile barriers of the two halves).
+#ifndef BBG_NTT_FINE_SYNC
+#define BBG_NTT_FINE_SYNC 1
+#endif
+template <int QB1, int QB2> BBG_D void exchange_sync()
+{
+#if BBG_NTT_ABLATE == 1 || BBG_NTT_ABLATE == 2
+#elif defined(__CUDA_ARCH__) && BBG_NTT_FINE_SYNC
+    if constexpr (QB1 <= 5) __syncwarp();
+    else
+    {
+        constexpr int LO = (QB2 > 5 ? QB2 : 5) - 5, HI = QB1 - 5; // varying bits of the warp index (3 bits)
+        static_assert(HI <= 3 && LO < HI, "tile of 256 threads");
+        if constexpr (HI - LO == 3) NTT_SYNC();
+        else
+        {
+            const int w = ((int)threadIdx.x >> 5) & 7;
+            const int g = (w & ((1 << LO) - 1)) | ((w >> HI) << LO); // < 4
+            asm volatile("bar.sync %0, %1;" ::"r"(3 + 4 * ((int)threadIdx.x / NT) + g), "n"(32 << (HI - LO)) : "memory");
+        }
+    }
+#else
+    NTT_SYNC();
+#endif
+}
 BBG_HD int pad(int q) { return q + (q >> 5); }          // twiddle planes: power-of-two strides
 // data planes: XOR swizzle of the bank bits with tile-slot bits 3..7.  A bijection on [0, TILE) that makes every
 // access pattern of every radix step conflict-free (checked exhaustively for all sub-transform lengths and both
@@ -160,6 +188,8 @@ struct PassParams
     fe post_const;          // pass B: extra constant (fft/ifft_with_constant)
     int has_post_const;
     int scatter_shift;      // pass B as the last of three passes: block b's output o goes to dst[(o << scatter_shift) + b]
+    int stagger_half;       // clock cycles the second half of every CTA waits before its first tile (0: none), and
+    int stagger_cta;        // ... CTA b waits (b mod 4) quarters of this many more: see launch_pass_L
 };
 
 // DIF butterflies on the 3-bit owned field x[m] <-> k = base | m << B of a 2^L-point transform:
@@ -292,12 +322,15 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
     }
     else
     {
-        if (!FIRST) NTT_SYNC(); // everyone has read its inputs of this step
+        // (a thread stores to the very slots it loaded in this step: nobody else reads them before the exchange below)
+#if !BBG_NTT_FINE_SYNC
+        if (!FIRST) NTT_SYNC();
+#endif
 #if BBG_NTT_ABLATE != 2
 #pragma unroll
         for (int m = 0; m < 8; ++m) sm_store(data, TM::template slot<B>(t, m), x[m]);
 #endif
-        NTT_SYNC();
+        exchange_sync<B + TM::KSHIFT, (B >= 3 ? B - 3 : 0) + TM::KSHIFT>();
     }
 }
 
@@ -324,6 +357,17 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
     uint32_t* tw = (uint32_t*)smem_raw + TPC * 8 * PLANE;
     for (int i = threadIdx.x; i < 16 * TWP; i += NT * TPC) tw[i] = p.sub_tw[i];
     __syncthreads();
+#if defined(__CUDA_ARCH__)
+    // The two halves run the same instruction stream on the same schedulers: started together they would load, multiply
+    // and store in lock step and leave the multiply pipe idle during both tiles' global-memory phases.  Half a tile period
+    // of skew keeps one tile computing while the other moves data.
+    if ((p.stagger_half | p.stagger_cta) != 0)
+    {
+        const long long wait = (long long)half * p.stagger_half + (long long)(blockIdx.x & 3) * (p.stagger_cta >> 2);
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) {}
+    }
+#endif
     for (int work = blockIdx.x * TPC + half; work < p.total_work; work += gridDim.x * TPC)
     {
         // polynomial-minor order: the CTAs in flight work on the same few tiles of all polynomials of the batch, so the
@@ -739,8 +783,21 @@ template <int L, bool COLS_LOW> int launch_pass_L(const PassParams& p, cudaStrea
     int grid = (2 / TPC) * bbg_rt::num_sms();
     if (grid > (p.total_work + TPC - 1) / TPC) grid = (p.total_work + TPC - 1) / TPC;
     auto kernel = ntt_pass_kernel<L, COLS_LOW>; // (alias: the template's comma would split the macro argument)
+    PassParams q = p;
+    {
+        static int half_cycles = -1, cta_cycles = -1;
+        if (half_cycles < 0)
+        {
+            const char* e = getenv(COLS_LOW ? "BBG_NTT_STAGGER_A" : "BBG_NTT_STAGGER_B");
+            half_cycles = e ? atoi(e) : 0;
+            e = getenv(COLS_LOW ? "BBG_NTT_STAGGER_CTA_A" : "BBG_NTT_STAGGER_CTA_B");
+            cta_cycles = e ? atoi(e) : 0;
+        }
+        q.stagger_half = p.total_work >= 4 * grid * TPC ? half_cycles : 0; // (short launches: the skew would only add to the tail)
+        q.stagger_cta = p.total_work >= 4 * grid * TPC ? cta_cycles : 0;
+    }
     bbg_prof::Scope prof(COLS_LOW ? bbg_prof::NTT_PASS_A : bbg_prof::NTT_PASS_B, st);
-    BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT * TPC), SMEM_BYTES, st, p);
+    BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT * TPC), SMEM_BYTES, st, q);
     ++g_ntt_launches;
     return bbg_rt::last_error();
 }

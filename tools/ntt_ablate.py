@@ -17,7 +17,17 @@ def one(path):
     import barretenberg_b200 as bb
 
     lib = bb.Library(path)
-    out = {"lib": os.path.basename(path)}
+    out = {"lib": os.path.basename(path), "env": {k: v for k, v in os.environ.items() if k.startswith("BBG_NTT_")}}
+    # ifft(fft(x)) == x through this library (the ablation builds fail this by construction)
+    x0 = np.random.default_rng(7).integers(0, 1 << 60, size=(2 << 20, 4), dtype=np.uint64)
+    d0 = lib.dev_alloc(x0.nbytes)
+    lib.h2d(d0, x0)
+    lib.ntt_dev("coset_fft", d0, 20, batch=2)
+    lib.ntt_dev("coset_ifft", d0, 20, batch=2)
+    y0 = np.zeros_like(x0)
+    lib.d2h(y0, d0)
+    lib.dev_free(d0)
+    out["round_trip_ok"] = bool((x0 == y0).all())
     for log_n, op in ((20, "fft"), (22, "coset_fft")):
         n, batch = 1 << log_n, 8
         x = np.random.default_rng(1).integers(0, 1 << 60, size=(batch * n, 4), dtype=np.uint64)
@@ -46,7 +56,11 @@ if __name__ == "__main__":
     if len(sys.argv) == 3 and sys.argv[1] == "--one":
         one(sys.argv[2])
     else:
-        libs = sys.argv[1:] or [os.path.join(ROOT, "barretenberg_b200", "libbbgpu.so")] + sorted(
-            os.path.join(ROOT, "build", "ablate", f) for f in os.listdir(os.path.join(ROOT, "build", "ablate")) if f.endswith(".so"))
+        found = []
+        for sub in ("ablate", "variants"):
+            d = os.path.join(ROOT, "build", sub)
+            if os.path.isdir(d):
+                found += sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".so"))
+        libs = sys.argv[1:] or [os.path.join(ROOT, "barretenberg_b200", "libbbgpu.so")] + found
         for p in libs:
             subprocess.run([sys.executable, os.path.abspath(__file__), "--one", p], timeout=300)
