@@ -64,6 +64,7 @@ struct Plan
     int chunk_log;
     uint32_t chunks_per_window;
     int reduce_outputs; // per window: chunk bits + 2
+    uint32_t red_splits; // blocks per (window, output) of the reduction, a power of two
     // fixed-base form (a table of pre-doubled windows, below): every window's digits fall into ONE bucket set and entry
     // (w, j) reads point j of window w's table, entry_stride entries further on
     int sets;              // bucket sets per MSM: W, or 1 in the fixed-base form
@@ -427,17 +428,35 @@ __global__ void __launch_bounds__(128) msm_chunk_kernel(const fe* buckets, uint3
 // ---- 6b. block tree reductions: out[w][r] -------------------------------------------------------------
 // r < chunk_bits : sum of A_t over chunks t of window w with bit r set
 // r = chunk_bits : sum of V_t;   r = chunk_bits + 1 : sum of A_t
+// A window's chunks are cut into `splits` contiguous ranges of `len` chunks (both powers of two), one block each, so that a
+// single large bucket set (the fixed-base form: 2^18 buckets in ONE set) is reduced by hundreds of blocks instead of a
+// dozen; a block only visits the chunks that count for its output (bit r set), so all of its threads carry the same load.
+// part[(w * outputs + r) * splits + s]; msm_reduce_final_kernel adds the `splits` partial sums.
+// The blocks are latency-bound (a chain of full additions per thread, then eight tree levels), so what counts is that ALL of
+// them are resident at once: two per SM at <= 128 registers, and `splits` chosen so that the grid fits that single wave.
 constexpr int RED_BLOCK = 256;
-__global__ void __launch_bounds__(RED_BLOCK) msm_reduce_kernel(const fe* A, const fe* V, uint32_t chunks_per_window, int chunk_bits, fe* out)
+constexpr int RED_BLOCKS_PER_SM = 2;
+__global__ void __launch_bounds__(RED_BLOCK, RED_BLOCKS_PER_SM) msm_reduce_kernel(const fe* A, const fe* V, uint32_t chunks_per_window, int chunk_bits, uint32_t len, fe* part)
 {
     __shared__ uint32_t sm[RED_BLOCK * 32];
     const int r = blockIdx.x, w = blockIdx.y;
-    const fe* src = (r == chunk_bits ? V : A) + 4 * (size_t)w * chunks_per_window;
+    const uint32_t base = blockIdx.z * len;
+    const fe* src = (r == chunk_bits ? V : A) + 4 * ((size_t)w * chunks_per_window + base);
     xyzz_pt sum = G1::infinity();
-    for (uint32_t t = threadIdx.x; t < chunks_per_window; t += RED_BLOCK)
+    if (r >= chunk_bits || (1u << r) >= len)
     {
-        if (r < chunk_bits && !((t >> r) & 1u)) continue;
-        sum = G1::add(sum, load_xyzz(src + 4 * (size_t)t));
+        // every chunk of the range counts, or (bit r is a bit of the range's index) none does
+        if (r >= chunk_bits || ((base >> r) & 1u))
+            for (uint32_t t = threadIdx.x; t < len; t += RED_BLOCK) sum = G1::add(sum, load_xyzz(src + 4 * (size_t)t));
+    }
+    else
+    {
+        const uint32_t low = (1u << r) - 1;
+        for (uint32_t u = threadIdx.x; u < (len >> 1); u += RED_BLOCK)
+        {
+            const uint32_t t = ((u & ~low) << 1) | (1u << r) | (u & low); // u with a one inserted at bit r
+            sum = G1::add(sum, load_xyzz(src + 4 * (size_t)t));
+        }
     }
     for (int off = RED_BLOCK / 2; off > 0; off >>= 1)
     {
@@ -446,7 +465,89 @@ __global__ void __launch_bounds__(RED_BLOCK) msm_reduce_kernel(const fe* A, cons
         __syncthreads();
         if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
     }
-    if (threadIdx.x == 0) store_xyzz(out + 4 * ((size_t)w * (chunk_bits + 2) + r), sum);
+    if (threadIdx.x == 0) store_xyzz(part + 4 * (((size_t)w * (chunk_bits + 2) + r) * gridDim.z + blockIdx.z), sum);
+}
+// out[o] = sum_s part[o * splits + s]; one block of blockDim.x (a power of two <= 64) threads per output
+__global__ void __launch_bounds__(64) msm_reduce_final_kernel(const fe* part, uint32_t splits, fe* out)
+{
+    __shared__ uint32_t sm[32 * 32];
+    const fe* src = part + 4 * (size_t)blockIdx.x * splits;
+    xyzz_pt sum = G1::infinity();
+    for (uint32_t s = threadIdx.x; s < splits; s += blockDim.x) sum = G1::add(sum, load_xyzz(src + 4 * (size_t)s));
+    for (int off = (int)blockDim.x / 2; off > 0; off >>= 1)
+    {
+        __syncthreads();
+        if ((int)threadIdx.x >= off && (int)threadIdx.x < 2 * off) store_xyzz(sm + 32 * (threadIdx.x - off), sum);
+        __syncthreads();
+        if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
+    }
+    if (threadIdx.x == 0) store_xyzz(out + 4 * (size_t)blockIdx.x, sum);
+}
+
+// ---- 6c. the same outputs with two additions per chunk instead of (chunk_bits + 2) / 2 ---------------------------------
+// One halving tree over the chunk totals x_j yields EVERY bit-sliced sum: when the tree folds thread j + off into thread j
+// (off = 128, 64, .., 1), the values held by threads [off, 2 off) are exactly the partial sums of the chunks whose index bit
+// log2(off) is set; those threads keep them and halve among themselves in the remaining steps while the main tree carries
+// on below them.  After eight steps thread 0 holds the block total and thread 2^h the sum over chunks with bit h set:
+// 502 additions per 256 chunks, eight deep, every thread at most one addition per step.
+// grid (blocks per set, sets, 2): z = 0 works on the A_t of chunks [256 B, 256 B + 256) of set w and writes T_0..T_7 and the
+// block total, z = 1 is the plain sum of the V_t.  part[(w * nb + B) * 10 + o], o = 0..7: T_o, 8: total, 9: sum V.
+constexpr int TREE_BLOCK = 256;
+constexpr int TREE_OUT = 10;
+BBG_D xyzz_pt bit_tree(xyzz_pt v, bool all_bits, uint32_t* sm)
+{
+    const int tid = (int)threadIdx.x;
+    const int top = tid > 0 ? (1 << (31 - __clz(tid))) : 0; // highest set bit of tid: base of the group tid belongs to
+    for (int off = TREE_BLOCK / 2; off > 0; off >>= 1)
+    {
+        __syncthreads();
+        store_xyzz(sm + 32 * tid, v);
+        __syncthreads();
+        const bool active = tid < off || (all_bits && tid >= 2 * off && tid - top < off);
+        if (active) v = G1::add(v, load_xyzz(sm + 32 * (tid + off)));
+    }
+    return v;
+}
+__global__ void __launch_bounds__(TREE_BLOCK, 2) msm_tree_reduce_kernel(const fe* A, const fe* V, uint32_t chunks_per_window, fe* part)
+{
+    __shared__ uint32_t sm[TREE_BLOCK * 32];
+    const uint32_t B = blockIdx.x, w = blockIdx.y, nb = gridDim.x;
+    const bool is_v = blockIdx.z != 0;
+    const uint32_t t = B * TREE_BLOCK + threadIdx.x;
+    xyzz_pt v = G1::infinity();
+    if (t < chunks_per_window) v = load_xyzz((is_v ? V : A) + 4 * ((size_t)w * chunks_per_window + t));
+    v = bit_tree(v, !is_v, sm);
+    fe* dst = part + 4 * (((size_t)w * nb + B) * TREE_OUT);
+    const int tid = (int)threadIdx.x;
+    if (is_v)
+    {
+        if (tid == 0) store_xyzz(dst + 4 * 9, v);
+    }
+    else if (tid == 0) store_xyzz(dst + 4 * 8, v);
+    else if ((tid & (tid - 1)) == 0) store_xyzz(dst + 4 * (31 - __clz(tid)), v);
+}
+// second level over the nb <= 256 blocks of a set, grid (10, sets): o < 8: T_o = sum_B part[B][o];  o = 8: sum V;
+// o = 9: the bit tree over the block totals gives T_(8+h) and the sum of all A_t.  out[w][r] as msm_reduce_kernel writes it.
+__global__ void __launch_bounds__(TREE_BLOCK, 2) msm_tree_final_kernel(const fe* part, uint32_t nb, int chunk_bits, fe* out)
+{
+    __shared__ uint32_t sm[TREE_BLOCK * 32];
+    const int o = blockIdx.x, tid = (int)threadIdx.x;
+    const uint32_t w = blockIdx.y;
+    const int src_o = o < 8 ? o : (o == 8 ? 9 : 8);
+    xyzz_pt v = G1::infinity();
+    if ((uint32_t)tid < nb) v = load_xyzz(part + 4 * (((size_t)w * nb + tid) * TREE_OUT + src_o));
+    v = bit_tree(v, o == 9, sm);
+    fe* dst = out + 4 * ((size_t)w * (chunk_bits + 2));
+    if (o < 8)
+    {
+        if (tid == 0 && o < chunk_bits) store_xyzz(dst + 4 * o, v);
+    }
+    else if (o == 8)
+    {
+        if (tid == 0) store_xyzz(dst + 4 * chunk_bits, v);
+    }
+    else if (tid == 0) store_xyzz(dst + 4 * (chunk_bits + 1), v);
+    else if ((tid & (tid - 1)) == 0 && 8 + (31 - __clz(tid)) < chunk_bits) store_xyzz(dst + 4 * (8 + (31 - __clz(tid))), v);
 }
 
 // table[2i] = P_i, table[2i+1] = (beta x_i, -y_i)   (scalar_multiplication.cpp:131-140)
@@ -780,7 +881,12 @@ uint32_t pick_slice(size_t max_entries)
 }
 
 // Window width of a fixed-base table for MSMs of about n points: one bucket set of 2^(c-1) buckets whatever the number of
-// windows, so the per-bucket cost is paid once and c can grow (same cost constants as pick_windows).
+// windows, so the per-bucket cost is paid once and c can grow.  Costs in mixed-addition equivalents, fitted to B200
+// measurements (tools/msm_fixed_base.py, 2^17..2^20): 1.13 per sorted entry; ~6 per bucket (fix-up, chunk sums and the split
+// tree reduction, which all scale with the ONE bucket set); and the top window, whose 127 - (W-1) c bits put all of its 2n
+// digits into the lowest 2^(top-1) buckets of the shared set: beyond ~2048 entries per bucket the counting atomics of the
+// digit pass contend and the fix-up sees giant buckets (measured at 2^20: c = 17, top 8 bits, digits 0.16 -> 0.57 ms,
+// fix-up 0.11 -> 0.20 ms; c = 18, top 1 bit: +0.7 / +1.1 ms).
 void pick_windows_fixed_base(size_t n, int& c_out, int& W_out)
 {
     double best = -1;
@@ -793,9 +899,9 @@ void pick_windows_fixed_base(size_t n, int& c_out, int& W_out)
         if (W > 16) continue;
         const int top_bits = 127 - (W - 1) * c;
         const double buckets = (double)((size_t)1 << (c - 1));
-        const double avg = (double)W * 2.0 * (double)n / buckets;
-        double cost = (double)W * 2.0 * (double)n * 1.13 + buckets * (11.0 + 0.3 * avg / 64.0);
-        if (top_bits < 4) cost += 2.0 * (double)n * (4 - top_bits) / 8.0; // (a thin top window costs a table, not a bucket set)
+        double cost = (double)W * 2.0 * (double)n * 1.13 + buckets * 6.0;
+        const double per_top_bucket = 2.0 * (double)n / (double)((size_t)1 << (top_bits - 1));
+        if (per_top_bucket > 2048.0) cost += 2.0 * (double)n * (per_top_bucket / 2048.0 < 8.0 ? per_top_bucket / 2048.0 : 8.0) * 0.25;
         if (best < 0 || cost < best)
         {
             best = cost;
@@ -831,6 +937,7 @@ Plan make_plan(size_t n, int fixed_c = 0, uint32_t entry_stride = 0)
     int bits = 0;
     while ((1u << bits) < pl.chunks_per_window) ++bits;
     pl.reduce_outputs = bits + 2;
+    pl.red_splits = 1; // (set per launch: depends on the batch and on the device's SM count)
     return pl;
 }
 
@@ -896,6 +1003,27 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     const size_t o_V = carve((size_t)total_chunks * 128);
     const size_t red_count = (size_t)pl.sets * pl.reduce_outputs;
     const size_t o_red = carve(red_count * 128);
+    // Which reduction: both are latency-bound chains of full additions (~3.7 us each for a lone warp, measured).  Bucket sets
+    // of 2^11 .. 2^16 chunks take the two-additions-per-chunk tree (6c: two launches, 2 x 9 additions deep whatever the
+    // size: 0.125 ms against 0.185 / 0.33 ms for 2^12 / 2^15 chunks per set at 2^20 points); smaller sets are quicker through
+    // the single launch of the bit-sliced reduction (6b: chunks / 256 + 8 deep; 0.068 against 0.105 ms at 2^17 points), which
+    // is also kept beyond 2^16 chunks (c >= 21: sizes where this tail no longer counts), cut into the largest power of two
+    // of ranges per (set, output) that still fits one resident wave.
+    uint32_t tree_blocks = (pl.chunks_per_window > 1024u && pl.chunks_per_window <= 256u * TREE_BLOCK) ? pl.chunks_per_window / TREE_BLOCK : 0;
+    if (const char* e = getenv("BBG_MSM_TREE_REDUCE")) // development / tests: 0 / 1 force the bit-sliced reduction / the tree
+    {
+        if (e[0] == '0') tree_blocks = 0;
+        else if (pl.chunks_per_window <= 256u * TREE_BLOCK) tree_blocks = (pl.chunks_per_window + TREE_BLOCK - 1) / TREE_BLOCK;
+    }
+    while (tree_blocks == 0 && red_count * (pl.red_splits * 2) <= (size_t)(RED_BLOCKS_PER_SM * bbg_rt::num_sms()) &&
+           pl.chunks_per_window / (pl.red_splits * 2) >= (uint32_t)RED_BLOCK)
+        pl.red_splits *= 2;
+    if (const char* e = getenv("BBG_MSM_RED_SPLITS")) // tests: force the split path where the SM count would not choose it
+    {
+        const uint32_t v = (uint32_t)atoi(e);
+        if (v >= 1 && (v & (v - 1)) == 0 && pl.chunks_per_window / v >= 1) pl.red_splits = v;
+    }
+    const size_t o_red_part = carve(tree_blocks != 0 ? (size_t)pl.sets * tree_blocks * TREE_OUT * 128 : red_count * pl.red_splits * 128);
     BBG_CHECK(g_ws.ensure(off));
     char* ws = (char*)g_ws.p;
     uint32_t* digits = (uint32_t*)(ws + o_digits);
@@ -949,10 +1077,24 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_REDUCE, st);
-        BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.sets), dim3(RED_BLOCK), 0, st, (const fe*)A, (const fe*)V,
-                   pl.chunks_per_window, pl.reduce_outputs - 2, red);
+        fe* red_part = (fe*)(ws + o_red_part);
+        if (tree_blocks != 0)
+        {
+            BBG_LAUNCH(msm_tree_reduce_kernel, dim3(tree_blocks, (unsigned)pl.sets, 2), dim3(TREE_BLOCK), 0, st, (const fe*)A, (const fe*)V,
+                       pl.chunks_per_window, red_part);
+            BBG_LAUNCH(msm_tree_final_kernel, dim3(TREE_OUT, (unsigned)pl.sets), dim3(TREE_BLOCK), 0, st, (const fe*)red_part, tree_blocks,
+                       pl.reduce_outputs - 2, red);
+        }
+        else
+        {
+            BBG_LAUNCH(msm_reduce_kernel, dim3((unsigned)pl.reduce_outputs, (unsigned)pl.sets, pl.red_splits), dim3(RED_BLOCK), 0, st, (const fe*)A,
+                       (const fe*)V, pl.chunks_per_window, pl.reduce_outputs - 2, pl.chunks_per_window / pl.red_splits, pl.red_splits > 1 ? red_part : red);
+            if (pl.red_splits > 1)
+                BBG_LAUNCH(msm_reduce_final_kernel, dim3((unsigned)red_count), dim3(pl.red_splits < 64 ? pl.red_splits : 64), 0, st, (const fe*)red_part,
+                           pl.red_splits, red);
+        }
     }
-    g_msm_launches += 9 + batch;
+    g_msm_launches += 9 + batch + ((tree_blocks != 0 || pl.red_splits > 1) ? 1 : 0);
     BBG_CHECK(bbg_rt::last_error());
 
     // the per-window reductions travel to the ticket's pinned slot behind the kernels

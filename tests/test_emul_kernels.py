@@ -340,7 +340,7 @@ def test_compute_kate_opening_coefficients(emu, n):
     assert (got == _canonical(want)).all()
 
 
-@pytest.mark.parametrize("window", [0, 9, 13])
+@pytest.mark.parametrize("window", [0, 9, 13, 15, 16])
 def test_msm_fixed_base_windows(emu, window, monkeypatch):
     """Fixed-base form (generate_pippenger_precompute_table / pippenger_precomputed, scalar_multiplication.cpp:90-129,
     :478-573): tables registered while bbg_set_srs_precompute is on get pre-doubled windows, and every MSM over them — whole,
@@ -348,6 +348,13 @@ def test_msm_fixed_base_windows(emu, window, monkeypatch):
     planner's own width; others force a width so that several window counts and top-window sizes are exercised."""
     if window:
         monkeypatch.setenv("BBG_MSM_FIXED_WINDOW", str(window))
+    if window == 16:
+        # the bit-sliced bucket reduction kept for very large bucket sets, in its split form (several blocks per output +
+        # final sum); every other case takes the two-additions-per-chunk tree, with 1, 2 and 8 blocks per set
+        monkeypatch.setenv("BBG_MSM_TREE_REDUCE", "0")
+        monkeypatch.setenv("BBG_MSM_RED_SPLITS", "8")
+    elif window in (9, 13):
+        monkeypatch.setenv("BBG_MSM_TREE_REDUCE", "1")  # (small bucket sets would take the bit-sliced reduction)
     n = 1300
     table, a0, d = H.generator_multiples_table(55, n)
     emu.set_srs_precompute(True)
