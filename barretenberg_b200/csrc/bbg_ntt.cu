@@ -32,6 +32,7 @@
 //   uploaded).
 #include "bbg_internal.h"
 
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -124,6 +125,49 @@ BBG_D void prefetch_l2(const void* p)
 #endif
 }
 
+// ---- next-tile staging ------------------------------------------------------------------------------------------------
+// A tile's inputs travel global -> shared memory by cp.async (no registers, no scoreboard) into the tile's OWN data region
+// while the previous tile's last radix step still multiplies and stores: the region is free from the moment that step has
+// read it.  The staged image is raw: element of tile slot q as two 16-byte chunks 2q, 2q + 1, chunk c at chunk position
+// c ^ ((c >> 3) & 1) (a warp's 128-bit loads of consecutive slots then cover all banks once per quarter warp).
+// Measured (r02, tools/ntt_ablate.py, batch 8): SLOWER than loading into registers at the top of the tile - fft 2^20 1.386 ->
+// 1.482 ms, coset_fft 2^22 6.19 -> 6.51 ms (two more whole-tile barriers, 100 more bytes of spills, and the tile waits as one
+// for its copies where the warps used to trickle in as their own loads arrived).  Kept compiled out as the record of the
+// experiment; the product build loads through registers.
+#ifndef BBG_NTT_STAGE
+#define BBG_NTT_STAGE 0
+#endif
+BBG_HD int stage_pos(int c) { return (c ^ ((c >> 3) & 1)) << 2; } // word offset of chunk c
+BBG_D void cp_async16(uint32_t* smem_dst, const void* gmem_src)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#else
+    memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+BBG_D void cp_async_commit()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+BBG_D void cp_async_wait_all()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+BBG_D fe staged_load(const uint32_t* data, int q)
+{
+    fe r;
+    const uint4 lo = *reinterpret_cast<const uint4*>(data + stage_pos(2 * q));
+    const uint4 hi = *reinterpret_cast<const uint4*>(data + stage_pos(2 * q + 1));
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+
 BBG_D void sm_store(uint32_t* data, int q, const fe& x)
 {
     const int p = dswz(q);
@@ -188,8 +232,6 @@ struct PassParams
     fe post_const;          // pass B: extra constant (fft/ifft_with_constant)
     int has_post_const;
     int scatter_shift;      // pass B as the last of three passes: block b's output o goes to dst[(o << scatter_shift) + b]
-    int stagger_half;       // clock cycles the second half of every CTA waits before its first tile (0: none), and
-    int stagger_cta;        // ... CTA b waits (b mod 4) quarters of this many more: see launch_pass_L
 };
 
 // DIF butterflies on the 3-bit owned field x[m] <-> k = base | m << B of a 2^L-point transform:
@@ -237,7 +279,31 @@ template <int L, bool COLS_LOW> struct TileMap
     static BBG_D int c_of(int q) { return COLS_LOW ? (q & ((1 << CLOG) - 1)) : (q >> L); }
 };
 
-// (nsrc, ntile): the tile this half of the CTA works on next, or nsrc == nullptr - prefetched into L2 by the first step
+// queue the copies of tile `tile` of polynomial `src` into `data` (256 threads x 16 chunks of 16 bytes)
+template <int L, bool COLS_LOW> BBG_D void stage_tile(const PassParams& p, const fe* src, int tile, uint32_t* data)
+{
+    typedef TileMap<L, COLS_LOW> TM;
+    const int t = threadIdx.x & (NT - 1);
+    const int rest = p.log_n - L;
+#pragma unroll
+    for (int j = 0; j < 2 * TILE / NT; ++j)
+    {
+        const int i = t + j * NT; // chunk: half (i & 1) of the element of tile slot i >> 1
+        const int q = i >> 1;
+        const int k = TM::k_of(q), c = TM::c_of(q);
+        size_t g;
+        if (COLS_LOW) g = ((size_t)k << rest) + ((size_t)tile << TM::CLOG) + c;
+        else g = ((((size_t)tile << TM::CLOG) + c) << L) + k;
+        cp_async16(data + stage_pos(i), reinterpret_cast<const char*>(src + g) + 16 * (i & 1));
+#if BBG_NTT_PREFETCH
+        // the matrix entries of a tile are the same index set as its inputs: start them towards L2 a whole tile ahead
+        if (COLS_LOW && p.mat != nullptr && (i & 1) == 0) prefetch_l2(p.mat + g);
+#endif
+    }
+    cp_async_commit();
+}
+
+// (nsrc, ntile): the tile this half of the CTA works on next (nsrc == nullptr: none), staged by the last step
 template <int L, bool COLS_LOW, int B, int R, bool FIRST, bool LAST>
 BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int tile, uint32_t* data, const uint32_t* tw, const fe* nsrc, int ntile)
 {
@@ -251,6 +317,10 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
         {
             const int q = TM::template slot<B>(t, m);
             const int k = TM::k_of(q), c = TM::c_of(q);
+#if BBG_NTT_STAGE && BBG_NTT_ABLATE != 5
+            (void)c;
+            x[m] = staged_load(data, q);
+#else
             size_t g;
             if (COLS_LOW) g = ((size_t)k << rest) + ((size_t)tile << TM::CLOG) + c;
             else g = ((((size_t)tile << TM::CLOG) + c) << L) + k;
@@ -261,16 +331,8 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             x[m] = load_fe(src + g);
 #endif
 #if BBG_NTT_PREFETCH
-            // the matrix entries of this tile are the same index set as its inputs: start them towards L2 now, ten stages
-            // before they are multiplied in; and the inputs of the next tile
             if (COLS_LOW && p.mat != nullptr) prefetch_l2(p.mat + g);
-            if (BBG_NTT_PREFETCH > 1 && nsrc != nullptr)
-            {
-                size_t gn;
-                if (COLS_LOW) gn = ((size_t)k << rest) + ((size_t)ntile << TM::CLOG) + c;
-                else gn = ((((size_t)ntile << TM::CLOG) + c) << L) + k;
-                prefetch_l2(nsrc + gn);
-            }
+#endif
 #endif
             if (COLS_LOW && p.vec != nullptr) x[m] = NTT_MUL(x[m], load_fe(p.vec + k));
         }
@@ -280,6 +342,13 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
 #if BBG_NTT_ABLATE != 2
 #pragma unroll
         for (int m = 0; m < 8; ++m) x[m] = sm_load(data, TM::template slot<B>(t, m));
+#endif
+#if BBG_NTT_STAGE && BBG_NTT_ABLATE != 5
+        if (LAST)
+        {
+            NTT_SYNC(); // every thread of the tile has its last inputs in registers: the region is free
+            if (nsrc != nullptr) stage_tile<L, COLS_LOW>(p, nsrc, ntile, data);
+        }
 #endif
     }
     {
@@ -326,6 +395,9 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
 #if !BBG_NTT_FINE_SYNC
         if (!FIRST) NTT_SYNC();
 #endif
+#if BBG_NTT_STAGE && BBG_NTT_ABLATE != 5
+        if (FIRST) NTT_SYNC(); // the staged image has been read by everyone before the limb planes overwrite it
+#endif
 #if BBG_NTT_ABLATE != 2
 #pragma unroll
         for (int m = 0; m < 8; ++m) sm_store(data, TM::template slot<B>(t, m), x[m]);
@@ -355,32 +427,34 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
     const int half = (int)threadIdx.x / NT; // which of the CTA's tiles this thread works on
     uint32_t* data = (uint32_t*)smem_raw + half * 8 * PLANE;
     uint32_t* tw = (uint32_t*)smem_raw + TPC * 8 * PLANE;
-    for (int i = threadIdx.x; i < 16 * TWP; i += NT * TPC) tw[i] = p.sub_tw[i];
-    __syncthreads();
-#if defined(__CUDA_ARCH__)
-    // The two halves run the same instruction stream on the same schedulers: started together they would load, multiply
-    // and store in lock step and leave the multiply pipe idle during both tiles' global-memory phases.  Half a tile period
-    // of skew keeps one tile computing while the other moves data.
-    if ((p.stagger_half | p.stagger_cta) != 0)
+    const int batch = p.total_work / p.num_tiles;
+#if BBG_NTT_STAGE && BBG_NTT_ABLATE != 5
     {
-        const long long wait = (long long)half * p.stagger_half + (long long)(blockIdx.x & 3) * (p.stagger_cta >> 2);
-        const long long t0 = clock64();
-        while (clock64() - t0 < wait) {}
+        // the first tile's copies fly while the twiddle image is loaded
+        const int work0 = blockIdx.x * TPC + half;
+        if (work0 < p.total_work) stage_tile<L, COLS_LOW>(p, p.src + (size_t)(work0 % batch) * p.batch_stride, work0 / batch, data);
     }
 #endif
+    for (int i = threadIdx.x; i < 16 * TWP; i += NT * TPC) tw[i] = p.sub_tw[i];
+    __syncthreads();
     for (int work = blockIdx.x * TPC + half; work < p.total_work; work += gridDim.x * TPC)
     {
         // polynomial-minor order: the CTAs in flight work on the same few tiles of all polynomials of the batch, so the
         // inter-pass matrix tile (pass A; 128 MiB per 2^22 transform, more than L2 holds) is read from HBM once per batch
-        const int batch = p.total_work / p.num_tiles;
         const int tile = work / batch;
         const size_t b = (size_t)(work % batch);
         const int nwork = work + (int)gridDim.x * TPC;
         const fe* nsrc = nwork < p.total_work ? p.src + (size_t)(nwork % batch) * p.batch_stride : nullptr;
+#if BBG_NTT_STAGE && BBG_NTT_ABLATE != 5
+        cp_async_wait_all(); // this thread's copies of the tile have landed ...
+        NTT_SYNC();          // ... and everybody else's
+#endif
         fe x[8];
         run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.scatter_shift ? p.dst + b : p.dst + b * p.batch_stride, tile, data, tw, nsrc,
                                            nwork / batch);
+#if !(BBG_NTT_STAGE && BBG_NTT_ABLATE != 5)
         NTT_SYNC(); // the last step's shared-memory reads finish before the next tile overwrites
+#endif
     }
 }
 
@@ -671,6 +745,37 @@ void split(unsigned log_n, int& L1, int& L2)
     }
     L1 = (int)(log_n + 1) / 2;
     L2 = (int)log_n - L1;
+    // 2^20 = 2^9 x 2^11 rather than 2^10 x 2^10: a 10-stage sub-transform is 3 + 3 + 3 + 1 stages, its fourth radix step one
+    // stage of trivial twiddles behind a whole exchange; 9 + 11 stages need five exchanges instead of six and pass A reads
+    // 128-byte column pieces instead of 64-byte ones (measured, batch 8: 1.387 -> 1.358 ms; 2^11 x 2^9: 1.396; at 2^21 the
+    // default 2^11 x 2^10 stays ahead of 2^10 x 2^11, 2.98 against 3.05 ms)
+    if (log_n == 20) { L1 = 9; L2 = 11; }
+    // development override: BBG_NTT_SPLIT="20:9,21:10" sets L1 per log_n (read once; both lengths must stay in 6..11)
+    static int override_l1[32];
+    static bool parsed = false;
+    if (!parsed)
+    {
+        parsed = true;
+        if (const char* e = getenv("BBG_NTT_SPLIT"))
+        {
+            while (*e)
+            {
+                const int lg = atoi(e);
+                const char* colon = strchr(e, ':');
+                if (colon == nullptr) break;
+                const int l1 = atoi(colon + 1);
+                if (lg >= 12 && lg <= 22 && l1 >= 6 && l1 <= TILE_LOG && lg - l1 >= 6 && lg - l1 <= TILE_LOG) override_l1[lg] = l1;
+                const char* comma = strchr(colon, ',');
+                if (comma == nullptr) break;
+                e = comma + 1;
+            }
+        }
+    }
+    if (log_n < 32 && override_l1[log_n] != 0)
+    {
+        L1 = override_l1[log_n];
+        L2 = (int)log_n - L1;
+    }
 }
 
 int get_vec(unsigned log_n, int kind, cudaStream_t st, const fe** out)
@@ -783,21 +888,8 @@ template <int L, bool COLS_LOW> int launch_pass_L(const PassParams& p, cudaStrea
     int grid = (2 / TPC) * bbg_rt::num_sms();
     if (grid > (p.total_work + TPC - 1) / TPC) grid = (p.total_work + TPC - 1) / TPC;
     auto kernel = ntt_pass_kernel<L, COLS_LOW>; // (alias: the template's comma would split the macro argument)
-    PassParams q = p;
-    {
-        static int half_cycles = -1, cta_cycles = -1;
-        if (half_cycles < 0)
-        {
-            const char* e = getenv(COLS_LOW ? "BBG_NTT_STAGGER_A" : "BBG_NTT_STAGGER_B");
-            half_cycles = e ? atoi(e) : 0;
-            e = getenv(COLS_LOW ? "BBG_NTT_STAGGER_CTA_A" : "BBG_NTT_STAGGER_CTA_B");
-            cta_cycles = e ? atoi(e) : 0;
-        }
-        q.stagger_half = p.total_work >= 4 * grid * TPC ? half_cycles : 0; // (short launches: the skew would only add to the tail)
-        q.stagger_cta = p.total_work >= 4 * grid * TPC ? cta_cycles : 0;
-    }
     bbg_prof::Scope prof(COLS_LOW ? bbg_prof::NTT_PASS_A : bbg_prof::NTT_PASS_B, st);
-    BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT * TPC), SMEM_BYTES, st, q);
+    BBG_LAUNCH(kernel, dim3((unsigned)grid), dim3(NT * TPC), SMEM_BYTES, st, p);
     ++g_ntt_launches;
     return bbg_rt::last_error();
 }

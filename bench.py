@@ -107,6 +107,10 @@ def workload_config(args, world):
         "workload": "configs[0]+configs[1]: 1x MSM 2^%d (BN254 G1, points (a0+i*d)G, uniform scalars) + NTT batch of %d polys: "
                     "fft 2^%d, ifft 2^%d, coset_fft 2^%d" % (args.log_n, BATCH, args.log_n, args.log_n, args.log_n + 2),
         "msm_points": 1 << args.log_n,
+        "msm_table": "plain Pippenger windows" if getattr(args, "no_srs_precompute", False) else
+                     "the SRS is registered once with the library (ReferenceString::monomials): fixed-base windows built at registration "
+                     "(GPU generate_pippenger_precompute_table / pippenger_precomputed), not per step; components_ms.msm_*_plain_windows "
+                     "is the same MSM over an unregistered table",
         "ntt_batch": BATCH,
         "ntt_sizes": [1 << args.log_n, 1 << args.log_n, 1 << (args.log_n + 2)],
         "streams": "device-resident step: the MSM runs on a second stream beside the NTT batch; e2e: sequential blocking calls, as the reference's signatures are",
@@ -416,7 +420,15 @@ def run_b200(args, rank, local_rank, world):
     # host copy of the table for the e2e arm, registered once (what ReferenceString + the shim do)
     h_table = pin((2 * max(n_loc, 1), 8))
     lib.d2h(h_table, d_table)
+    # A ReferenceString is a fixed base: with bbg_set_srs_precompute on (the shims' default), registering it also builds its
+    # pre-doubled windows on the device, once — the GPU form of generate_pippenger_precompute_table / pippenger_precomputed
+    # (scalar_multiplication.cpp:90-129, :478-573) — and every MSM that names the table adds all windows into one bucket set.
+    lib.set_srs_precompute(not args.no_srs_precompute)
+    t_reg = time.perf_counter()
     lib.srs_register(h_table)
+    srs_register_ms = (time.perf_counter() - t_reg) * 1e3
+    d_plain_table = d_table  # an unregistered copy of the same table: plain Pippenger windows
+    d_table, fb_c, fb_windows = lib.srs_device_table(h_table) if n_loc else (d_table, 0, 0)
 
     # ---- NTT inputs --------------------------------------------------------------------------------------
     h_poly_n = pin((max(P, 1), n, 4))
@@ -570,7 +582,8 @@ def run_b200(args, rank, local_rank, world):
     def msm_only():
         lib.msm_partial_dev(d_scalars, d_table, n_loc)
 
-    ops_ms = {"msm_2p%d" % log_n: time_op(msm_only, host_finish=True)}
+    ops_ms = {"msm_2p%d" % log_n: time_op(msm_only, host_finish=True),
+              "msm_2p%d_plain_windows" % log_n: time_op(lambda: lib.msm_partial_dev(d_scalars, d_plain_table, n_loc), host_finish=True)}
     if n_loc >= 1024:
         # degenerate digit distribution (constant polynomials do occur in a prover): every scalar equal, so each window's
         # entries fall into one bucket — the block-reduction fix-up path
@@ -694,6 +707,8 @@ def run_b200(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x8 Montgomery (bn254 Fq/Fr)", "data": "synthetic", "config": workload_config(args, world),
             "components_ms": ops_ms, "clocks": clocks,
+            "msm_fixed_base": {"window_bits": fb_c, "windows": fb_windows, "srs_register_ms": srs_register_ms,
+                               "table_mib": (fb_windows * n_loc * 128) >> 20},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "note": "the reference-signature calls: 1 x bbg_msm_g1 (blocking, registered SRS) + %d x single-polynomial bbg_ntt_fr on "
                             "aligned_alloc (pageable) buffers; long-lived buffers page-locked in place by the library on their second "
@@ -744,6 +759,7 @@ def main():
     ap.add_argument("--no-prove", action="store_true", help="skip the full-prover leg (BASELINE configs[4])")
     ap.add_argument("--no-msm26", action="store_true", help="skip the 2^26-point MSM leg (BASELINE configs[3])")
     ap.add_argument("--log-big", type=int, default=26, help="log2 of the large synthetic MSM (BASELINE configs[3]: 26)")
+    ap.add_argument("--no-srs-precompute", action="store_true", help="plain Pippenger windows for the registered SRS too (no fixed-base tables)")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e, microbench and CPU-baseline legs (short runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

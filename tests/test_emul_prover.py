@@ -49,3 +49,13 @@ def test_resident_prover_emulated_matches_cpu_reference(srs, composer, log_gates
     assert emu["n"] == cpu["n"] and emu["widgets"] == cpu["widgets"]
     for k, v in cpu["proof"].items():
         assert emu["proof"][k] == v, k
+
+
+def test_degenerate_circuit_with_infinity_commitment_verifies_emulated(srs):
+    """0 / 1 witnesses only: T_HI is the point at infinity (unspecified limbs on the reference side, group.hpp:143-146, which
+    enter the next challenge): the proof must verify on both builds and agree up to that commitment."""
+    cpu = run("prover_cpu", 6, "bool_degenerate")
+    emu = run("prover_gpu_emul", 6, "bool_degenerate")
+    assert cpu["verified"] and emu["verified"]
+    for k in ("W_L", "W_R", "W_O", "Z_1", "T_LO", "T_MID"):
+        assert emu["proof"][k] == cpu["proof"][k], k

@@ -260,6 +260,53 @@ def test_msm_full_size_closed_form_and_reference(lib, log_n):
         r.ref_aligned_free(tbuf)
 
 
+@pytest.mark.parametrize("log_n,parts", [(24, 1), (26, 1), (26, 8)])
+def test_msm_configs3_large_synthetic_closed_form(lib, log_n, parts):
+    """BASELINE configs[3]: 2^26 synthetic points (a0 + i d) G generated on the device, uniform scalars.  No CPU oracle
+    finishes this size in seconds, so the check is the size-independent closed form sum k_i (a0 + i d) G =
+    [(sum k_i (a0 + i d)) mod r] G (one exact Fr dot product on the host, one 1-point MSM); parts = 8: the same points as 8
+    point-range shards (the multi-GPU cut, scalar_multiplication.cpp:703-728) run one after another on this device, partials
+    folded on the host.  Same kernels and planner as the bench's msm_2p26 leg."""
+    import sys
+
+    if H.ROOT not in sys.path:
+        sys.path.insert(0, H.ROOT)
+    from barretenberg_b200 import parallel
+    from barretenberg_b200 import synthetic as S
+
+    n = 1 << log_n
+    a0, d = 0x7654321, 0xABCDE
+    BLK = 1 << 20
+    partials, total = [], 0
+    for part in range(parts):
+        lo, hi = parallel.shard_range(n, part, parts)
+        n_loc = hi - lo
+        d_points = lib.dev_alloc(n_loc * 64)
+        d_table = lib.dev_alloc(n_loc * 128)
+        lib.generate_multiples_dev(S.to_limbs(S.mont(a0 + lo * d)), S.to_limbs(S.mont(d)), d_points, n_loc)
+        lib.generate_pippenger_point_table_dev(d_points, d_table, n_loc)
+        lib.sync()
+        lib.dev_free(d_points)
+        d_scalars = lib.dev_alloc(n_loc * 32)
+        for pos in range(lo, hi, BLK):
+            piece = S.random_field(9000 + pos // BLK, min(BLK, hi - pos))
+            lib.h2d(d_scalars + (pos - lo) * 32, piece)
+            total = (total + S.dot_mod_r(piece, a0 + pos * d, d)) % S.FR_MODULUS
+        partials.append(lib.msm_partial_dev(d_scalars, d_table, n_loc))
+        lib.dev_free(d_scalars)
+        lib.dev_free(d_table)
+    got = lib.fold_partials(np.stack(partials))
+    d_g, d_gt, d_s1 = lib.dev_alloc(64), lib.dev_alloc(128), lib.dev_alloc(32)
+    lib.generate_multiples_dev(S.to_limbs(S.mont(1)), S.to_limbs(0), d_g, 1)
+    lib.generate_pippenger_point_table_dev(d_g, d_gt, 1)
+    lib.h2d(d_s1, S.to_limbs(S.mont(total)).reshape(1, 4))
+    expect = lib.msm_dev(d_s1, d_gt, 1)
+    for p_ in (d_g, d_gt, d_s1):
+        lib.dev_free(p_)
+    assert not H.is_infinity(got)
+    assert (got == expect).all()
+
+
 def test_msm_sharded_partials_fold(lib):
     """configs[2] on one GPU: 8 point-range shards -> XYZZ partials -> host fold == whole MSM."""
     n = 1 << 14

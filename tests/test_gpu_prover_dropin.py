@@ -124,3 +124,21 @@ def test_resident_prover_on_every_gpu_of_the_box(srs, log_gates, composer):
     assert classic["verified"]
     for k, v in cpu["proof"].items():
         assert classic["proof"][k] == v, k
+
+
+@pytest.mark.parametrize("binary", ["prover_gpu", "prover_gpu_classic"])
+@pytest.mark.parametrize("log_gates", [6, 10])
+def test_degenerate_circuit_with_infinity_commitment_verifies(srs, log_gates, binary):
+    """A circuit of 0 / 1 witnesses only (the reference's own bool-composer test circuit): the quotient has degree < 2n, so
+    T_HI is the point at infinity, whose coordinates the reference leaves unspecified (groups/group.hpp:143-146) and then
+    hashes into the next challenge (waffle/proof_system/challenge.hpp:15-23).  Byte identity is therefore only defined up to
+    that commitment; what must hold on both builds: the reference verifier accepts the proof, and everything committed
+    before the infinity point is identical."""
+    H.require_built(binary)
+    cpu = run("prover_cpu", log_gates, composer="bool_degenerate")
+    gpu = run(binary, log_gates, repeat=2, composer="bool_degenerate")
+    assert cpu["verified"], "the reference rejects its own degenerate proof"
+    assert gpu["verified"] and gpu["repeat_mismatches"] == 0
+    assert gpu["n"] == cpu["n"]
+    for k in ("W_L", "W_R", "W_O", "Z_1", "T_LO", "T_MID"):
+        assert gpu["proof"][k] == cpu["proof"][k], k

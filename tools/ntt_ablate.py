@@ -28,7 +28,7 @@ def one(path):
     lib.d2h(y0, d0)
     lib.dev_free(d0)
     out["round_trip_ok"] = bool((x0 == y0).all())
-    for log_n, op in ((20, "fft"), (22, "coset_fft")):
+    for log_n, op in ((20, "fft"), (21, "coset_fft"), (22, "coset_fft")):
         n, batch = 1 << log_n, 8
         x = np.random.default_rng(1).integers(0, 1 << 60, size=(batch * n, 4), dtype=np.uint64)
         d = lib.dev_alloc(x.nbytes)
