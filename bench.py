@@ -565,6 +565,16 @@ def run_b200(args, rank, local_rank, world):
     dev_ms = max_over_ranks(max(dev_ms, wall_ms))  # the MSM's host-side fold is part of the step: take the longer clock
     value = dev_ms / args.steps
 
+    if args.steps_only:
+        # launch lists under ncu: nothing but identical steps after the set-up, so kernel shares compare with `kernels`
+        if rank == 0:
+            print(json.dumps({"metric": "ms_per_step_msm2p%d_plus_ntt_batch" % log_n, "value": value, "unit": "ms", "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "gpu_launches": int(launches), "steps_only": True}))
+        barrier()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- per-op device timings (events on the library stream) ------------------------------------------------
     def time_op(fn, reps=3, host_finish=False):
         fn()
@@ -672,7 +682,16 @@ def run_b200(args, rank, local_rank, world):
         n4 = 4 * n
         if top in ("ntt_pass_a", "ntt_pass_b"):
             # per step the pass kernel runs on: P polys x (fft, ifft at n) and P polys x coset_fft at 4n
-            total_macs = P * (macs["fft"] + macs["ifft"] + macs["coset_fft_4n"]) / 2.0  # two passes share the transform's products
+            # a transform's reference-algorithm products are attributed to the two pass kernels by the butterfly stages each
+            # one executes (2^20 = 2^9 x 2^11: 9 of 20 stages in pass A; 2^22 = 2^11 x 2^11: half each); ifft's n extra
+            # products (x 1/n) and coset_fft's 4n (x g^i) ride on pass A's matrix
+            a_share_n = (9.0 / 20.0) if log_n == 20 else ((log_n + 1) // 2) / float(log_n)
+            a_share_4n = ((log_n + 3) // 2) / float(log_n + 2)
+            mpm = MAC_PER_FIELD_MUL
+            pass_a_macs = (macs["fft"] * a_share_n + (macs["ifft"] - n * mpm) * a_share_n + n * mpm
+                           + (macs["coset_fft_4n"] - n4 * mpm) * a_share_4n + n4 * mpm)
+            all_macs = macs["fft"] + macs["ifft"] + macs["coset_fft_4n"]
+            total_macs = P * (pass_a_macs if top == "ntt_pass_a" else all_macs - pass_a_macs)
             total_bytes = P * (2 * n + n4) * 64.0  # read + write 32 B per element per pass
             per_launch_macs = total_macs / kern[top]["launches_per_step"]
             per_launch_bytes = total_bytes / kern[top]["launches_per_step"]
@@ -680,17 +699,39 @@ def run_b200(args, rank, local_rank, world):
             per_launch_macs = macs["msm_mixed_adds"] * (n_loc / n) if top == "msm_accumulate" else 0.0
             per_launch_bytes = n_loc * 96.0
         dur_s = kern[top]["ms_per_launch"] * 1e-3
-        traffic = None
+        # ncu evidence for the same kernel (tools/ncu_metrics_json.py on the committed --set full capture): DRAM traffic per
+        # launch and the multiply pipe's measured activity — what the pipe really did, next to the algorithmic fraction
+        traffic, ncu_rows = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(top)
-        except (OSError, ValueError):
+            with open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json")) as f:
+                ncu_all = json.load(f)
+            ncu_rows = {k: v for k, v in ncu_all.items() if k.startswith(top) and isinstance(v, dict)}
+            # traffic is quoted per average launch like `achieved`: weight the captured launches by the step's mix
+            if top in ("ntt_pass_a", "ntt_pass_b"):
+                l1_n, l2_n = (9, 11) if log_n == 20 else ((log_n + 1) // 2, log_n - (log_n + 1) // 2)
+                l1_4n = (log_n + 3) // 2
+                ka = "%s_L%d" % (top, l1_n if top == "ntt_pass_a" else l2_n)
+                kb = "%s_L%d" % (top, l1_4n if top == "ntt_pass_a" else log_n + 2 - l1_4n)
+                if ka in ncu_rows and kb in ncu_rows and P == BATCH:
+                    traffic = (2 * ncu_rows[ka]["traffic_bytes"] + ncu_rows[kb]["traffic_bytes"]) / 3.0
+            elif top in ncu_rows:
+                traffic = ncu_rows[top]["traffic_bytes"]
+        except (OSError, ValueError, KeyError):
             pass
         roofline = {
             "kernel": top, "bound": "imad", "achieved": per_launch_macs / dur_s / 1e9, "peak": mac_peak / 1e9, "unit": "GMAC/s",
             "frac": per_launch_macs / dur_s / mac_peak, "traffic": traffic,
-            "note": "INT32 multiply pipe, not HBM or tensor: achieved = reference-algorithm 32x32->64 multiply-adds (SURVEY.md §8d) / "
-                    "CUDA-event kernel time; peak = dependency-free mad.wide.u32 rate measured in this run (narrow IMAD issue rate %.3g/s)" % peaks["imad_per_s"],
+            "algorithmic_bytes": per_launch_bytes,
+            "ncu": {"source": "profiles/ncu_kernel_metrics.json (ncu --set full of tools/ncu_target.py, same kernels, 1 x B200)",
+                    "launches": ncu_rows,
+                    "pipe_active_pct": (None if not ncu_rows else
+                                        {k: v["fmaheavy_pct"] for k, v in ncu_rows.items()})},
+            "note": "INT32 multiply pipe, not HBM or tensor: achieved = reference-algorithm 32x32->64 multiply-adds (SURVEY.md §8d; a "
+                    "transform's products attributed to the pass kernels by the butterfly stages each executes) / CUDA-event kernel time; "
+                    "peak = dependency-free mad.wide.u32 rate measured in this run (narrow IMAD issue rate %.3g/s).  frac is ALGORITHMIC: "
+                    "the kernels issue fewer multiply slots than the reference's 136-MAC products imply (precomputed-quotient twiddle "
+                    "products 214 instead of 264 slots, trivial twiddles skipped), so what the pipe really did is ncu.pipe_active_pct "
+                    "(sm__pipe_fmaheavy_cycles_active of the committed capture), not frac" % peaks["imad_per_s"],
             "hbm": {"achieved": per_launch_bytes / dur_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": per_launch_bytes / dur_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src},
         }
@@ -760,6 +801,7 @@ def main():
     ap.add_argument("--no-msm26", action="store_true", help="skip the 2^26-point MSM leg (BASELINE configs[3])")
     ap.add_argument("--log-big", type=int, default=26, help="log2 of the large synthetic MSM (BASELINE configs[3]: 26)")
     ap.add_argument("--no-srs-precompute", action="store_true", help="plain Pippenger windows for the registered SRS too (no fixed-base tables)")
+    ap.add_argument("--steps-only", action="store_true", help="set-up, warm-up and timed steps only (launch lists under ncu)")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e, microbench and CPU-baseline legs (short runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -25,7 +25,10 @@ def main():
     os.environ.setdefault("BBG_MULTI_MIN_SHARD", "512")
     lib = bb.Library(devices=list(range(g)))
     assert lib.device_count() == g
-    for log_n in (13, 16, 18):
+    for log_n, precompute in ((13, False), (16, False), (18, False), (14, True), (17, True), (19, True)):
+        # precompute: every device also builds the fixed-base windows of its replica when the table is registered
+        # (bbg_set_srs_precompute) and the per-device point ranges take the one-bucket-set form
+        lib.set_srs_precompute(precompute)
         n = 1 << log_n
         a0, d = 0x1234567 + log_n, 0x89ABC
         # table built on the primary device, then registered from the host copy (what ReferenceString + the shim do)
@@ -37,7 +40,9 @@ def main():
         lib.d2h(table, d_table)
         lib.dev_free(d_points)
         lib.dev_free(d_table)
-        lib.srs_register(table)
+        keep = lib.srs_register(table)
+        if precompute and n >= 1024:
+            assert lib.srs_device_table(keep)[2] >= 6, "fixed-base windows were not built"
         scs = [S.random_field(100 * log_n + i, n) for i in range(4)]
         scs[1][: n // 2] = scs[1][0]  # one giant bucket per window in the first half
         scs[2][:] = 0
@@ -60,6 +65,7 @@ def main():
         for t, i in zip(tickets, (0, 3)):
             assert (lib.msm_finish(t) == expect[i]).all(), ("launch", log_n, i)
         lib.srs_unregister(table)
+    lib.set_srs_precompute(False)
     if H.have_ref():
         n = 1 << 16
         table, a0, d = H.generator_multiples_table(3, n)
