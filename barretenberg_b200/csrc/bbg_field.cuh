@@ -78,7 +78,7 @@ BBG_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b)
 {
     uint32_t c;
 #if defined(__CUDA_ARCH__)
-    asm("add.cc.u32 %0, %9, %17;\n\t"
+    asm volatile("add.cc.u32 %0, %9, %17;\n\t"
         "addc.cc.u32 %1, %10, %18;\n\t"
         "addc.cc.u32 %2, %11, %19;\n\t"
         "addc.cc.u32 %3, %12, %20;\n\t"
@@ -108,7 +108,7 @@ BBG_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b)
 {
     uint32_t c;
 #if defined(__CUDA_ARCH__)
-    asm("sub.cc.u32 %0, %9, %17;\n\t"
+    asm volatile("sub.cc.u32 %0, %9, %17;\n\t"
         "subc.cc.u32 %1, %10, %18;\n\t"
         "subc.cc.u32 %2, %11, %19;\n\t"
         "subc.cc.u32 %3, %12, %20;\n\t"
@@ -149,7 +149,7 @@ BBG_HD void mul_row(uint32_t* acc, const uint32_t* x, uint32_t y)
 BBG_HD void mad_row_carry(uint32_t* acc, uint32_t& top, const uint32_t* x, uint32_t y)
 {
 #if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+    asm volatile("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
         "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
         "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
         "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
@@ -179,7 +179,7 @@ BBG_HD void mad_row_carry(uint32_t* acc, uint32_t& top, const uint32_t* x, uint3
 BBG_HD void mad_row(uint32_t* acc, const uint32_t* x, uint32_t y)
 {
 #if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+    asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
         "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
         "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
         "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
@@ -202,7 +202,7 @@ BBG_HD void mad_row(uint32_t* acc, const uint32_t* x, uint32_t y)
 BBG_HD void shift_mad_row(uint32_t* sh, uint32_t& e0, const uint32_t* x, uint32_t y)
 {
 #if defined(__CUDA_ARCH__)
-    asm("add.cc.u32 %8, %8, %1;\n\t"
+    asm volatile("add.cc.u32 %8, %8, %1;\n\t"
         "madc.lo.cc.u32 %0, %9, %13, %2;\n\t"
         "madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
         "madc.lo.cc.u32 %2, %10, %13, %4;\n\t"
