@@ -756,4 +756,58 @@ BBG_HD void store_fe(void* p, const fe& a)
     q[1] = hi;
 }
 
+// The same for pointers KNOWN to be global memory, 32-byte aligned: one 256-bit access per element (sm_100 has
+// ld / st.global.v8.b32 -> LDG.E.256 / STG.E.256): half the load / store instructions of the two-quadword form and a whole
+// 32-byte sector per lane, which is what the strided accesses of the NTT passes and the MSM's point gathers are made of.
+BBG_HD fe load_fe_global(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    fe r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p)
+                 : "memory");
+    return r;
+#else
+    return load_fe(p);
+#endif
+}
+// read-only data (tables, matrices, points) through the non-coherent path.  volatile on purpose: a plain asm counts as
+// speculatable, and the compiler did move such a load above the null check that guards an optional table (illegal address)
+BBG_HD fe load_fe_const(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    fe r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "l"(p));
+    return r;
+#else
+    return load_fe(p);
+#endif
+}
+// 256-bit load through the ordinary (coherent) path, no ordering against the surrounding stores
+BBG_HD fe load_fe_wide(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    fe r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+#else
+    return load_fe(p);
+#endif
+}
+BBG_HD void store_fe_global(void* p, const fe& a)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]),
+                 "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7])
+                 : "memory");
+#else
+    store_fe(p, a);
+#endif
+}
+
 } // namespace bbg

@@ -205,5 +205,30 @@ BBG_HD void store_xyzz(void* p, const xyzz_pt& a)
     store_fe((char*)p + 64, a.zz);
     store_fe((char*)p + 96, a.zzz);
 }
+// the same for pointers known to be GLOBAL memory (32-byte aligned): one 256-bit access per coordinate (bbg_field.cuh)
+BBG_HD affine_pt load_affine_const(const void* p) // read-only tables (the SRS)
+{
+    affine_pt r;
+    r.x = load_fe_const(p);
+    r.y = load_fe_const((const char*)p + 32);
+    return r;
+}
+BBG_HD xyzz_pt load_xyzz_global(const void* p)
+{
+    xyzz_pt r;
+    r.x = load_fe_wide(p);
+    r.y = load_fe_wide((const char*)p + 32);
+    r.zz = load_fe_wide((const char*)p + 64);
+    r.zzz = load_fe_wide((const char*)p + 96);
+    return r;
+}
+BBG_HD void store_xyzz_global(void* p, const xyzz_pt& a)
+{
+    store_fe_global(p, a.x);
+    store_fe_global((char*)p + 32, a.y);
+    store_fe_global((char*)p + 64, a.zz);
+    store_fe_global((char*)p + 96, a.zzz);
+}
+
 
 } // namespace bbg

@@ -301,9 +301,20 @@ __global__ void msm_scatter_kernel(const uint32_t* digits, const uint32_t* ranks
 }
 
 // ---- 4. accumulate ---------------------------------------------------------------------------------
+// BBG_MSM_WIDE (default 1): the point gathers and the bucket stores of the accumulate pass as 256-bit accesses
+#ifndef BBG_MSM_WIDE
+#define BBG_MSM_WIDE 1
+#endif
+#if BBG_MSM_WIDE
+#define MSM_LOAD_POINT(p) load_affine_const(p)
+#define MSM_STORE_BUCKET(p, v) store_xyzz_global((p), (v))
+#else
+#define MSM_LOAD_POINT(p) load_affine(p)
+#define MSM_STORE_BUCKET(p, v) store_xyzz((p), (v))
+#endif
 BBG_D affine_pt fetch_point(const fe* table, uint32_t entry)
 {
-    affine_pt p = load_affine(table + 2 * (size_t)(entry & 0x7fffffffu));
+    affine_pt p = MSM_LOAD_POINT(table + 2 * (size_t)(entry & 0x7fffffffu));
     if (entry >> 31) p.y = Fq::neg(p.y);
     return p;
 }
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* 
     {
         if (i == bucket_end)
         {
-            store_xyzz(is_head ? head + 4 * slice : buckets + 4 * (size_t)b, acc);
+            MSM_STORE_BUCKET(is_head ? head + 4 * slice : buckets + 4 * (size_t)b, acc);
             acc = G1::infinity();
             is_head = false;
             do
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* 
     if (is_head) dst = head + 4 * slice;              // bucket began before this slice
     else if (bucket_end <= end) dst = buckets + 4 * (size_t)b; // complete inside the slice
     else dst = tail + 4 * slice;                      // continues into the next slice
-    store_xyzz(dst, acc);
+    MSM_STORE_BUCKET(dst, acc);
 }
 
 // ---- 5. fix-up of buckets that span slices; empty buckets become infinity ----------------------------

@@ -73,6 +73,37 @@ __device__ __noinline__ fe fr_mul_shared(const fe a, const fe b) { return Fr::mu
 #ifndef BBG_NTT_PREFETCH
 #define BBG_NTT_PREFETCH 1
 #endif
+// how the pass kernels read global memory: 0 two 128-bit loads, 1 one 256-bit load through the non-coherent path,
+// 2 one 256-bit load through the ordinary path; per pass (A: column tiles, B: row tiles) and for pass A's matrix.
+// Measured (r02, batch 8; fft 2^20 / coset_fft 2^21 / 2^22 in ms): all 128-bit 1.360 / 2.97 / 6.16; 256-bit stores and
+// loads as set below 1.297 / 3.00 / 6.09 (pass B 2^22 2.70 -> 2.60, pass A 2^9-point columns 0.650 -> 0.625; pass A on
+// single-column tiles does not gain, whichever way it loads)
+#ifndef BBG_NTT_LOAD_A
+#define BBG_NTT_LOAD_A 2
+#endif
+#ifndef BBG_NTT_LOAD_B
+#define BBG_NTT_LOAD_B 1
+#endif
+#ifndef BBG_NTT_LOAD_MAT
+#define BBG_NTT_LOAD_MAT 2
+#endif
+#ifndef BBG_NTT_STORE_A
+#define BBG_NTT_STORE_A 1
+#endif
+#ifndef BBG_NTT_STORE_B
+#define BBG_NTT_STORE_B 1
+#endif
+template <int MODE> BBG_D void ntt_store(fe* p, const fe& x)
+{
+    if constexpr (MODE == 1) store_fe_global(p, x);
+    else store_fe(p, x);
+}
+template <int MODE> BBG_D fe ntt_load(const fe* p)
+{
+    if constexpr (MODE == 1) return load_fe_const(p);
+    else if constexpr (MODE == 2) return load_fe_wide(p);
+    else return load_fe(p);
+}
 #if BBG_NTT_ABLATE == 1 || BBG_NTT_ABLATE == 2
 #define NTT_SYNC() ((void)0)
 #elif defined(__CUDA_ARCH__)
@@ -328,13 +359,19 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
             x[m] = Fr::zero();
             x[m].v[0] = (uint32_t)g;
 #else
-            x[m] = load_fe(src + g);
+            x[m] = ntt_load<COLS_LOW ? BBG_NTT_LOAD_A : BBG_NTT_LOAD_B>(src + g); // (a pass never writes the buffer it reads)
 #endif
 #if BBG_NTT_PREFETCH
             if (COLS_LOW && p.mat != nullptr) prefetch_l2(p.mat + g);
 #endif
 #endif
-            if (COLS_LOW && p.vec != nullptr) x[m] = NTT_MUL(x[m], load_fe(p.vec + k));
+        }
+        // the coset pre-scale in a loop of its own: the element loads above are volatile asm statements, which the compiler keeps
+        // in program order against the (volatile) products - interleaved, every load would wait for the product before it
+        if (COLS_LOW && p.vec != nullptr)
+        {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) x[m] = NTT_MUL(x[m], load_fe(p.vec + TM::k_of(TM::template slot<B>(t, m))));
         }
     }
     else
@@ -369,9 +406,9 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
                 const size_t o = ((size_t)isub << rest) + ((size_t)tile << TM::CLOG) + c;
 #if BBG_NTT_ABLATE == 5
                 const fe y5 = NTT_MUL(x[m], x[(m + 1) & 7]);
-                if (y5.v[0] == 0x12345u && y5.v[7] == 0x777u) store_fe(dst + o, y5);
+                if (y5.v[0] == 0x12345u && y5.v[7] == 0x777u) store_fe_global(dst + o, y5);
 #else
-                store_fe(dst + o, NTT_MUL(x[m], load_fe(p.mat + o)));
+                ntt_store<BBG_NTT_STORE_A>(dst + o, NTT_MUL(x[m], ntt_load<BBG_NTT_LOAD_MAT>(p.mat + o)));
 #endif
             }
             else
@@ -380,12 +417,12 @@ BBG_D void do_step(fe (&x)[8], const PassParams& p, const fe* src, fe* dst, int 
                 size_t o = row + ((size_t)isub << rest);
                 if (p.scatter_shift) o <<= p.scatter_shift; // (dst already points at this block's column)
                 fe y = x[m];
-                if (p.vec != nullptr) y = NTT_MUL(y, load_fe(p.vec + isub));
+                if (p.vec != nullptr) y = NTT_MUL(y, load_fe_const(p.vec + isub));
                 if (p.has_post_const) y = NTT_MUL(y, p.post_const);
 #if BBG_NTT_ABLATE == 5
                 if (y.v[0] == 0x12345u && y.v[7] == 0x777u)
 #endif
-                store_fe(dst + o, Fr::reduce(y));
+                ntt_store<BBG_NTT_STORE_B>(dst + o, Fr::reduce(y));
             }
         }
     }
@@ -435,7 +472,28 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
         if (work0 < p.total_work) stage_tile<L, COLS_LOW>(p, p.src + (size_t)(work0 % batch) * p.batch_stride, work0 / batch, data);
     }
 #endif
-    for (int i = threadIdx.x; i < 16 * TWP; i += NT * TPC) tw[i] = p.sub_tw[i];
+    // twiddle image: 66 KiB per CTA by 16-byte cp.async (no register round trips: the plain copy loop was 33 dependent
+    // load-store iterations, ~14 us of prologue per kernel - 8% of a single 2^20 transform), with the first tile's inputs
+    // started towards L2 meanwhile
+    for (int i = threadIdx.x; i < 4 * TWP; i += NT * TPC) cp_async16(tw + 4 * i, p.sub_tw + 4 * i);
+    cp_async_commit();
+    {
+        const int work0 = blockIdx.x * TPC + half;
+        if (work0 < p.total_work)
+        {
+            typedef TileMap<L, COLS_LOW> TM;
+            const fe* src0 = p.src + (size_t)(work0 % batch) * p.batch_stride;
+            const int tile0 = work0 / batch, t = threadIdx.x & (NT - 1), rest = p.log_n - L;
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+            {
+                const int q = TM::template slot<L - 3>(t, m);
+                const int k = TM::k_of(q), c = TM::c_of(q);
+                prefetch_l2(COLS_LOW ? src0 + ((size_t)k << rest) + ((size_t)tile0 << TM::CLOG) + c : src0 + ((((size_t)tile0 << TM::CLOG) + c) << L) + k);
+            }
+        }
+    }
+    cp_async_wait_all();
     __syncthreads();
     for (int work = blockIdx.x * TPC + half; work < p.total_work; work += gridDim.x * TPC)
     {
@@ -480,13 +538,23 @@ __global__ void __launch_bounds__(NT) ntt_small_kernel(SmallParams p)
     uint32_t* tw = data + 8 * PLANE;
     const int L = p.log_n, n = 1 << L, t = threadIdx.x;
     fe* poly = p.coeffs + (size_t)blockIdx.x * p.batch_stride;
-    for (int i = t; i < 16 * TWP; i += NT) tw[i] = p.sub_tw[i];
+    {
+        // only the part of the image this size reads (entries e < n / 2 of each of the 16 planes), by 16-byte cp.async
+        const int per_plane = (pad((n >> 1) - 1) + 4) >> 2; // 16-byte chunks per plane covering words 0 .. pad(n / 2 - 1); <= TWP / 4
+        for (int i = t; i < 16 * per_plane; i += NT)
+        {
+            const int off = (i / per_plane) * TWP + 4 * (i % per_plane);
+            cp_async16(tw + off, p.sub_tw + off);
+        }
+        cp_async_commit();
+    }
     for (int i = t; i < n; i += NT)
     {
-        fe x = load_fe(poly + i);
-        if (p.pre != nullptr) x = Fr::mul(x, load_fe(p.pre + i));
+        fe x = load_fe_global(poly + i);
+        if (p.pre != nullptr) x = Fr::mul(x, load_fe_const(p.pre + i));
         sm_store(data, i, x);
     }
+    cp_async_wait_all();
     for (int s = L - 1; s >= 0; --s)
     {
         __syncthreads();
@@ -507,9 +575,9 @@ __global__ void __launch_bounds__(NT) ntt_small_kernel(SmallParams p)
     {
         const unsigned o = __brev((unsigned)i) >> (32 - L);
         fe y = sm_load(data, i);
-        if (p.post != nullptr) y = Fr::mul(y, load_fe(p.post + o));
+        if (p.post != nullptr) y = Fr::mul(y, load_fe_const(p.post + o));
         if (p.has_post_const) y = Fr::mul(y, p.post_const);
-        store_fe(poly + o, Fr::reduce(y));
+        store_fe_global(poly + o, Fr::reduce(y));
     }
 }
 

@@ -1,11 +1,4 @@
-O=gpurun_out/r2i_ntt_split.jsonl
-: > $O
-for sp in "" "20:9,21:10" "20:11,21:11" "20:9,21:11"; do
-  BBG_NTT_SPLIT=$sp python tools/ntt_ablate.py barretenberg_b200/libbbgpu.so >> $O 2>>gpurun_out/r2i_err.log
-done
-python - <<'PY'
-import json
-for l in open('gpurun_out/r2i_ntt_split.jsonl'):
-    d=json.loads(l); print(d['env'], d['round_trip_ok'], {k:v for k,v in d.items() if k.endswith('_ms')})
-PY
-tail -3 gpurun_out/r2i_err.log
+python tools/msm_variants.py --logs 20,17 2>gpurun_out/r2t_err.log | tee gpurun_out/r2t_msm_wide.jsonl
+python tools/msm_fixed_base.py --logs 20 --windows 0 2>>gpurun_out/r2t_err.log | cut -c1-400 | tee -a gpurun_out/r2t_msm_wide.jsonl
+python -m pytest tests/test_gpu_parity.py tests/test_shim_msm.py -m gpu -x -q -k "msm or shim" 2>&1 | tail -3
+tail -2 gpurun_out/r2t_err.log

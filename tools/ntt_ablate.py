@@ -49,6 +49,21 @@ def one(path):
             if k in prof:
                 out["%s_2p%d_%s_ms" % (op, log_n, k)] = round(prof[k][0] / prof[k][1], 4)
         lib.dev_free(d)
+    # single polynomial (what a prover's one-at-a-time calls and a rank with one polynomial see)
+    for log_n, op in ((20, "fft"), (22, "coset_fft"), (12, "fft")):
+        n = 1 << log_n
+        x = np.random.default_rng(2).integers(0, 1 << 60, size=(n, 4), dtype=np.uint64)
+        d = lib.dev_alloc(x.nbytes)
+        lib.h2d(d, x)
+        for _ in range(3):
+            lib.ntt_dev(op, d, log_n, batch=1)
+        lib.sync()
+        reps = 20
+        lib.timer_start()
+        for _ in range(reps):
+            lib.ntt_dev(op, d, log_n, batch=1)
+        out["%s_2p%d_batch1_ms" % (op, log_n)] = round(lib.timer_stop() / reps, 4)
+        lib.dev_free(d)
     print(json.dumps(out), flush=True)
 
 
