@@ -88,7 +88,8 @@ class Library:
             self.check(L.bbg_init(device if devices is None else int(devices[0])))
 
     FIELD_OPS = {"mul_coarse": 0, "sqr_coarse": 1, "mul_const": 2, "add_coarse": 3, "sub_coarse": 4, "reduce_once": 5, "neg": 6,
-                 "to_mont": 7, "from_mont": 8, "invert": 9, "sub_lazy": 10, "mul": 11, "mul_const_raw": 12}
+                 "to_mont": 7, "from_mont": 8, "invert": 9, "sub_lazy": 10, "mul": 11, "mul_const_raw": 12,
+                 "invert_binary": 13}
     G1_OPS = {"mixed_add": 0, "add_doubled": 1, "dbl_dbl": 2, "accumulate": 3, "add": 4, "endo_entry": 5, "dbl_affine": 6}
 
     def set_srs_precompute(self, on=True):

@@ -290,6 +290,14 @@ int bbg_init(int device)
     if (e != cudaSuccess || count == 0) return BBG_E_NO_DEVICE;
     if (device < 0 || device >= count) return BBG_E_BAD_ARGUMENT;
     BBG_CHECK(cudaSetDevice(device));
+    if (const char* gran = getenv("BBG_L2_FETCH_GRANULARITY")) // development: 32 / 64 / 128 bytes fetched per L2 miss (a hint to the driver)
+    {
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gran));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "bbgpu: L2 fetch granularity %zu -> %zu\n", before, after);
+    }
     if (g_stream == nullptr)
     {
         BBG_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
@@ -1124,7 +1132,7 @@ int bbg_field_selftest(int field, int op, const uint64_t* a, const uint64_t* b, 
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     BBG_CHECK(ensure_ready());
-    if (field < 0 || field > 1 || op < 0 || op > 12) return BBG_E_BAD_ARGUMENT;
+    if (field < 0 || field > 1 || op < 0 || op > 13) return BBG_E_BAD_ARGUMENT;
     return selftest_run(false, field, op, a, b, out, count);
 }
 int bbg_g1_selftest(int op, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t count)

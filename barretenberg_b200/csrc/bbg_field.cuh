@@ -731,6 +731,100 @@ template <typename FP> struct Field
         }
         return reduce(acc);
     }
+    // The same inverse by Kaliski's almost-inverse (binary extended Euclid on shifts, additions and subtractions only: no
+    // multiply-pipe work, ~1.4 * 254 short iterations) and a correcting power of two: phase one gives a^-1 * 2^k mod p with
+    // 254 <= k <= 508, then * (1/2)^k and * R^3 as Montgomery products restore the Montgomery form.  About a seventh of the
+    // Fermat chain's latency for a lone thread (what a batched inversion waits for); data-dependent time, which is fine here:
+    // nothing on this path is secret.  a = 0 gives 0, as a^(p-2) does.  Canonical result.
+    static BBG_HD fe invert_binary(const fe& a_in)
+    {
+        const fe a = reduce(a_in);
+        uint32_t u[8], v[8], r[8], s[8], t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            u[i] = FP::P(i);
+            v[i] = a.v[i];
+            r[i] = 0;
+            s[i] = 0;
+        }
+        s[0] = 1;
+        uint32_t k = 0;
+        // invariants: u s + v r = p, so r, s <= p while the loop runs and r < 2p after it
+        while ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) != 0)
+        {
+            if ((u[0] & 1u) == 0)
+            {
+                shr1(u);
+                shl1(s);
+            }
+            else if ((v[0] & 1u) == 0)
+            {
+                shr1(v);
+                shl1(r);
+            }
+            else
+            {
+                const uint32_t borrow = cc::sub8(t, u, v);
+                if (!borrow && (t[0] | t[1] | t[2] | t[3] | t[4] | t[5] | t[6] | t[7]) != 0) // u > v
+                {
+                    shr1(t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) u[i] = t[i];
+                    cc::add8(t, r, s);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[i] = t[i];
+                    shl1(s);
+                }
+                else
+                {
+                    cc::sub8(t, v, u);
+                    shr1(t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = t[i];
+                    cc::add8(t, s, r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s[i] = t[i];
+                    shl1(r);
+                }
+            }
+            ++k;
+        }
+        uint32_t pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = FP::P(i);
+        if (!cc::sub8(t, r, pl)) // r >= p
+        {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = t[i];
+        }
+        fe x;
+        cc::sub8(x.v, pl, r); // p - r = a^-1 2^k (as plain residues); r = 0 only for a = 0
+        // Montgomery form of 1/2: (R mod p) halved modulo p
+        fe half = one();
+        if (half.v[0] & 1u)
+        {
+            cc::add8(t, half.v, pl);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) half.v[i] = t[i];
+        }
+        shr1(half.v);
+        const fe r2 = constant([](int i) { return FP::R2(i); });
+        // x = A^-1 2^k with A = a R the input:  x * (2^-k R) / R = a^-1 / R,  then * (R^2 * R^2 / R) / R = a^-1 R
+        return reduce(mul(mul(x, pow_u64(half, k)), mul(r2, r2)));
+    }
+    static BBG_HD void shr1(uint32_t* x)
+    {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+        x[7] >>= 1;
+    }
+    static BBG_HD void shl1(uint32_t* x)
+    {
+#pragma unroll
+        for (int i = 7; i > 0; --i) x[i] = (x[i] << 1) | (x[i - 1] >> 31);
+        x[0] <<= 1;
+    }
 };
 
 typedef Field<FqParams> Fq;

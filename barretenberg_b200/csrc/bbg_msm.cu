@@ -148,14 +148,37 @@ BBG_HD uint32_t window_bits(const uint32_t k[4], int pos, int c)
 // ---- 1. digits -------------------------------------------------------------------------------------
 // (the counting atomic returns the entry's rank inside its bucket: the scatter then needs no atomics of its own)
 // set_stride: NB when every window has its own bucket set, 0 when all windows share one (fixed-base form)
+// A warp whose 32 lanes all count into the SAME bucket adds once (match.all, one instruction; lane 0 adds 32, each lane
+// takes its place behind the returned base): a polynomial with long runs of equal coefficients — constants, selectors,
+// 0 / 1 witnesses occur in the prover — otherwise sends 2^21 atomics per window to one address and the L2 atomic unit
+// serialises them (constant scalars at 2^20: digit pass 0.57 -> 0.10 ms).  Grouping lanes by value (match.any) would also
+// catch interleaved repetitions but iterates over the distinct values: +0.1 ms on uniform scalars, measured, so not that.
+BBG_D uint32_t count_into_bucket(uint32_t* counts, uint32_t key, bool counted)
+{
+#if defined(__CUDA_ARCH__)
+    int same = 0;
+    __match_all_sync(0xffffffffu, counted ? key : 0xffffffffu, &same);
+    if (same)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        uint32_t base = 0;
+        if (lane == 0 && counted) base = atomicAdd(&counts[key], 32u);
+        return __shfl_sync(0xffffffffu, base, 0) + lane;
+    }
+#endif
+    return counted ? atomicAdd(&counts[key], 1u) : 0u;
+}
 __global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uint32_t NB, uint32_t set_stride, uint32_t* digits, uint32_t* ranks,
                                   uint32_t* counts)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const fe k = Fr::from_mont(load_fe(scalars + i)); // scalar_multiplication.cpp:469-472
-    uint32_t half[2][4];
-    split_endo(k, half[0], half[1]);
+    const bool live = i < n; // (no early exit: every lane of a warp takes part in the aggregated counting)
+    uint32_t half[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+    if (live)
+    {
+        const fe k = Fr::from_mont(load_fe(scalars + i)); // scalar_multiplication.cpp:469-472
+        split_endo(k, half[0], half[1]);
+    }
     const size_t num_points = 2 * n;
     uint32_t carry[2] = { 0, 0 };
     for (int w = 0; w < W; ++w)
@@ -173,27 +196,24 @@ __global__ void msm_digits_kernel(const fe* scalars, size_t n, int c, int W, uin
                 neg = 0x80000000u;
                 carry[h] = 1;
             }
-            if (d != 0)
-            {
-                // a top-window digit above NB cannot occur for half scalars < 2^127 (the reference's wNAF makes the
-                // same assumption, wnaf.hpp:11); clamp defensively so no bucket index is ever out of range
-                if (d > NB) d = NB;
-                packed[h] = (d - 1) | neg;
-                rank[h] = atomicAdd(&counts[(size_t)w * set_stride + (d - 1)], 1u);
-            }
-            else
-            {
-                packed[h] = NO_DIGIT;
-            }
+            // a top-window digit above NB cannot occur for half scalars < 2^127 (the reference's wNAF makes the
+            // same assumption, wnaf.hpp:11); clamp defensively so no bucket index is ever out of range
+            if (d > NB) d = NB;
+            const bool counted = live && d != 0;
+            packed[h] = counted ? ((d - 1) | neg) : NO_DIGIT;
+            rank[h] = count_into_bucket(counts, (uint32_t)((size_t)w * set_stride + (d - 1)), counted);
         }
-        uint2 pair;
-        pair.x = packed[0];
-        pair.y = packed[1];
-        *(uint2*)(digits + (size_t)w * num_points + 2 * i) = pair;
-        uint2 rpair;
-        rpair.x = rank[0];
-        rpair.y = rank[1];
-        *(uint2*)(ranks + (size_t)w * num_points + 2 * i) = rpair;
+        if (live)
+        {
+            uint2 pair;
+            pair.x = packed[0];
+            pair.y = packed[1];
+            *(uint2*)(digits + (size_t)w * num_points + 2 * i) = pair;
+            uint2 rpair;
+            rpair.x = rank[0];
+            rpair.y = rank[1];
+            *(uint2*)(ranks + (size_t)w * num_points + 2 * i) = rpair;
+        }
     }
 }
 
@@ -319,6 +339,20 @@ BBG_D affine_pt fetch_point(const fe* table, uint32_t entry)
     return p;
 }
 
+// DIRECT: the entries ARE the points (what the pair-sum rounds below leave: affine points in bucket order, possibly the
+// point at infinity), no index array in between.
+template <bool DIRECT> BBG_D affine_pt accumulate_fetch(const fe* table, const uint32_t* sorted, uint32_t i)
+{
+    if (DIRECT)
+    {
+        affine_pt p;
+        p.x = load_fe_wide(table + 2 * (size_t)i);
+        p.y = load_fe_wide(table + 2 * (size_t)i + 1);
+        return p;
+    }
+    return fetch_point(table, sorted[i]);
+}
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* sorted, const uint32_t* offsets, uint32_t total_buckets,
                                                             const fe* table, uint32_t S, fe* buckets, fe* head, fe* tail)
 {
@@ -339,7 +373,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* 
     uint32_t bucket_end = offsets[b + 1];
     bool is_head = offsets[b] < start;
     xyzz_pt acc = G1::infinity();
-    affine_pt next = fetch_point(table, sorted[start]);
+    affine_pt next = accumulate_fetch<DIRECT>(table, sorted, start);
     for (uint32_t i = start; i < end; ++i)
     {
         if (i == bucket_end)
@@ -354,14 +388,367 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* 
             } while (bucket_end == i); // skip empty buckets
         }
         const affine_pt cur = next;
-        if (i + 1 < end) next = fetch_point(table, sorted[i + 1]);
-        acc = G1::madd(acc, cur);
+        if (i + 1 < end) next = accumulate_fetch<DIRECT>(table, sorted, i + 1);
+        if (!DIRECT || !G1::affine_is_infinity(cur)) acc = G1::madd(acc, cur);
     }
     fe* dst;
     if (is_head) dst = head + 4 * slice;              // bucket began before this slice
     else if (bucket_end <= end) dst = buckets + 4 * (size_t)b; // complete inside the slice
     else dst = tail + 4 * slice;                      // continues into the next slice
     MSM_STORE_BUCKET(dst, acc);
+}
+
+// ---- 3b. pair-sum rounds: batched AFFINE additions ahead of the accumulate pass -----------------------------------------
+// A mixed addition into an XYZZ accumulator costs 10 field products.  Two AFFINE points add with one inversion, three
+// products and a square — and inversions batch (Montgomery's trick: three more products per denominator plus one shared
+// inversion).  The sorted entry array is therefore first folded by R rounds of pairwise affine additions inside the buckets
+// (6 products per addition + the inversion's share), each round halving the entries, and only the remaining ~1/2^R of the
+// additions run through the accumulate pass.  What the reference's callers observe is the sum, not the order (SURVEY §8
+// note 3), so the result is unchanged.  NOT the default: on B200 the rounds turn a multiply-bound pass into an HBM-bound one
+// and lose (pick_pair_rounds below; profiles/r02_msm_pair_rounds.md) — selectable with BBG_MSM_PAIR_ROUNDS, tested either way.
+//
+// One round: the input is an array of affine points partitioned into bucket regions [start[b], start[b+1]), the first
+// count[b] positions of a region valid.  Positions are paired GLOBALLY, (2j, 2j+1) = pair slot j: two valid points of the
+// same bucket are added, anything else (a lone first / last point of a bucket, which the alignment leaves over) is copied.
+// The point at position p of bucket b goes to out_start[b] + (p >> 1) - (start[b] >> 1): with out_start[b] = (start[b] >> 1)
+// + b the regions of the next round follow in closed form (msm_pair_plan_kernel), no scan between rounds; the last round
+// writes to the dense offsets of a scan over the final counts, which is what the accumulate pass expects.
+//
+// A 256-thread CTA takes an item of 256 * B consecutive pair slots, warp w the slots [32 B w, 32 B (w + 1)), lane l every
+// 32nd of them (coalesced point loads and stores).  Forward: each thread walks its B slots, classifies them and multiplies
+// the denominators x2 - x1 (2 y for the rare P + P) into a running product, saving the prefix products to an L2-resident
+// scratch.  Then ONE inversion per CTA: a product tree over the 256 totals in shared memory, Fermat inversion of the root
+// by one thread, the tree walked back down.  Backward: each thread walks its slots in reverse, peels the inverse of each
+// denominator off the running inverse and finishes the addition.  An intermediate point at infinity (P + (-P)) is marked by
+// an all-ones top word of x and the reference's flag bit in y, values no reduced coordinate can take.
+constexpr int PAIR_NT = 256;
+constexpr int PAIR_CTAS_PER_SM = 2;
+constexpr uint32_t PAIR_BMAX = 96;
+constexpr uint32_t PAIR_BMIN = 8;
+constexpr int PAIR_MAX_ROUNDS = 4;
+constexpr uint32_t PAIR_BUCKET_MASK = (1u << 26) - 1u;
+constexpr uint32_t PAIR_A_OUT = 1u << 26, PAIR_B_OUT = 1u << 27, PAIR_B_SAME = 1u << 28;
+constexpr uint32_t PAIR_KIND_SHIFT = 29; // 0 nothing to compute, 1 add, 2 double, 3 the sum is the point at infinity
+constexpr uint32_t PAIR_INF_WORD = 0xffffffffu;
+
+struct PairParams
+{
+    const fe* src;             // points of this round (round 1: the point table, read through `sorted`)
+    const uint32_t* sorted;    // round 1 only: entry = table index | sign << 31
+    const uint32_t* in_start;  // [total_buckets + 1]
+    const uint32_t* in_count;  // [total_buckets], nullptr: every position of a region is valid (round 1)
+    const uint32_t* out_start; // [total_buckets]
+    fe* dst;
+    uint32_t total_buckets;
+    uint32_t bmax; // pair slots per thread and item, <= PAIR_BMAX
+    fe* prefix;    // scratch: gridDim.x * PAIR_BMAX * PAIR_NT field elements
+    uint32_t* rec; // scratch: gridDim.x * PAIR_BMAX * PAIR_NT words
+};
+
+BBG_HD bool pair_is_infinity(const fe& x) { return x.v[7] == PAIR_INF_WORD; }
+BBG_HD affine_pt pair_infinity()
+{
+    affine_pt r;
+    r.x = Fq::zero();
+    r.y = Fq::zero();
+    r.x.v[7] = PAIR_INF_WORD;
+    r.y.v[7] = 0x80000000u; // (group.hpp:133-151: what G1::affine_is_infinity tests)
+    return r;
+}
+// smallest b' >= b with start[b' + 1] > p, given start[b] <= p < start[total_buckets]: the bucket region holding position p
+BBG_D uint32_t pair_advance(const uint32_t* start, uint32_t total_buckets, uint32_t b, uint32_t p)
+{
+    for (int i = 0; i < 4; ++i)
+    {
+        if (start[b + 1] > p) return b;
+        ++b;
+    }
+    uint32_t lo = b, hi = total_buckets; // start[lo] <= p < start[hi]  (runs of empty buckets: constant scalars leave 2^18 of them)
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (start[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+BBG_D uint32_t pair_count(const PairParams& q, uint32_t b) { return q.in_count != nullptr ? q.in_count[b] : q.in_start[b + 1] - q.in_start[b]; }
+template <bool FIRST> BBG_D fe pair_load_x(const PairParams& q, uint32_t p)
+{
+    if (FIRST) return load_fe_const(q.src + 2 * (size_t)(q.sorted[p] & 0x7fffffffu));
+    return load_fe_wide(q.src + 2 * (size_t)p);
+}
+template <bool FIRST> BBG_D affine_pt pair_load(const PairParams& q, uint32_t p)
+{
+    if (FIRST) return fetch_point(q.src, q.sorted[p]);
+    affine_pt r;
+    r.x = load_fe_wide(q.src + 2 * (size_t)p);
+    r.y = load_fe_wide(q.src + 2 * (size_t)p + 1);
+    return r;
+}
+BBG_D void pair_store(const PairParams& q, uint32_t b, uint32_t j, const affine_pt& a)
+{
+    fe* d = q.dst + 2 * (size_t)(q.out_start[b] + j - (q.in_start[b] >> 1));
+    store_fe_global(d, a.x);
+    store_fe_global(d + 1, a.y);
+}
+
+BBG_D void pair_prefetch_l2(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); // (a hint: no register, no scoreboard entry)
+#else
+    (void)p;
+#endif
+}
+// the point at position p, or (first round) the table entry e = sorted[p] already in a register
+template <bool FIRST> BBG_D affine_pt pair_point(const PairParams& q, uint32_t p, uint32_t e)
+{
+    if (FIRST) return fetch_point(q.src, e);
+    return pair_load<false>(q, p);
+}
+
+template <bool FIRST> __global__ void __launch_bounds__(PAIR_NT, PAIR_CTAS_PER_SM) msm_pair_round_kernel(PairParams q)
+{
+    __shared__ __align__(16) uint32_t tree[2 * PAIR_NT * 8]; // product tree over the threads' totals: node i = node 2i * node 2i+1, leaves 256..511
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t E = q.in_start[q.total_buckets];
+    const uint32_t slots = (E >> 1) + (E & 1u);
+    // slots per thread: whole waves of the grid at no more than bmax slots
+    const uint32_t per_wave = (uint32_t)PAIR_NT * gridDim.x;
+    const uint32_t waves = (slots + per_wave * q.bmax - 1) / (per_wave * q.bmax);
+    uint32_t B = waves == 0 ? PAIR_BMIN : (slots + per_wave * waves - 1) / (per_wave * waves);
+    if (B < PAIR_BMIN) B = PAIR_BMIN;
+    if (B > q.bmax) B = q.bmax;
+    const uint32_t item_slots = (uint32_t)PAIR_NT * B;
+    const uint32_t items = (slots + item_slots - 1) / item_slots;
+    fe* prefix = q.prefix + (size_t)blockIdx.x * PAIR_BMAX * PAIR_NT;
+    uint32_t* rec = q.rec + (size_t)blockIdx.x * PAIR_BMAX * PAIR_NT;
+    // second position of pair slot j (the last slot of an odd-length array has none: its first position stands in, unused)
+    auto second = [&](uint32_t j) { return 2u * j + 1u < E ? 2u * j + 1u : 2u * j; };
+
+    for (uint32_t item = blockIdx.x; item < items; item += gridDim.x)
+    {
+        const uint32_t wbase = item * item_slots + warp * 32u * B + lane;
+        // ---- forward: classify, denominators, prefix products ----
+        // The x coordinates travel one slot ahead of their use and, in the first round, their table indices two slots ahead:
+        // a slot is one product, far too little to cover a gather from HBM behind an index load.
+        fe run = Fq::one();
+        uint32_t b = 0;
+        fe nxa = Fq::zero(), nxb = Fq::zero();
+        uint32_t ia = 0, ib = 0;
+        if (wbase < slots)
+        {
+            b = pair_advance(q.in_start, q.total_buckets, 0, 2u * wbase);
+            nxa = pair_load_x<FIRST>(q, 2u * wbase);
+            nxb = pair_load_x<FIRST>(q, second(wbase));
+            if (FIRST && B > 1 && wbase + 32u < slots)
+            {
+                ia = q.sorted[2u * (wbase + 32u)];
+                ib = q.sorted[second(wbase + 32u)];
+            }
+        }
+        for (uint32_t k = 0; k < B; ++k)
+        {
+            const uint32_t j = wbase + k * 32u;
+            uint32_t r = 0;
+            if (j < slots)
+            {
+                const fe xa = nxa, xb = nxb;
+                const uint32_t jn = j + 32u;
+                if (k + 1 < B && jn < slots)
+                {
+                    if (FIRST)
+                    {
+                        nxa = load_fe_const(q.src + 2 * (size_t)(ia & 0x7fffffffu));
+                        nxb = load_fe_const(q.src + 2 * (size_t)(ib & 0x7fffffffu));
+                        if (k + 2 < B && jn + 32u < slots)
+                        {
+                            ia = q.sorted[2u * (jn + 32u)];
+                            ib = q.sorted[second(jn + 32u)];
+                        }
+                    }
+                    else
+                    {
+                        nxa = load_fe_wide(q.src + 2 * (size_t)(2u * jn));
+                        nxb = load_fe_wide(q.src + 2 * (size_t)second(jn));
+                    }
+                }
+                const uint32_t p0 = 2u * j, p1 = p0 + 1u;
+                b = pair_advance(q.in_start, q.total_buckets, b, p0);
+                const uint32_t valid_end = q.in_start[b] + pair_count(q, b);
+                const bool a_valid = p0 < valid_end;
+                const bool same = p1 < q.in_start[b + 1];
+                bool b_valid = false;
+                if (same) b_valid = p1 < valid_end;
+                else if (p1 < E)
+                {
+                    const uint32_t b1 = pair_advance(q.in_start, q.total_buckets, b + 1, p1);
+                    b_valid = p1 < q.in_start[b1] + pair_count(q, b1);
+                }
+                r = b;
+                if (a_valid && b_valid && same)
+                {
+                    if (pair_is_infinity(xa)) r |= PAIR_B_OUT | PAIR_B_SAME; // 0 + B
+                    else if (pair_is_infinity(xb)) r |= PAIR_A_OUT;          // A + 0
+                    else
+                    {
+                        fe d = Fq::sub(xb, xa);
+                        uint32_t kind = 1;
+                        if (Fq::is_zero(d))
+                        {
+                            const affine_pt A = pair_load<FIRST>(q, p0), Bp = pair_load<FIRST>(q, p1);
+                            kind = 3; // A + (-A)
+                            if (Fq::is_zero(Fq::sub(A.y, Bp.y)))
+                            {
+                                d = Fq::dbl(A.y); // A + A: slope 3 x^2 / 2 y
+                                if (!Fq::is_zero(d)) kind = 2;
+                            }
+                        }
+                        if (kind != 3)
+                        {
+                            store_fe_global(prefix + (size_t)k * PAIR_NT + tid, run);
+                            run = Fq::mul(run, d);
+                        }
+                        r |= kind << PAIR_KIND_SHIFT;
+                    }
+                }
+                else
+                {
+                    if (a_valid) r |= PAIR_A_OUT;
+                    if (b_valid) r |= PAIR_B_OUT | (same ? PAIR_B_SAME : 0u);
+                }
+            }
+            rec[(size_t)k * PAIR_NT + tid] = r;
+        }
+        // ---- one inversion for the CTA ----
+        fe* node = (fe*)tree;
+        node[PAIR_NT + tid] = run;
+        for (uint32_t size = PAIR_NT / 2; size >= 1; size >>= 1)
+        {
+            __syncthreads();
+            if (tid < size) node[size + tid] = Fq::mul(node[2 * (size + tid)], node[2 * (size + tid) + 1]);
+        }
+        __syncthreads();
+#ifdef BBG_PAIR_FERMAT
+        if (tid == 0) node[1] = Fq::invert(node[1]);
+#else
+        if (tid == 0) node[1] = Fq::invert_binary(node[1]); // (a lone thread: ~35 K cycles against ~200 K for the Fermat chain)
+#endif
+        for (uint32_t size = 1; size < PAIR_NT; size <<= 1)
+        {
+            __syncthreads();
+            if (tid < size)
+            {
+                const uint32_t i = size + tid;
+                const fe inv = node[i], left = node[2 * i], right = node[2 * i + 1];
+                node[2 * i] = Fq::mul(inv, right);
+                node[2 * i + 1] = Fq::mul(inv, left);
+            }
+        }
+        __syncthreads();
+        fe inv = node[PAIR_NT + tid]; // 1 / (this thread's product)
+        __syncthreads();               // (the tree is rewritten by the next item)
+        // ---- backward: finish the additions ----
+        // The lines of the slot below are asked into L2 one slot ahead (in the first round behind indices read two ahead).
+        uint32_t ca = 0, cb = 0, na = 0, nb = 0; // first round: table entries of this slot / of the one below
+        auto entry_a = [&](uint32_t jj) { return jj < slots ? q.sorted[2u * jj] : 0u; };
+        auto entry_b = [&](uint32_t jj) { return jj < slots ? q.sorted[second(jj)] : 0u; };
+        if (FIRST)
+        {
+            const uint32_t jt = wbase + (B - 1) * 32u;
+            ca = entry_a(jt);
+            cb = entry_b(jt);
+            if (B > 1)
+            {
+                na = entry_a(jt - 32u);
+                nb = entry_b(jt - 32u);
+            }
+        }
+        for (uint32_t k = B; k-- > 0;)
+        {
+            const uint32_t j = wbase + k * 32u, p0 = 2u * j, p1 = p0 + 1u;
+            const uint32_t ea = ca, eb = cb;
+            if (k > 0)
+            {
+                if (FIRST)
+                {
+                    if (j - 32u < slots)
+                    {
+                        pair_prefetch_l2(q.src + 2 * (size_t)(na & 0x7fffffffu));
+                        pair_prefetch_l2(q.src + 2 * (size_t)(nb & 0x7fffffffu));
+                    }
+                    ca = na;
+                    cb = nb;
+                    if (k > 1)
+                    {
+                        na = entry_a(j - 64u);
+                        nb = entry_b(j - 64u);
+                    }
+                }
+                else if (j - 32u < slots)
+                    pair_prefetch_l2(q.src + 4 * (size_t)(j - 32u)); // (both points of a slot share a 128-byte line)
+            }
+            const uint32_t r = rec[(size_t)k * PAIR_NT + tid];
+            if ((r & ~PAIR_BUCKET_MASK) == 0) continue;
+            const uint32_t b0 = r & PAIR_BUCKET_MASK, kind = r >> PAIR_KIND_SHIFT;
+            if (kind == 1)
+            {
+                const affine_pt A = pair_point<FIRST>(q, p0, ea), Bp = pair_point<FIRST>(q, p1, eb);
+                const fe inv_d = Fq::mul(inv, load_fe_global(prefix + (size_t)k * PAIR_NT + tid));
+                inv = Fq::mul(inv, Fq::sub(Bp.x, A.x));
+                const fe lam = Fq::mul(Fq::sub(Bp.y, A.y), inv_d);
+                affine_pt S;
+                S.x = Fq::sub(Fq::sub(Fq::sqr(lam), A.x), Bp.x);
+                S.y = Fq::sub(Fq::mul(lam, Fq::sub(A.x, S.x)), A.y);
+                pair_store(q, b0, j, S);
+            }
+            else if (kind == 2)
+            {
+                const affine_pt A = pair_point<FIRST>(q, p0, ea);
+                const fe inv_d = Fq::mul(inv, load_fe_global(prefix + (size_t)k * PAIR_NT + tid));
+                inv = Fq::mul(inv, Fq::dbl(A.y));
+                const fe xx = Fq::sqr(A.x);
+                const fe lam = Fq::mul(Fq::add(Fq::dbl(xx), xx), inv_d);
+                affine_pt S;
+                S.x = Fq::sub(Fq::sub(Fq::sqr(lam), A.x), A.x);
+                S.y = Fq::sub(Fq::mul(lam, Fq::sub(A.x, S.x)), A.y);
+                pair_store(q, b0, j, S);
+            }
+            else if (kind == 3)
+                pair_store(q, b0, j, pair_infinity());
+            if (r & PAIR_A_OUT) pair_store(q, b0, j, pair_point<FIRST>(q, p0, ea));
+            if (r & PAIR_B_OUT)
+            {
+                const uint32_t b1 = (r & PAIR_B_SAME) ? b0 : pair_advance(q.in_start, q.total_buckets, b0 + 1, p1);
+                pair_store(q, b1, j, pair_point<FIRST>(q, p1, eb));
+            }
+        }
+    }
+}
+
+// Regions of every round from the sort's offsets, one thread per bucket (and one for the end marker b = total_buckets):
+// start_{r+1}[b] = (start_r[b] >> 1) + b, count_{r+1}[b] = number of pair slots the count_r[b] valid positions touch.
+// starts / counts: [rounds][total_buckets + 1], row r = the INPUT regions of round r (row 0 of starts is the offsets array
+// itself and is not written); final_counts[b] = what is left after the last round (scanned into the dense offsets).
+__global__ void msm_pair_plan_kernel(const uint32_t* offsets, uint32_t total_buckets, int rounds, uint32_t* starts, uint32_t* counts,
+                                     uint32_t* final_counts)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > total_buckets) return;
+    uint32_t s = offsets[b];
+    uint32_t n = b < total_buckets ? offsets[b + 1] - s : 0u;
+    const size_t row = (size_t)total_buckets + 1;
+    for (int r = 1; r <= rounds; ++r)
+    {
+        n = n == 0 ? 0u : ((s + n - 1u) >> 1) - (s >> 1) + 1u;
+        s = (s >> 1) + b;
+        if (r < rounds)
+        {
+            starts[(size_t)r * row + b] = s;
+            counts[(size_t)r * row + b] = n;
+        }
+    }
+    if (b < total_buckets) final_counts[b] = n;
 }
 
 // ---- 5. fix-up of buckets that span slices; empty buckets become infinity ----------------------------
@@ -952,6 +1339,24 @@ Plan make_plan(size_t n, int fixed_c = 0, uint32_t entry_stride = 0)
     return pl;
 }
 
+// Rounds of pairwise affine additions ahead of the accumulate pass (3b).  OFF unless BBG_MSM_PAIR_ROUNDS asks for them:
+// measured on B200 (r02, profiles/r02_msm_pair_rounds.md) the rounds need 30% fewer multiply-pipe slots than the accumulate
+// pass they replace but are bound by HBM instead: every entry's point is gathered twice (x for the denominators, x and y
+// again once the inverses exist), a 64-byte point costs a 128-byte line from a table far larger than L2, and round one
+// moves 4.8 GB (3.2 TB/s, the multiply pipe 42% busy) where the accumulate pass moves 1.9 GB at 88% — 2^20 points over
+// fixed-base windows: 3.33 ms with one round, 3.50 ms with three, against 3.04 ms without.
+int pick_pair_rounds(size_t max_entries, uint32_t total_buckets)
+{
+    (void)max_entries;
+    int rounds = 0;
+    if (const char* e = getenv("BBG_MSM_PAIR_ROUNDS")) // development / tests
+    {
+        const int v = atoi(e);
+        if (v >= 0 && v <= PAIR_MAX_ROUNDS && total_buckets <= PAIR_BUCKET_MASK) rounds = v;
+    }
+    return rounds;
+}
+
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // `batch` MSMs of the same size over the same point table in ONE pipeline on the current device: MSM b's windows become
@@ -994,6 +1399,21 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     pl.max_entries = single.max_entries * batch;
     pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
 
+    // pair-sum rounds (3b) fold the sorted entries before the accumulate pass, which then runs on what is left
+    const int pair_rounds = pick_pair_rounds(pl.max_entries, pl.total_buckets);
+    const size_t pair_row = (size_t)pl.total_buckets + 1;
+    const unsigned pair_grid = (unsigned)(PAIR_CTAS_PER_SM * bbg_rt::num_sms());
+    size_t pair_cap[PAIR_MAX_ROUNDS + 1] = { pl.max_entries }; // entries (with the holes between regions) after round r
+    for (int r = 1; r <= pair_rounds; ++r) pair_cap[r] = pair_cap[r - 1] / 2 + pl.total_buckets + 1;
+    uint32_t S_acc = pl.S;
+    size_t acc_slices = pl.max_slices;
+    if (pair_rounds > 0)
+    {
+        if (pair_cap[1] >= ((size_t)1 << 32)) return 1008;
+        S_acc = pick_slice(pair_cap[pair_rounds]);
+        acc_slices = (pair_cap[pair_rounds] + S_acc - 1) / S_acc;
+    }
+
     // carve the workspace
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
@@ -1006,9 +1426,9 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     const uint32_t scan_blocks = (pl.total_buckets + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
     const size_t o_spine = carve(((size_t)scan_blocks + 1) * 4);
     const size_t o_buckets = carve((size_t)pl.total_buckets * 128);
-    const size_t o_head = carve(pl.max_slices * 128);
-    const size_t o_tail = carve(pl.max_slices * 128);
-    const size_t o_work_list = carve((pl.max_slices / FIXUP_SERIAL_SPAN + 2) * 4);
+    const size_t o_head = carve(acc_slices * 128);
+    const size_t o_tail = carve(acc_slices * 128);
+    const size_t o_work_list = carve((acc_slices / FIXUP_SERIAL_SPAN + 2) * 4);
     const uint32_t total_chunks = pl.chunks_per_window * (uint32_t)pl.sets;
     const size_t o_A = carve((size_t)total_chunks * 128);
     const size_t o_V = carve((size_t)total_chunks * 128);
@@ -1035,6 +1455,19 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
         if (v >= 1 && (v & (v - 1)) == 0 && pl.chunks_per_window / v >= 1) pl.red_splits = v;
     }
     const size_t o_red_part = carve(tree_blocks != 0 ? (size_t)pl.sets * tree_blocks * TREE_OUT * 128 : red_count * pl.red_splits * 128);
+    // pair-sum rounds: two point buffers (the rounds alternate between them), the regions of the rounds, the dense offsets of
+    // what is left, and the CTAs' scratch
+    size_t o_pair_x = 0, o_pair_y = 0, o_pair_starts = 0, o_pair_counts = 0, o_pair_offsets = 0, o_pair_prefix = 0, o_pair_rec = 0;
+    if (pair_rounds > 0)
+    {
+        o_pair_x = carve(pair_cap[1] * 64);
+        o_pair_y = carve(pair_rounds > 1 ? pair_cap[2] * 64 : 0);
+        o_pair_starts = carve((size_t)pair_rounds * pair_row * 4);
+        o_pair_counts = carve((size_t)pair_rounds * pair_row * 4);
+        o_pair_offsets = carve(pair_row * 4);
+        o_pair_prefix = carve((size_t)pair_grid * PAIR_BMAX * PAIR_NT * 32);
+        o_pair_rec = carve((size_t)pair_grid * PAIR_BMAX * PAIR_NT * 4);
+    }
     BBG_CHECK(g_ws.ensure(off));
     char* ws = (char*)g_ws.p;
     uint32_t* digits = (uint32_t*)(ws + o_digits);
@@ -1070,16 +1503,58 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
         BBG_LAUNCH_NOSYNC(msm_scatter_kernel, dim3((unsigned)((pl.max_entries + 255) / 256)), dim3(256), st, (const uint32_t*)digits, (const uint32_t*)ranks,
                           pl.num_points, pl.W, single.W, pl.NB, pl.entry_stride, (const uint32_t*)offsets, sorted);
     }
+    const uint32_t* acc_offsets = offsets; // the regions the accumulate pass and the fix-up work on
+    if (pair_rounds > 0)
+    {
+        bbg_prof::Scope prof(bbg_prof::MSM_PAIR, st);
+        uint32_t* starts = (uint32_t*)(ws + o_pair_starts);
+        uint32_t* pcounts = (uint32_t*)(ws + o_pair_counts);
+        uint32_t* dense = (uint32_t*)(ws + o_pair_offsets);
+        fe* buf[2] = { (fe*)(ws + o_pair_x), (fe*)(ws + o_pair_y) };
+        // (`counts` has served the sort: it now takes what every bucket holds after the last round)
+        BBG_LAUNCH_NOSYNC(msm_pair_plan_kernel, dim3((unsigned)((pair_row + 255) / 256)), dim3(256), st, (const uint32_t*)offsets, pl.total_buckets, pair_rounds,
+                          starts, pcounts, counts);
+        BBG_LAUNCH(scan_block_sums_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, spine);
+        BBG_LAUNCH(scan_spine_kernel, dim3(1), dim3(SCAN_BLOCK), 0, st, spine, scan_blocks);
+        BBG_LAUNCH(scan_apply_kernel, dim3(scan_blocks), dim3(SCAN_BLOCK), 0, st, (const uint32_t*)counts, pl.total_buckets, (const uint32_t*)spine, dense);
+        for (int r = 1; r <= pair_rounds; ++r)
+        {
+            PairParams q;
+            q.src = r == 1 ? (const fe*)d_table : buf[r & 1]; // round r writes buf[(r - 1) & 1]
+            q.sorted = r == 1 ? sorted : nullptr;
+            q.in_start = r == 1 ? offsets : starts + (size_t)(r - 1) * pair_row;
+            q.in_count = r == 1 ? nullptr : pcounts + (size_t)(r - 1) * pair_row;
+            q.out_start = r == pair_rounds ? dense : starts + (size_t)r * pair_row;
+            q.dst = buf[(r - 1) & 1];
+            q.total_buckets = pl.total_buckets;
+            q.bmax = PAIR_BMAX;
+            if (const char* e = getenv("BBG_MSM_PAIR_BMAX")) // development
+            {
+                const int v = atoi(e);
+                if (v >= (int)PAIR_BMIN && v <= (int)PAIR_BMAX) q.bmax = (uint32_t)v;
+            }
+            q.prefix = (fe*)(ws + o_pair_prefix);
+            q.rec = (uint32_t*)(ws + o_pair_rec);
+            if (r == 1) BBG_LAUNCH(msm_pair_round_kernel<true>, dim3(pair_grid), dim3(PAIR_NT), 0, st, q);
+            else BBG_LAUNCH(msm_pair_round_kernel<false>, dim3(pair_grid), dim3(PAIR_NT), 0, st, q);
+        }
+        acc_offsets = dense;
+        g_msm_launches += 4 + pair_rounds;
+    }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_ACCUMULATE, st);
-        BBG_LAUNCH_NOSYNC(msm_accumulate_kernel, dim3((unsigned)((pl.max_slices + 127) / 128)), dim3(128), st, (const uint32_t*)sorted,
-                          (const uint32_t*)offsets, pl.total_buckets, (const fe*)d_table, pl.S, buckets, head, tail);
+        if (pair_rounds > 0)
+            BBG_LAUNCH_NOSYNC(msm_accumulate_kernel<true>, dim3((unsigned)((acc_slices + 127) / 128)), dim3(128), st, (const uint32_t*)nullptr, acc_offsets,
+                              pl.total_buckets, (const fe*)(ws + (((pair_rounds - 1) & 1) ? o_pair_y : o_pair_x)), S_acc, buckets, head, tail);
+        else
+            BBG_LAUNCH_NOSYNC(msm_accumulate_kernel<false>, dim3((unsigned)((acc_slices + 127) / 128)), dim3(128), st, (const uint32_t*)sorted, acc_offsets,
+                              pl.total_buckets, (const fe*)d_table, S_acc, buckets, head, tail);
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_FIXUP, st);
-        BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, (const uint32_t*)offsets, pl.total_buckets, pl.S, buckets,
+        BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, acc_offsets, pl.total_buckets, S_acc, buckets,
                           (const fe*)head, (const fe*)tail, work_count, work_list);
-        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, (const uint32_t*)offsets, pl.S, buckets, (const fe*)head,
+        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, (const fe*)head,
                    (const fe*)tail, (const uint32_t*)work_count, (const uint32_t*)work_list);
     }
     {

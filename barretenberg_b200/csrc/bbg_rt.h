@@ -88,13 +88,14 @@ enum id
     PLONK_ELEMENTWISE,
     PLONK_SCAN,
     PLONK_EVAL,
+    MSM_PAIR,
     NUM_IDS
 };
 inline const char* name(int i)
 {
     static const char* n[NUM_IDS] = { "ntt_pass_a", "ntt_pass_b", "ntt_small", "ntt_tables", "msm_digits", "msm_scan", "msm_scatter",
                                       "msm_accumulate", "msm_fixup", "msm_chunk", "msm_reduce", "msm_host_finish", "g1_generate",
-                                      "plonk_elementwise", "plonk_scan", "plonk_eval" };
+                                      "plonk_elementwise", "plonk_scan", "plonk_eval", "msm_pair_rounds" };
     return (i >= 0 && i < NUM_IDS) ? n[i] : "?";
 }
 struct State

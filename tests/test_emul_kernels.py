@@ -385,3 +385,59 @@ def test_msm_fixed_base_windows(emu, window, monkeypatch):
         assert (emu.msm(sc, table) == exp).all()
     finally:
         emu.set_srs_precompute(False)
+
+
+@pytest.mark.parametrize("rounds,bmax", [(1, 96), (2, 8), (3, 12), (4, 96)])
+def test_msm_pair_sum_rounds(emu, rounds, bmax, monkeypatch):
+    """Pair-sum rounds ahead of the accumulate pass (batched affine additions, bbg_msm.cu 3b), forced on for sizes the
+    planner would leave to the accumulate pass alone: random scalars, zero / repeated / unreduced scalars, P + P and
+    P + (-P) inside buckets (repeated points: doubling and cancellation), giant buckets, long runs of empty buckets, the
+    fixed-base form and a batch — every result must equal the oracle's, whatever the number of rounds and the item size."""
+    monkeypatch.setenv("BBG_MSM_PAIR_ROUNDS", str(rounds))
+    monkeypatch.setenv("BBG_MSM_PAIR_BMAX", str(bmax))
+    n = 2500
+    table, a0, d = H.generator_multiples_table(71, n)
+    sc = H.random_scalars_mont(72, n)
+    sc[1] = 0
+    sc[2] = sc[3]
+    sc[4] = H.to_limbs(H.from_limbs(sc[4]) + H.FR_MODULUS)
+    before = emu.launch_count()
+    assert (emu.msm(sc, table) == H.oracle_msm(sc, table)).all()
+    assert emu.launch_count() - before == 10 + 4 + rounds  # the rounds did run
+    # one digit value shared by all scalars: one giant bucket per window, every other bucket empty
+    same = np.tile(H.random_scalars_mont(73, 1)[0], (n, 1))
+    assert (emu.msm(same, table) == H.closed_form_msm(same, a0, d)).all()
+    vals = H.random_scalars_mont(74, 3)
+    few = np.ascontiguousarray(vals[np.arange(n) % 3])
+    assert (emu.msm(few, table) == H.closed_form_msm(few, a0, d)).all()
+    assert H.is_infinity(emu.msm(np.zeros((n, 4), dtype=np.uint64), table))
+    # P, -P, P, -P ... with pairwise equal scalars: every bucket cancels to the point at infinity
+    m = 400
+    pts = np.ascontiguousarray(table[0:2 * m:2]).copy()
+    neg = np.zeros(4, dtype=np.uint64)
+    for i in range(1, m, 2):
+        pts[i, :4] = pts[i - 1, :4]
+        H.oracle().orc_neg(H.FQ, H.ptr(pts[i - 1, 4:].copy()), H.ptr(neg))
+        pts[i, 4:] = neg
+    t2 = emu.generate_pippenger_point_table(pts)
+    sc2 = H.random_scalars_mont(75, m)
+    sc2[1::2] = sc2[0::2]
+    assert H.is_infinity(emu.msm(sc2, t2))
+    sc2 = H.random_scalars_mont(76, m)  # independent scalars: cancellations and doublings only where digits collide
+    assert (emu.msm(sc2, t2) == H.oracle_msm(sc2, t2)).all()
+    # one point repeated: every addition inside a bucket is P + P or P + (-P) or meets a point at infinity
+    t3 = emu.generate_pippenger_point_table(np.tile(pts[0], (m, 1)))
+    sc3 = H.random_scalars_mont(77, m)
+    sc3[:50] = sc3[0]
+    assert (emu.msm(sc3, t3) == H.oracle_msm(sc3, t3)).all()
+    # fixed-base form (one bucket set, entries from every window's table) and a batch
+    emu.set_srs_precompute(True)
+    try:
+        keep = emu.srs_register(table)
+        assert (emu.msm(sc, keep) == H.oracle_msm(sc, table)).all()
+        scs = [H.random_scalars_mont(80 + i, n) for i in range(2)]
+        for g_, s_ in zip(emu.msm_batched(scs, [keep] * 2), scs):
+            assert (g_ == H.oracle_msm(s_, table)).all()
+        emu.srs_unregister(keep)
+    finally:
+        emu.set_srs_precompute(False)

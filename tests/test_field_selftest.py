@@ -111,8 +111,13 @@ def check_field(lib, field, count, seed):
     x = a[:m].copy()
     x[0] = H.to_limbs(7)  # 0 has no inverse
     x[4] = H.to_limbs(p + 3)
+    x[5] = H.to_limbs(0)  # both routines return 0 for it, as a^(p-2) does
+    x[6] = H.to_limbs(p)
+    x[7] = H.to_limbs(p - 1)
+    x[8] = H.to_limbs(1)
     got = lib.field_selftest(field, "invert", x)
     assert (got == oracle_field(field, "invert", x)).all()
+    assert (lib.field_selftest(field, "invert_binary", x) == got).all()  # binary extended Euclid: the same canonical limbs
     one = oracle_field(field, "mul", got, x)
     invertible = oracle_field(field, "reduce_once", x).any(axis=1)
     assert (one[invertible] == H.to_limbs(H.R_MONT % p)).all() and invertible.sum() > m - 64

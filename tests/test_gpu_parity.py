@@ -216,6 +216,37 @@ def test_msm_repetitive_scalars_giant_buckets(lib, distinct):
     assert (got == H.closed_form_msm(sc, a0, d)).all()
 
 
+@pytest.mark.parametrize("rounds", [0, 1, 2, 3, 4])
+def test_msm_pair_sum_rounds(lib, rounds, monkeypatch):
+    """Pair-sum rounds ahead of the accumulate pass (batched affine additions: bbg_msm.cu 3b), 0 .. 4 of them forced: the
+    commitment does not depend on how the additions inside the buckets are arranged (SURVEY §8 note 3).  Uniform scalars
+    against the closed form, constant scalars (one giant bucket per window, 2^15 - 1 empty ones), one point repeated
+    (every addition a doubling, a cancellation or against the point at infinity) against the oracle, plain and fixed-base."""
+    monkeypatch.setenv("BBG_MSM_PAIR_ROUNDS", str(rounds))
+    n = 1 << 18
+    table, a0, d = H.generator_multiples_table(17, n)
+    sc = H.random_scalars_mont(41, n)
+    sc[1] = 0
+    sc[2] = sc[3]
+    want = H.closed_form_msm(sc, a0, d)
+    assert (lib.msm(sc, table) == want).all()
+    const = np.tile(H.random_scalars_mont(42, 1)[0], (n, 1))
+    assert (lib.msm(const, table) == H.closed_form_msm(const, a0, d)).all()
+    m = 3000
+    pts = np.tile(np.ascontiguousarray(table[0::2])[5], (m, 1))
+    t3 = lib.generate_pippenger_point_table(pts)
+    sc3 = H.random_scalars_mont(43, m)
+    sc3[:64] = sc3[0]
+    assert (lib.msm(sc3, t3) == H.oracle_msm(sc3, t3)).all()
+    lib.set_srs_precompute(True)
+    try:
+        keep = lib.srs_register(table)
+        assert (lib.msm(sc, keep) == want).all()
+        lib.srs_unregister(keep)
+    finally:
+        lib.set_srs_precompute(False)
+
+
 def test_batched_msm_and_srs_cache(lib):
     n = 4096
     table, _, _ = H.generator_multiples_table(21, n)

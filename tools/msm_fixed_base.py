@@ -1,6 +1,7 @@
 """Development aid: device-resident MSM over a registered table with and without the fixed-base windows
 (bbg_set_srs_precompute), for several forced window widths (BBG_MSM_FIXED_WINDOW; 0 = the planner's choice).
-usage: python tools/msm_fixed_base.py [--logs 20] [--windows 0,13,15,16,17,18,19,20]   (one JSON line per case)"""
+usage: python tools/msm_fixed_base.py [--logs 20] [--windows 0,13,15,16,17,18,19,20] [--pair-rounds 0,1,2,3]   (one JSON line per case;
+--pair-rounds forces the number of pair-sum rounds ahead of the accumulate pass, BBG_MSM_PAIR_ROUNDS, default: the planner's)"""
 import json
 import os
 import sys
@@ -22,6 +23,9 @@ def main():
         logs = [int(v) for v in args[args.index("--logs") + 1].split(",")]
     if "--windows" in args:
         windows = [int(v) for v in args[args.index("--windows") + 1].split(",")]
+    pair_rounds = [None]
+    if "--pair-rounds" in args:
+        pair_rounds = [int(v) for v in args[args.index("--pair-rounds") + 1].split(",")]
     lib = bb.Library()
     for log_n in logs:
         n = 1 << log_n
@@ -32,11 +36,25 @@ def main():
         h_tab = np.zeros((2 * n, 8), dtype=np.uint64)
         lib.d2h(h_tab, d_tab)
         sc = S.random_field(5, n)
+        if "--constant" in args:  # every scalar the same: one giant bucket per window (the prover's repetitive polynomials)
+            sc = np.ascontiguousarray(np.tile(sc[0], (n, 1)))
         d_sc = lib.dev_alloc(n * 32)
         lib.h2d(d_sc, sc)
+        os.environ["BBG_MSM_PAIR_ROUNDS"] = "0"
         ref = lib.msm_dev(d_sc, d_tab, n)
+        os.environ.pop("BBG_MSM_PAIR_ROUNDS", None)
 
         def timed(d_table, label, extra):
+            for r in pair_rounds:
+                if r is None:
+                    os.environ.pop("BBG_MSM_PAIR_ROUNDS", None)
+                else:
+                    os.environ["BBG_MSM_PAIR_ROUNDS"] = str(r)
+                    extra = dict(extra, pair_rounds=r)
+                timed_one(d_table, label, extra)
+            os.environ.pop("BBG_MSM_PAIR_ROUNDS", None)
+
+        def timed_one(d_table, label, extra):
             out = lib.msm_dev(d_sc, d_table, n)
             ok = bool((out == ref).all())
             lib.profile_enable(True)
