@@ -486,6 +486,18 @@ int bbg_ntt_fr_batched(uint64_t* const* coeffs, size_t batch, unsigned log2_n, i
         return bbg_rt::sync(g_stream);
     }
 #endif
+#ifndef BBG_EMULATE
+    // one polynomial in a page-locked buffer (the caller's own, or one the registration cache locked in place): uploads,
+    // passes and downloads overlapped block by block (bbg_ntt.cu, ntt_host_blocks)
+    static const bool host_blocks = [] { const char* e = getenv("BBG_NTT_HOST_BLOCKS"); return e == nullptr || e[0] != '0'; }();
+    if (batch == 1 && host_blocks && ntt_host_blocks_applicable(log2_n))
+    {
+        const bbg_hostcopy::PinnedSpan sp = bbg_hostcopy::reg_cache().peek(coeffs[0], bytes);
+        if (sp.whole || (sp.mid > 0 && !sp.mixed))
+            return ntt_host_blocks(coeffs[0], sp.whole ? 0 : sp.head, sp.whole ? bytes : sp.head + sp.mid, g_stage_coeffs.p, log2_n, op, constant, g_stream,
+                                   g_copy_in, g_copy_out);
+    }
+#endif
     for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_hostcopy::h2d((char*)g_stage_coeffs.p + i * bytes, coeffs[i], bytes, g_stream));
     BBG_CHECK(ntt_device(g_stage_coeffs.p, n, batch, log2_n, op, constant, g_stream));
     for (size_t i = 0; i < batch; ++i) BBG_CHECK(bbg_hostcopy::d2h(coeffs[i], (char*)g_stage_coeffs.p + i * bytes, bytes, g_stream));

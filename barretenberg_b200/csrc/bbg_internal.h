@@ -35,6 +35,12 @@ enum ntt_op
 
 // device-resident NTT: batch polynomials of 2^log_n elements, `stride` elements apart, in place.
 int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int op, const uint64_t* constant, cudaStream_t stream);
+#ifndef BBG_EMULATE
+bool ntt_host_blocks_applicable(unsigned log_n);
+// the transform of ONE polynomial in a (partly) page-locked host buffer with uploads / passes / downloads overlapped block by block
+int ntt_host_blocks(void* h_coeffs, size_t safe_lo, size_t safe_hi, void* d_coeffs, unsigned log_n, int op, const uint64_t* constant, cudaStream_t st,
+                    cudaStream_t copy_in, cudaStream_t copy_out);
+#endif
 void ntt_use_side_scratch(bool on); // route the following ntt_device calls to a second scratch buffer (second stream)
 int ntt_release_tables();
 // coset evaluations of L_1 on the 2^log_target domain for a 2^log_src circuit (compute_lagrange_polynomial_fft)

@@ -31,6 +31,7 @@
 //   first time a domain size is used and cached (the reference's host round_roots tables are never
 //   uploaded).
 #include "bbg_internal.h"
+#include "bbg_hostcopy.h"
 
 #include <cstring>
 #include <map>
@@ -263,6 +264,7 @@ struct PassParams
     fe post_const;          // pass B: extra constant (fft/ifft_with_constant)
     int has_post_const;
     int scatter_shift;      // pass B as the last of three passes: block b's output o goes to dst[(o << scatter_shift) + b]
+    int tile_begin = 0;     // this launch covers tiles tile_begin .. tile_begin + num_tiles - 1 (host-buffer transforms go in blocks)
 };
 
 // DIF butterflies on the 3-bit owned field x[m] <-> k = base | m << B of a 2^L-point transform:
@@ -469,7 +471,7 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
     {
         // the first tile's copies fly while the twiddle image is loaded
         const int work0 = blockIdx.x * TPC + half;
-        if (work0 < p.total_work) stage_tile<L, COLS_LOW>(p, p.src + (size_t)(work0 % batch) * p.batch_stride, work0 / batch, data);
+        if (work0 < p.total_work) stage_tile<L, COLS_LOW>(p, p.src + (size_t)(work0 % batch) * p.batch_stride, work0 / batch + p.tile_begin, data);
     }
 #endif
     // twiddle image: 66 KiB per CTA by 16-byte cp.async (no register round trips: the plain copy loop was 33 dependent
@@ -483,7 +485,7 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
         {
             typedef TileMap<L, COLS_LOW> TM;
             const fe* src0 = p.src + (size_t)(work0 % batch) * p.batch_stride;
-            const int tile0 = work0 / batch, t = threadIdx.x & (NT - 1), rest = p.log_n - L;
+            const int tile0 = work0 / batch + p.tile_begin, t = threadIdx.x & (NT - 1), rest = p.log_n - L;
 #pragma unroll
             for (int m = 0; m < 8; ++m)
             {
@@ -499,7 +501,7 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
     {
         // polynomial-minor order: the CTAs in flight work on the same few tiles of all polynomials of the batch, so the
         // inter-pass matrix tile (pass A; 128 MiB per 2^22 transform, more than L2 holds) is read from HBM once per batch
-        const int tile = work / batch;
+        const int tile = work / batch + p.tile_begin;
         const size_t b = (size_t)(work % batch);
         const int nwork = work + (int)gridDim.x * TPC;
         const fe* nsrc = nwork < p.total_work ? p.src + (size_t)(nwork % batch) * p.batch_stride : nullptr;
@@ -509,7 +511,7 @@ template <int L, bool COLS_LOW> __global__ void __launch_bounds__(NT * TPC, 1) n
 #endif
         fe x[8];
         run_from<L, COLS_LOW, L - 3, true>(x, p, p.src + b * p.batch_stride, p.scatter_shift ? p.dst + b : p.dst + b * p.batch_stride, tile, data, tw, nsrc,
-                                           nwork / batch);
+                                           nwork / batch + p.tile_begin);
 #if !(BBG_NTT_STAGE && BBG_NTT_ABLATE != 5)
         NTT_SYNC(); // the last step's shared-memory reads finish before the next tile overwrites
 #endif
@@ -1128,6 +1130,58 @@ int ntt_three_pass(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, 
 }
 } // namespace
 
+// The two passes of an n = 2^12 .. 2^22 transform: tables fetched (generated at first use), parameters filled in
+int setup_two_pass(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, bool inverse, bool coset, bool with_constant, const fe& k, cudaStream_t st,
+                   PassParams& a, PassParams& b, int& L1, int& L2)
+{
+    const size_t n = (size_t)1 << log_n;
+    split(log_n, L1, L2);
+    BBG_CHECK(active_scratch().ensure(batch * n * 32));
+    a.src = (const fe*)d_coeffs;
+    a.dst = (fe*)active_scratch().p;
+    a.batch_stride = stride;
+    a.log_n = (int)log_n;
+    a.num_tiles = (int)(n >> TILE_LOG);
+    a.total_work = a.num_tiles * (int)batch;
+    a.vec = nullptr;
+    a.has_post_const = 0;
+    a.post_const = Fr::one();
+    a.scatter_shift = 0;
+    b = a;
+    // pass A writes polynomial i at scratch + i * n; pass B reads it back from there
+    b.src = (const fe*)active_scratch().p;
+    b.dst = (fe*)d_coeffs;
+    BBG_CHECK(get_sub_tw(L1, inverse, st, &a.sub_tw));
+    BBG_CHECK(get_sub_tw(L2, inverse, st, &b.sub_tw));
+    const int variant = (inverse ? 1 : 0) | (coset ? 2 : 0);
+    BBG_CHECK(get_matrix(log_n, variant, st, &a.mat));
+    b.mat = nullptr;
+    if (coset && !inverse)
+    {
+        const fe* pc = nullptr;
+        BBG_CHECK(get_vec(log_n, VEC_PRE_COSET, st, &pc));
+        if (with_constant)
+        {
+            const unsigned cnt = 1u << L1;
+            BBG_CHECK(g_tables.tmp_vec.ensure((size_t)cnt * 32));
+            BBG_LAUNCH_NOSYNC(scale_vector_kernel, dim3((cnt + 127) / 128), dim3(128), st, (fe*)g_tables.tmp_vec.p, pc, k, cnt);
+            ++g_ntt_launches;
+            pc = (const fe*)g_tables.tmp_vec.p;
+        }
+        a.vec = pc;
+    }
+    else if (coset && inverse)
+    {
+        BBG_CHECK(get_vec(log_n, VEC_POST_ICOSET, st, &b.vec));
+    }
+    else if (with_constant)
+    {
+        b.has_post_const = 1;
+        b.post_const = k;
+    }
+    return 0;
+}
+
 int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int op, const uint64_t* constant, cudaStream_t st)
 {
     if (log_n < 1 || log_n > 28) return 1002; // n = 2 .. 2^28 (the two-adicity of the field, fr.hpp:59-63)
@@ -1195,51 +1249,8 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
     if (log_n > 2 * (unsigned)TILE_LOG) return ntt_three_pass(d_coeffs, stride, batch, log_n, inverse, coset, with_constant, k, st);
 
     int L1, L2;
-    split(log_n, L1, L2);
-    BBG_CHECK(active_scratch().ensure(batch * n * 32));
     PassParams a, b;
-    a.src = (const fe*)d_coeffs;
-    a.dst = (fe*)active_scratch().p;
-    a.batch_stride = stride;
-    a.log_n = (int)log_n;
-    a.num_tiles = (int)(n >> TILE_LOG);
-    a.total_work = a.num_tiles * (int)batch;
-    a.vec = nullptr;
-    a.has_post_const = 0;
-    a.post_const = Fr::one();
-    a.scatter_shift = 0;
-    b = a;
-    // pass A writes polynomial i at scratch + i * n; pass B reads it back from there
-    b.src = (const fe*)active_scratch().p;
-    b.dst = (fe*)d_coeffs;
-    BBG_CHECK(get_sub_tw(L1, inverse, st, &a.sub_tw));
-    BBG_CHECK(get_sub_tw(L2, inverse, st, &b.sub_tw));
-    const int variant = (inverse ? 1 : 0) | (coset ? 2 : 0);
-    BBG_CHECK(get_matrix(log_n, variant, st, &a.mat));
-    b.mat = nullptr;
-    if (coset && !inverse)
-    {
-        const fe* pc = nullptr;
-        BBG_CHECK(get_vec(log_n, VEC_PRE_COSET, st, &pc));
-        if (with_constant)
-        {
-            const unsigned cnt = 1u << L1;
-            BBG_CHECK(g_tables.tmp_vec.ensure((size_t)cnt * 32));
-            BBG_LAUNCH_NOSYNC(scale_vector_kernel, dim3((cnt + 127) / 128), dim3(128), st, (fe*)g_tables.tmp_vec.p, pc, k, cnt);
-            ++g_ntt_launches;
-            pc = (const fe*)g_tables.tmp_vec.p;
-        }
-        a.vec = pc;
-    }
-    else if (coset && inverse)
-    {
-        BBG_CHECK(get_vec(log_n, VEC_POST_ICOSET, st, &b.vec));
-    }
-    else if (with_constant)
-    {
-        b.has_post_const = 1;
-        b.post_const = k;
-    }
+    BBG_CHECK(setup_two_pass(d_coeffs, stride, batch, log_n, inverse, coset, with_constant, k, st, a, b, L1, L2));
     // pass A: d_coeffs (stride) -> scratch (dense);  pass B: scratch (dense) -> d_coeffs (stride)
     {
         PassParams pa = a;
@@ -1271,4 +1282,147 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
     }
     return 0;
 }
+#ifndef BBG_EMULATE
+// ---- a host buffer's transform with the copies cut into blocks --------------------------------------------------------------
+// The reference's signatures are blocking and in place on HOST memory: upload, two passes, download, 2 x 2.44 + 0.77 ms for
+// a 2^22 polynomial, the link idle while the passes run and the SMs idle while it copies.  Pass A works on COLUMN tiles of the
+// N1 x N2 input matrix and pass B's row tiles write COLUMNS of the N2 x N1 output matrix, so both copies are cut into column
+// blocks (cudaMemcpy2DAsync: N1 or N2 row pieces of a few KB each): pass A of block k runs while block k + 1 is on the wire,
+// pass B of block k + 1 while block k travels back — what stays exposed is one block's pass at either end.
+// [safe_lo, safe_hi): the byte range of the buffer that is page-locked (the registration cache locks whole pages only).  Row
+// pieces outside it (the first piece of the first row, the last of the last) go through bbg_hostcopy's mixed-memory path, the
+// downloads among them at the very end because a copy into pageable memory blocks the calling thread.
+namespace
+{
+std::vector<cudaEvent_t> g_block_events;
+int block_event(size_t i, cudaEvent_t* ev)
+{
+    while (g_block_events.size() <= i)
+    {
+        cudaEvent_t e;
+        BBG_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g_block_events.push_back(e);
+    }
+    *ev = g_block_events[i];
+    return 0;
+}
+struct EdgePiece
+{
+    size_t off, len;
+};
+// columns [x0, x0 + w) (bytes) of `rows` rows of `pitch` bytes, between the host buffer h and its device image d
+int copy_column_block(char* h, char* d, size_t x0, size_t w, size_t pitch, size_t rows, bool to_device, size_t safe_lo, size_t safe_hi, cudaStream_t st,
+                      std::vector<EdgePiece>* deferred)
+{
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    // rows 1 .. rows - 2 lie inside the locked range whatever the block (a row is longer than a page)
+    if (rows > 2)
+    {
+        const size_t off = pitch + x0;
+        BBG_CHECK(to_device ? cudaMemcpy2DAsync(d + off, pitch, h + off, pitch, w, rows - 2, kind, st)
+                            : cudaMemcpy2DAsync(h + off, pitch, d + off, pitch, w, rows - 2, kind, st));
+    }
+    for (int edge = 0; edge < (rows > 1 ? 2 : 1); ++edge)
+    {
+        const size_t off = (edge == 0 ? 0 : (rows - 1) * pitch) + x0;
+        if (off >= safe_lo && off + w <= safe_hi)
+            BBG_CHECK(to_device ? cudaMemcpyAsync(d + off, h + off, w, kind, st) : cudaMemcpyAsync(h + off, d + off, w, kind, st));
+        else if (to_device)
+            BBG_CHECK(bbg_hostcopy::h2d(d + off, h + off, w, st));
+        else
+            deferred->push_back({ off, w });
+    }
+    return 0;
+}
+} // namespace
+
+bool ntt_host_blocks_applicable(unsigned log_n)
+{
+    static const unsigned lo = [] { const char* e = getenv("BBG_NTT_HOST_BLOCKS_MIN_LOG"); const int v = e ? atoi(e) : 0; return v >= 14 && v <= 22 ? (unsigned)v : 21u; }();
+    return log_n >= lo && log_n <= 2 * (unsigned)TILE_LOG;
+}
+
+int ntt_host_blocks(void* h_coeffs, size_t safe_lo, size_t safe_hi, void* d_coeffs, unsigned log_n, int op, const uint64_t* constant, cudaStream_t st,
+                    cudaStream_t copy_in, cudaStream_t copy_out)
+{
+    if (!ntt_host_blocks_applicable(log_n)) return 1002;
+    if (op < OP_FFT || op > OP_COSET_FFT_WITH_CONSTANT) return 1003;
+    const bool inverse = (op == OP_IFFT || op == OP_COSET_IFFT || op == OP_IFFT_WITH_CONSTANT);
+    const bool coset = (op == OP_COSET_FFT || op == OP_COSET_IFFT || op == OP_COSET_FFT_WITH_CONSTANT);
+    const bool with_constant = (op >= OP_FFT_WITH_CONSTANT);
+    if (with_constant && constant == nullptr) return 1004;
+    fe k = Fr::one();
+    if (with_constant) k = load_fe(constant);
+    const size_t n = (size_t)1 << log_n;
+    int L1, L2;
+    PassParams a, b;
+    BBG_CHECK(setup_two_pass(d_coeffs, n, 1, log_n, inverse, coset, with_constant, k, st, a, b, L1, L2));
+    const int tiles = (int)(n >> TILE_LOG);
+    // Block width on the wire: 16 KiB row pieces.  Narrower pieces cost the copy engines more than the overlap returns
+    // (coset_fft 2^22 from a page-locked buffer, one B200: whole-buffer copies 5.69 ms; 2 KiB pieces 6.65, 8 KiB 5.35,
+    // 16 KiB 5.25 ms), which is also why sizes below 2^21 — whose rows leave no room for two such blocks — keep whole copies.
+    size_t piece = 16384;
+    if (const char* e = getenv("BBG_NTT_HOST_BLOCK_KB")) // development
+    {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 1024 && (v & (v - 1)) == 0) piece = (size_t)v << 10;
+    }
+    auto tiles_per_block = [&](int cl) {
+        size_t t = (piece / 32) >> cl;
+        if (t < 1) t = 1;
+        if (t > (size_t)tiles) t = (size_t)tiles;
+        return (int)t;
+    };
+    char* h = (char*)h_coeffs;
+    char* d = (char*)d_coeffs;
+    cudaEvent_t ev;
+    // uploads may start once everything already queued on the work stream is done with the device image
+    BBG_CHECK(block_event(0, &ev));
+    BBG_CHECK(cudaEventRecord(ev, st));
+    BBG_CHECK(cudaStreamWaitEvent(copy_in, ev, 0));
+    size_t events_used = 1;
+    {
+        // pass A: tile t = columns [t << cl, (t + 1) << cl) of the 2^L1 x 2^L2 input matrix
+        const int cl = TILE_LOG - L1;
+        const size_t pitch = ((size_t)32) << L2, rows = (size_t)1 << L1;
+        const int block_tiles = tiles_per_block(cl), blocks = tiles / block_tiles;
+        for (int blk = 0; blk < blocks; ++blk)
+        {
+            const size_t x0 = ((size_t)(blk * block_tiles) << cl) * 32, w = ((size_t)block_tiles << cl) * 32;
+            BBG_CHECK(copy_column_block(h, d, x0, w, pitch, rows, true, safe_lo, safe_hi, copy_in, nullptr));
+            BBG_CHECK(block_event(events_used++, &ev));
+            BBG_CHECK(cudaEventRecord(ev, copy_in));
+            BBG_CHECK(cudaStreamWaitEvent(st, ev, 0));
+            PassParams pa = a;
+            pa.num_tiles = block_tiles;
+            pa.total_work = block_tiles;
+            pa.tile_begin = blk * block_tiles;
+            BBG_CHECK(launch_pass<true>(L1, pa, st));
+        }
+    }
+    std::vector<EdgePiece> deferred;
+    {
+        // pass B: tile t = rows [t << cl, ..) of the intermediate matrix = COLUMNS [t << cl, ..) of the 2^L2 x 2^L1 output matrix
+        const int cl = TILE_LOG - L2;
+        const size_t pitch = ((size_t)32) << L1, rows = (size_t)1 << L2;
+        const int block_tiles = tiles_per_block(cl), blocks = tiles / block_tiles;
+        for (int blk = 0; blk < blocks; ++blk)
+        {
+            PassParams pb = b;
+            pb.num_tiles = block_tiles;
+            pb.total_work = block_tiles;
+            pb.tile_begin = blk * block_tiles;
+            BBG_CHECK(launch_pass<false>(L2, pb, st));
+            BBG_CHECK(block_event(events_used++, &ev));
+            BBG_CHECK(cudaEventRecord(ev, st));
+            BBG_CHECK(cudaStreamWaitEvent(copy_out, ev, 0));
+            const size_t x0 = ((size_t)(blk * block_tiles) << cl) * 32, w = ((size_t)block_tiles << cl) * 32;
+            BBG_CHECK(copy_column_block(h, d, x0, w, pitch, rows, false, safe_lo, safe_hi, copy_out, &deferred));
+        }
+    }
+    for (const EdgePiece& e : deferred) BBG_CHECK(bbg_hostcopy::d2h(h + e.off, d + e.off, e.len, copy_out));
+    BBG_CHECK(bbg_rt::sync(copy_out));
+    return bbg_rt::sync(st);
+}
+#endif
 } // namespace bbg

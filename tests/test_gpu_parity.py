@@ -216,6 +216,53 @@ def test_msm_repetitive_scalars_giant_buckets(lib, distinct):
     assert (got == H.closed_form_msm(sc, a0, d)).all()
 
 
+@pytest.mark.parametrize("log_n", [20, 21, 22])
+def test_ntt_host_buffer_blocks(lib, log_n):
+    """A single polynomial in a page-locked HOST buffer takes the block-pipelined path (ntt_host_blocks: column blocks
+    of the upload under pass A, pass B under the column blocks of the download).  Every entry point, on a buffer the
+    caller pinned and on a pageable, deliberately misaligned buffer that the registration cache locks in place (whole
+    pages only: the first and last row pieces straddle unlocked pages), must give the device-resident transform's limbs
+    — which test_ntt_vs_reference pins to the compiled reference at these sizes."""
+    import torch
+
+    n = 1 << log_n
+    x = H.random_scalars_mont(500 + log_n, n)
+    k = H.random_scalars_mont(7, 1)[0]
+    d = lib.dev_alloc(n * 32)
+    want = {}
+    for name in H.NTT_OPS:
+        lib.h2d(d, x)
+        lib.ntt_dev(name, d, log_n, constant=k if name.endswith("with_constant") else None)
+        out = np.zeros_like(x)
+        lib.d2h(out, d)
+        want[name] = out
+    lib.dev_free(d)
+    pinned = torch.zeros((n, 4), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    for name in H.NTT_OPS:
+        pinned[:] = x
+        lib.ntt(name, pinned, k)
+        assert (pinned == want[name]).all(), ("pinned", name)
+    raw = np.zeros(n * 4 + 512 + 8, dtype=np.uint64)
+    off = (-(raw.ctypes.data // 8) % 512) + 6  # 48 bytes past a page boundary: head and tail pages stay unlocked
+    buf = raw[off:off + n * 4].reshape(n, 4)
+    assert buf.ctypes.data % 4096 == 48
+    lib.set_host_register_cache(True)
+    try:
+        before = lib.host_register_stats()["registrations"]
+        for i in range(4):  # the cache page-locks a buffer that keeps coming back (6th copy)
+            buf[:] = x
+            lib.ntt("fft", buf)
+            assert (buf == want["fft"]).all(), ("sighting", i)
+        assert lib.host_register_stats()["registrations"] == before + 1
+        for name in H.NTT_OPS:
+            buf[:] = x
+            lib.ntt(name, buf, k)
+            assert (buf == want[name]).all(), ("registered", name)
+        lib.host_buffer_forget(buf)
+    finally:
+        lib.set_host_register_cache(False)
+
+
 @pytest.mark.parametrize("rounds", [0, 1, 2, 3, 4])
 def test_msm_pair_sum_rounds(lib, rounds, monkeypatch):
     """Pair-sum rounds ahead of the accumulate pass (batched affine additions: bbg_msm.cu 3b), 0 .. 4 of them forced: the
