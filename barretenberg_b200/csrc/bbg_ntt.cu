@@ -1038,8 +1038,18 @@ int domain_lookup_table_device(void* d_roots, unsigned log_size, cudaStream_t st
     return e;
 }
 
+#ifndef BBG_EMULATE
+namespace
+{
+std::vector<cudaEvent_t> g_block_events; // ntt_host_blocks: one per block in flight, created at first use
+}
+#endif
 int ntt_release_tables()
 {
+#ifndef BBG_EMULATE
+    for (cudaEvent_t e : g_block_events) cudaEventDestroy(e);
+    g_block_events.clear();
+#endif
     for (void* p : g_tables.owned) bbg_rt::dev_free(p);
     g_tables.owned.clear();
     g_tables.sub_tw.clear();
@@ -1294,7 +1304,6 @@ int ntt_device(void* d_coeffs, size_t stride, size_t batch, unsigned log_n, int 
 // downloads among them at the very end because a copy into pageable memory blocks the calling thread.
 namespace
 {
-std::vector<cudaEvent_t> g_block_events;
 int block_event(size_t i, cudaEvent_t* ev)
 {
     while (g_block_events.size() <= i)
