@@ -89,7 +89,7 @@ class Library:
 
     FIELD_OPS = {"mul_coarse": 0, "sqr_coarse": 1, "mul_const": 2, "add_coarse": 3, "sub_coarse": 4, "reduce_once": 5, "neg": 6,
                  "to_mont": 7, "from_mont": 8, "invert": 9, "sub_lazy": 10, "mul": 11, "mul_const_raw": 12,
-                 "invert_binary": 13}
+                 "invert_binary": 13, "mul2": 14}
     G1_OPS = {"mixed_add": 0, "add_doubled": 1, "dbl_dbl": 2, "accumulate": 3, "add": 4, "endo_entry": 5, "dbl_affine": 6}
 
     def set_srs_precompute(self, on=True):

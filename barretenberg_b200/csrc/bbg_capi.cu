@@ -1144,7 +1144,7 @@ int bbg_field_selftest(int field, int op, const uint64_t* a, const uint64_t* b, 
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     BBG_CHECK(ensure_ready());
-    if (field < 0 || field > 1 || op < 0 || op > 13) return BBG_E_BAD_ARGUMENT;
+    if (field < 0 || field > 1 || op < 0 || op > 14) return BBG_E_BAD_ARGUMENT;
     return selftest_run(false, field, op, a, b, out, count);
 }
 int bbg_g1_selftest(int op, const uint64_t* p, const uint64_t* q, uint64_t* out, size_t count)

@@ -407,6 +407,71 @@ template <typename FP> struct Field
         cc::add8(r.v, A, hi);
         return r;
     }
+    // (a b + c d) / 2^256 mod p in [0, 2p) for inputs in [0, 2p): two products under ONE interleaved reduction — word i adds
+    // a b_i + c d_i and then a single multiple of p, 8 x (16 + 9) = 200 wide products where two Montgomery products take 272.
+    // Bounds: the running sum stays below 5p (2^32 + 1) < 2^288, which is what the even / odd accumulator pair holds, and the
+    // result below p (8p / 2^256 + 1) < 2.52p, so one conditional subtraction of 2p brings it back into the lazy range.
+    // The mixed addition's y3 = R (Q - x3) - y1 PPP is the customer (bbg_g1.cuh).
+    static BBG_HD fe mul2(const fe& a, const fe& b, const fe& c, const fe& d)
+    {
+        uint32_t A[8], B[8];
+        const uint32_t *ae = a.v, *ao = a.v + 1, *ce = c.v, *co = c.v + 1;
+        uint32_t pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = FP::P(i);
+        const uint32_t *pe = pl, *po = pl + 1;
+        // word 0: even = A, odd = B
+        cc::mul_row(A, ae, b.v[0]);
+        cc::mul_row(B, ao, b.v[0]);
+        cc::mad_row(B, co, d.v[0]);
+        cc::mad_row_carry(A, B[7], ce, d.v[0]);
+        {
+            uint32_t m = A[0] * FP::NINV;
+            cc::mad_row(B, po, m);
+            cc::mad_row_carry(A, B[7], pe, m);
+        }
+#pragma unroll
+        for (int i = 1; i < 8; i += 2)
+        {
+            {
+                // odd word i: even = B, odd = A (A is shifted down two words on the way)
+                const uint32_t bi = b.v[i], di = d.v[i];
+                cc::shift_mad_row(A, B[0], ao, bi);
+                cc::mad_row_carry(B, A[7], ae, bi);
+                cc::mad_row(A, co, di);
+                cc::mad_row_carry(B, A[7], ce, di);
+                uint32_t m = B[0] * FP::NINV;
+                cc::mad_row(A, po, m);
+                cc::mad_row_carry(B, A[7], pe, m);
+            }
+            if (i + 1 < 8)
+            {
+                // even word i+1: even = A, odd = B
+                const uint32_t bi = b.v[i + 1], di = d.v[i + 1];
+                cc::shift_mad_row(B, A[0], ao, bi);
+                cc::mad_row_carry(A, B[7], ae, bi);
+                cc::mad_row(B, co, di);
+                cc::mad_row_carry(A, B[7], ce, di);
+                uint32_t m = A[0] * FP::NINV;
+                cc::mad_row(B, po, m);
+                cc::mad_row_carry(A, B[7], pe, m);
+            }
+        }
+        // after word 7: even = B with B[0] == 0, odd = A.  result[k] = B[k+1] + A[k], then back below 2p
+        fe s, t;
+        uint32_t hi[8], p2[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) hi[k] = B[k + 1];
+        hi[7] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p2[i] = FP::P2(i);
+        cc::add8(s.v, A, hi);
+        const uint32_t borrow = cc::sub8(t.v, s.v, p2);
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = borrow ? s.v[i] : t.v[i];
+        return r;
+    }
     // Montgomery square, result in [0, 2p) for a in [0, 2p): the same interleaved reduction as mul, but row i multiplies
     // a_i by  a_i B^i + 2 (a div B^(i+1)) B^(i+1)  (B = 2^32), i.e. by the words  a_i, a_(i+1) << 1, dd_(i+2) .. dd_7  with
     // dd_j = (a_j << 1) | (a_(j-1) >> 31) the words of 2a (2a < 2^256 since a < 2p < 2^255): every product a_i a_j is issued

@@ -35,7 +35,8 @@ template <typename F> __global__ void field_selftest_kernel(int op, const fe* a,
     case 10: r = F::sub_lazy(x, y); break;            // x - y + 2p, no correction: the butterfly difference of the NTT
     case 11: r = F::mul_full(x, y); break;            // __mul: canonical
     case 12: r = F::mul_const(x, F::from_mont(y), F::const_quotient(y)); break; // raw: must lie in [0, 2p)
-    case 13: r = F::invert_binary(x); break;          // the same inverse by the binary extended Euclid (the pair-sum rounds of the MSM)
+    case 13: r = F::invert_binary(x); break;
+    case 14: r = F::mul2(x, y, F::add(x, y), F::sub(x, y)); break; // x y + (x + y)(x - y) under one reduction (the mixed addition's y3)          // the same inverse by the binary extended Euclid (the pair-sum rounds of the MSM)
     default: r = F::zero();
     }
     store_fe(out + i, r);

@@ -88,6 +88,15 @@ def check_field(lib, field, count, seed):
         exp = oracle_field(field, op, a)
         bad = np.nonzero((got != exp).any(axis=1))[0]
         assert bad.size == 0, (op, field, int(bad[0]), hex(H.from_limbs(a[bad[0]])))
+    # two products under one reduction: x y + (x + y)(x - y), result in the lazy range
+    got = lib.field_selftest(field, "mul2", a, b)
+    top = got[:, 3]
+    assert (top <= np.uint64((2 * p) >> 192)).all()
+    for i in np.nonzero(top == np.uint64((2 * p) >> 192))[0][:64]:
+        assert H.from_limbs(got[i]) < 2 * p
+    exp = oracle_field(field, "add_coarse", oracle_field(field, "mul_coarse", a, b),
+                       oracle_field(field, "mul_coarse", oracle_field(field, "add_coarse", a, b), oracle_field(field, "sub_coarse", a, b)))
+    assert (oracle_field(field, "reduce_once", got) == oracle_field(field, "reduce_once", exp)).all(), ("mul2", field)
     # neg: the device stays in the lazy range (2p - a); same residue as the reference's p - a
     got = oracle_field(field, "reduce_once", lib.field_selftest(field, "neg", a))
     assert (got == oracle_field(field, "neg", a)).all(), ("neg", field)

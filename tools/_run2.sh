@@ -1,3 +1,6 @@
-ncu --set full --clock-control none -k regex:'msm_accumulate' -s 1 -c 1 -o /tmp/r2F_fat -f python tools/ncu_pair_target.py > gpurun_out/r2F_ncu.log 2>&1
-ncu -i /tmp/r2F_fat.ncu-rep --page raw --csv > gpurun_out/r2F_fat_raw.csv 2>/dev/null
-tail -2 gpurun_out/r2F_ncu.log
+O=gpurun_out/r2G_msm_mul2.jsonl
+: > $O
+python tools/msm_fixed_base.py --logs 20,17 --windows 0 2>>gpurun_out/r2G_err.log | cut -c1-600 >> $O
+cat $O
+python -m pytest tests/test_field_selftest.py tests/test_gpu_parity.py tests/test_shim_msm.py -m gpu -x -q -k "selftest or field or msm or shim" 2>&1 | tail -3
+tail -2 gpurun_out/r2G_err.log
