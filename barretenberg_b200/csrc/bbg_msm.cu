@@ -381,11 +381,26 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint32_t* 
             MSM_STORE_BUCKET(is_head ? head + 4 * slice : buckets + 4 * (size_t)b, acc);
             acc = G1::infinity();
             is_head = false;
+            // next non-empty bucket: a few steps, then a binary search — behind a giant bucket (constant scalars: one per
+            // window) tens of thousands of empty ones follow, and walking them one dependent load at a time made a single
+            // thread the whole kernel's tail (ncu: the SMs idle for half of the 4.4 ms of that case)
+            int steps = 0;
             do
             {
                 ++b;
                 bucket_end = offsets[b + 1];
-            } while (bucket_end == i); // skip empty buckets
+            } while (bucket_end == i && ++steps < 4);
+            if (bucket_end == i)
+            {
+                uint32_t lo_b = b, hi_b = total_buckets; // offsets[lo_b + 1] <= i < offsets[hi_b] ... find the first b with offsets[b + 1] > i
+                while (hi_b - lo_b > 1)
+                {
+                    const uint32_t mid = lo_b + ((hi_b - lo_b) >> 1);
+                    if (offsets[mid] <= i) lo_b = mid; else hi_b = mid;
+                }
+                b = lo_b;
+                bucket_end = offsets[b + 1];
+            }
         }
         const affine_pt cur = next;
         if (i + 1 < end) next = accumulate_fetch<DIRECT>(table, sorted, i + 1);
@@ -781,28 +796,53 @@ __global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets
     for (uint32_t s = s0 + 1; s <= s1; ++s) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
     store_xyzz(buckets + 4 * (size_t)b, sum);
 }
-__global__ void __launch_bounds__(FIXUP_BLOCK) msm_fixup_large_kernel(const uint32_t* offsets, uint32_t S, fe* buckets, const fe* head, const fe* tail,
-                                                                      const uint32_t* work_count, const uint32_t* work_list)
+// level 0: a queued bucket's heads s0 + 1 .. s1 are cut into sub-spans of FIXUP_SUB slices, one block each (a bucket of 2^20
+// entries spans ~19 000 slices: one block per BUCKET left all but a dozen SMs idle for a millisecond); the block's sum — for
+// the first sub-span including the bucket's tail slot — replaces the first head of its sub-span.  level 1: one block per
+// bucket adds those partial sums into the bucket.
+constexpr uint32_t FIXUP_SUB = 2048;
+__global__ void __launch_bounds__(FIXUP_BLOCK) msm_fixup_large_kernel(const uint32_t* offsets, uint32_t S, fe* buckets, fe* head, const fe* tail,
+                                                                      const uint32_t* work_count, const uint32_t* work_list, int level)
 {
     __shared__ uint32_t sm[FIXUP_BLOCK * 32];
     const uint32_t count = *work_count;
-    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x)
+    uint32_t item = 0; // running index over (bucket, sub-span) pairs at level 0, over buckets at level 1
+    for (uint32_t w = 0; w < count; ++w)
     {
-        const uint32_t b = work_list[item];
+        const uint32_t b = work_list[w];
         const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
         const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
-        xyzz_pt sum = G1::infinity();
-        if (threadIdx.x == 0) sum = load_xyzz(tail + 4 * (size_t)s0);
-        for (uint32_t s = s0 + 1 + threadIdx.x; s <= s1; s += FIXUP_BLOCK) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
-        for (int off = FIXUP_BLOCK / 2; off > 0; off >>= 1)
+        const uint32_t nsub = (s1 - s0 + FIXUP_SUB - 1) / FIXUP_SUB; // heads s0 + 1 .. s1
+        const uint32_t first = level == 0 ? 0u : nsub, last = level == 0 ? nsub : nsub + 1; // level 1: one pseudo sub-span
+        for (uint32_t sub = first; sub < last; ++sub, ++item)
         {
+            if (item % gridDim.x != blockIdx.x) continue;
+            xyzz_pt sum = G1::infinity();
+            if (level == 0)
+            {
+                const uint32_t lo = s0 + 1 + sub * FIXUP_SUB;
+                const uint32_t hi = lo + FIXUP_SUB - 1 < s1 ? lo + FIXUP_SUB - 1 : s1; // inclusive
+                if (threadIdx.x == 0 && sub == 0) sum = load_xyzz(tail + 4 * (size_t)s0);
+                for (uint32_t s = lo + threadIdx.x; s <= hi; s += FIXUP_BLOCK) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
+            }
+            else
+            {
+                for (uint32_t k = threadIdx.x; k < nsub; k += FIXUP_BLOCK) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)(s0 + 1 + k * FIXUP_SUB)));
+            }
+            for (int off = FIXUP_BLOCK / 2; off > 0; off >>= 1)
+            {
+                __syncthreads();
+                if ((int)threadIdx.x >= off && (int)threadIdx.x < 2 * off) store_xyzz(sm + 32 * (threadIdx.x - off), sum);
+                __syncthreads();
+                if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
+            }
+            if (threadIdx.x == 0)
+            {
+                if (level == 0) store_xyzz(head + 4 * (size_t)(s0 + 1 + sub * FIXUP_SUB), sum); // (every read of this sub-span is behind the barriers above)
+                else store_xyzz(buckets + 4 * (size_t)b, sum);
+            }
             __syncthreads();
-            if ((int)threadIdx.x >= off && (int)threadIdx.x < 2 * off) store_xyzz(sm + 32 * (threadIdx.x - off), sum);
-            __syncthreads();
-            if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
         }
-        if (threadIdx.x == 0) store_xyzz(buckets + 4 * (size_t)b, sum);
-        __syncthreads();
     }
 }
 
@@ -1554,8 +1594,10 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
         bbg_prof::Scope prof(bbg_prof::MSM_FIXUP, st);
         BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, acc_offsets, pl.total_buckets, S_acc, buckets,
                           (const fe*)head, (const fe*)tail, work_count, work_list);
-        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, (const fe*)head,
-                   (const fe*)tail, (const uint32_t*)work_count, (const uint32_t*)work_list);
+        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, head, (const fe*)tail,
+                   (const uint32_t*)work_count, (const uint32_t*)work_list, 0);
+        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, head, (const fe*)tail,
+                   (const uint32_t*)work_count, (const uint32_t*)work_list, 1);
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_CHUNK, st);
@@ -1580,7 +1622,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
                            pl.red_splits, red);
         }
     }
-    g_msm_launches += 9 + batch + ((tree_blocks != 0 || pl.red_splits > 1) ? 1 : 0);
+    g_msm_launches += 10 + batch + ((tree_blocks != 0 || pl.red_splits > 1) ? 1 : 0);
     BBG_CHECK(bbg_rt::last_error());
 
     // the per-window reductions travel to the ticket's pinned slot behind the kernels

@@ -120,6 +120,19 @@ def test_msm_giant_bucket_block_fixup(emu):
     assert (emu.msm(np.ascontiguousarray(sc), table) == H.closed_form_msm(np.ascontiguousarray(sc), a0, d)).all()
 
 
+def test_msm_giant_bucket_sub_spans(emu, monkeypatch):
+    """A bucket spanning more than FIXUP_SUB = 2048 slices (forced with a short slice length): the fix-up reduces it in
+    sub-spans, one block each, then adds the partial sums; the empty buckets behind it are skipped by binary search."""
+    monkeypatch.setenv("BBG_MSM_SLICE", "8")
+    n = 20000  # 20000 entries per giant bucket / 8 per slice = 2500 slices: two sub-spans
+    table, a0, d = H.generator_multiples_table(14, n)
+    sc = np.tile(H.random_scalars_mont(96, 1)[0], (n, 1))
+    assert (emu.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+    vals = H.random_scalars_mont(95, 2)
+    sc = np.ascontiguousarray(vals[np.arange(n) % 2])
+    assert (emu.msm(sc, table) == H.closed_form_msm(sc, a0, d)).all()
+
+
 def test_batched_msm_and_srs_cache(emu):
     n = 256
     table, _, _ = H.generator_multiples_table(21, n)
@@ -403,7 +416,7 @@ def test_msm_pair_sum_rounds(emu, rounds, bmax, monkeypatch):
     sc[4] = H.to_limbs(H.from_limbs(sc[4]) + H.FR_MODULUS)
     before = emu.launch_count()
     assert (emu.msm(sc, table) == H.oracle_msm(sc, table)).all()
-    assert emu.launch_count() - before == 10 + 4 + rounds  # the rounds did run
+    assert emu.launch_count() - before == 11 + 4 + rounds  # the rounds did run
     # one digit value shared by all scalars: one giant bucket per window, every other bucket empty
     same = np.tile(H.random_scalars_mont(73, 1)[0], (n, 1))
     assert (emu.msm(same, table) == H.closed_form_msm(same, a0, d)).all()
