@@ -772,10 +772,11 @@ __global__ void msm_pair_plan_kernel(const uint32_t* offsets, uint32_t total_buc
 // occur in the prover) are queued and reduced by a whole block each, so the cost of a giant bucket is
 // O(span / 128 + log 128) additions instead of O(span).
 constexpr uint32_t FIXUP_SERIAL_SPAN = 16;
+constexpr uint32_t FIXUP_SUB = 2048; // a bucket spanning more slices than this is reduced in sub-spans of that length
 constexpr int FIXUP_LARGE_GRID = 592; // 4 x 148: each block loops over queued buckets
 constexpr int FIXUP_BLOCK = 128;
 __global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets, uint32_t S, fe* buckets, const fe* head, const fe* tail,
-                                 uint32_t* work_count, uint32_t* work_list)
+                                 uint32_t* work_count, uint32_t* work_list, uint32_t* giant_list)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
@@ -787,6 +788,11 @@ __global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets
     }
     const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
     if (s0 == s1) return;
+    if (s1 - s0 > FIXUP_SUB)
+    {
+        giant_list[atomicAdd(work_count + 1, 1u)] = b; // reduced in sub-spans by many blocks (msm_fixup_giant_kernel)
+        return;
+    }
     if (s1 - s0 > FIXUP_SERIAL_SPAN)
     {
         work_list[atomicAdd(work_count, 1u)] = b;
@@ -796,20 +802,44 @@ __global__ void msm_fixup_kernel(const uint32_t* offsets, uint32_t total_buckets
     for (uint32_t s = s0 + 1; s <= s1; ++s) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
     store_xyzz(buckets + 4 * (size_t)b, sum);
 }
-// level 0: a queued bucket's heads s0 + 1 .. s1 are cut into sub-spans of FIXUP_SUB slices, one block each (a bucket of 2^20
-// entries spans ~19 000 slices: one block per BUCKET left all but a dozen SMs idle for a millisecond); the block's sum — for
-// the first sub-span including the bucket's tail slot — replaces the first head of its sub-span.  level 1: one block per
-// bucket adds those partial sums into the bucket.
-constexpr uint32_t FIXUP_SUB = 2048;
-__global__ void __launch_bounds__(FIXUP_BLOCK) msm_fixup_large_kernel(const uint32_t* offsets, uint32_t S, fe* buckets, fe* head, const fe* tail,
-                                                                      const uint32_t* work_count, const uint32_t* work_list, int level)
+__global__ void __launch_bounds__(FIXUP_BLOCK) msm_fixup_large_kernel(const uint32_t* offsets, uint32_t S, fe* buckets, const fe* head, const fe* tail,
+                                                                      const uint32_t* work_count, const uint32_t* work_list)
 {
     __shared__ uint32_t sm[FIXUP_BLOCK * 32];
     const uint32_t count = *work_count;
+    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x)
+    {
+        const uint32_t b = work_list[item];
+        const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+        const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
+        xyzz_pt sum = G1::infinity();
+        if (threadIdx.x == 0) sum = load_xyzz(tail + 4 * (size_t)s0);
+        for (uint32_t s = s0 + 1 + threadIdx.x; s <= s1; s += FIXUP_BLOCK) sum = G1::add(sum, load_xyzz(head + 4 * (size_t)s));
+        for (int off = FIXUP_BLOCK / 2; off > 0; off >>= 1)
+        {
+            __syncthreads();
+            if ((int)threadIdx.x >= off && (int)threadIdx.x < 2 * off) store_xyzz(sm + 32 * (threadIdx.x - off), sum);
+            __syncthreads();
+            if ((int)threadIdx.x < off) sum = G1::add(sum, load_xyzz(sm + 32 * threadIdx.x));
+        }
+        if (threadIdx.x == 0) store_xyzz(buckets + 4 * (size_t)b, sum);
+        __syncthreads();
+    }
+}
+// Giant buckets (spans over FIXUP_SUB slices; constant scalars: a bucket of 2^20 entries spans ~19 000 slices and one block
+// per BUCKET left all but a dozen SMs idle for a millisecond).  level 0: the heads s0 + 1 .. s1 are cut into sub-spans of
+// FIXUP_SUB slices, one block each; the block's sum — for the first sub-span including the bucket's tail slot — replaces
+// the first head of its sub-span.  level 1: one block per bucket adds those partial sums into the bucket.  The list is
+// short (a giant bucket holds > 2048 slices of the entry array), so every block walks it to find its items.
+__global__ void __launch_bounds__(FIXUP_BLOCK) msm_fixup_giant_kernel(const uint32_t* offsets, uint32_t S, fe* buckets, fe* head, const fe* tail,
+                                                                      const uint32_t* work_count, const uint32_t* giant_list, int level)
+{
+    __shared__ uint32_t sm[FIXUP_BLOCK * 32];
+    const uint32_t count = work_count[1];
     uint32_t item = 0; // running index over (bucket, sub-span) pairs at level 0, over buckets at level 1
     for (uint32_t w = 0; w < count; ++w)
     {
-        const uint32_t b = work_list[w];
+        const uint32_t b = giant_list[w];
         const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
         const uint32_t s0 = o0 / S, s1 = (o1 - 1) / S;
         const uint32_t nsub = (s1 - s0 + FIXUP_SUB - 1) / FIXUP_SUB; // heads s0 + 1 .. s1
@@ -1370,7 +1400,18 @@ Plan make_plan(size_t n, int fixed_c = 0, uint32_t entry_stride = 0)
     pl.max_entries = pl.num_points * (size_t)pl.W;
     pl.S = pick_slice(pl.max_entries);
     pl.max_slices = (pl.max_entries + pl.S - 1) / pl.S;
-    pl.chunk_log = CHUNK_LOG < pl.c - 1 ? CHUNK_LOG : pl.c - 1;
+    // buckets per running-sum thread: 8 for large bucket sets; a small MSM (a device's share of a multi-GPU commitment: 2^15
+    // buckets) has too few chunks of 8 to occupy the machine and each thread's 15 dependent additions are its whole run time:
+    // measured at 2^17 points (fixed-base, 2^15 buckets) 0.748 ms with chunks of 8, 0.701 with 4, 0.677 with 2; at 2^20 points
+    // (2^18 buckets) 2.95 / 3.05 / 3.60 ms (profiles/r02_msm_chunk_log.jsonl)
+    const size_t set_buckets = ((size_t)1 << (pl.c - 1)) * (size_t)pl.sets;
+    int chunk_log = set_buckets >= ((size_t)1 << 17) ? CHUNK_LOG : set_buckets >= ((size_t)1 << 16) ? 2 : 1;
+    if (const char* e = getenv("BBG_MSM_CHUNK_LOG")) // development
+    {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 5) chunk_log = v;
+    }
+    pl.chunk_log = chunk_log < pl.c - 1 ? chunk_log : pl.c - 1;
     pl.chunks_per_window = pl.NB >> pl.chunk_log;
     int bits = 0;
     while ((1u << bits) < pl.chunks_per_window) ++bits;
@@ -1469,6 +1510,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     const size_t o_head = carve(acc_slices * 128);
     const size_t o_tail = carve(acc_slices * 128);
     const size_t o_work_list = carve((acc_slices / FIXUP_SERIAL_SPAN + 2) * 4);
+    const size_t o_giant_list = carve((acc_slices / FIXUP_SUB + 2) * 4);
     const uint32_t total_chunks = pl.chunks_per_window * (uint32_t)pl.sets;
     const size_t o_A = carve((size_t)total_chunks * 128);
     const size_t o_V = carve((size_t)total_chunks * 128);
@@ -1521,6 +1563,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     fe* tail = (fe*)(ws + o_tail);
     uint32_t* work_count = (uint32_t*)(ws + o_work_count);
     uint32_t* work_list = (uint32_t*)(ws + o_work_list);
+    uint32_t* giant_list = (uint32_t*)(ws + o_giant_list);
     fe* A = (fe*)(ws + o_A);
     fe* V = (fe*)(ws + o_V);
     fe* red = (fe*)(ws + o_red);
@@ -1593,11 +1636,13 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
     {
         bbg_prof::Scope prof(bbg_prof::MSM_FIXUP, st);
         BBG_LAUNCH_NOSYNC(msm_fixup_kernel, dim3((pl.total_buckets + 127) / 128), dim3(128), st, acc_offsets, pl.total_buckets, S_acc, buckets,
-                          (const fe*)head, (const fe*)tail, work_count, work_list);
-        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, head, (const fe*)tail,
-                   (const uint32_t*)work_count, (const uint32_t*)work_list, 0);
-        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, head, (const fe*)tail,
-                   (const uint32_t*)work_count, (const uint32_t*)work_list, 1);
+                          (const fe*)head, (const fe*)tail, work_count, work_list, giant_list);
+        BBG_LAUNCH(msm_fixup_large_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, (const fe*)head, (const fe*)tail,
+                   (const uint32_t*)work_count, (const uint32_t*)work_list);
+        BBG_LAUNCH(msm_fixup_giant_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, head, (const fe*)tail,
+                   (const uint32_t*)work_count, (const uint32_t*)giant_list, 0);
+        BBG_LAUNCH(msm_fixup_giant_kernel, dim3(FIXUP_LARGE_GRID), dim3(FIXUP_BLOCK), 0, st, acc_offsets, S_acc, buckets, head, (const fe*)tail,
+                   (const uint32_t*)work_count, (const uint32_t*)giant_list, 1);
     }
     {
         bbg_prof::Scope prof(bbg_prof::MSM_CHUNK, st);
@@ -1622,7 +1667,7 @@ int context_launch(MsmContext& ctx, int id, int workspace, const void* const* d_
                            pl.red_splits, red);
         }
     }
-    g_msm_launches += 10 + batch + ((tree_blocks != 0 || pl.red_splits > 1) ? 1 : 0);
+    g_msm_launches += 11 + batch + ((tree_blocks != 0 || pl.red_splits > 1) ? 1 : 0);
     BBG_CHECK(bbg_rt::last_error());
 
     // the per-window reductions travel to the ticket's pinned slot behind the kernels
