@@ -290,14 +290,6 @@ int bbg_init(int device)
     if (e != cudaSuccess || count == 0) return BBG_E_NO_DEVICE;
     if (device < 0 || device >= count) return BBG_E_BAD_ARGUMENT;
     BBG_CHECK(cudaSetDevice(device));
-    if (const char* gran = getenv("BBG_L2_FETCH_GRANULARITY")) // development: 32 / 64 / 128 bytes fetched per L2 miss (a hint to the driver)
-    {
-        size_t before = 0, after = 0;
-        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gran));
-        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-        fprintf(stderr, "bbgpu: L2 fetch granularity %zu -> %zu\n", before, after);
-    }
     if (g_stream == nullptr)
     {
         BBG_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
